@@ -1,0 +1,111 @@
+/* obca_b200.h - C-ABI of the B200-native batched OBCA-MPC solver.
+ *
+ * The reference (tg623623nana/Vehicle_Motion_Planning_with_Obstacles_Avoidance_using_MPC) has no FFI of
+ * its own: its de-facto boundary is the Python method call  self.obca_solver.<method>(...)  on
+ * `class obca` (src/obca.py:10, constructed at src/closed_loop.py:22).  Each entry point below replaces
+ * the CasADi/IPOPT work behind those methods:
+ *
+ *   obca_b200_solve  mode 0  FREE          obca.obca_mpc4   src/obca.py:828-1071  (closed_loop.py:118,382)
+ *                    mode 1  FIXED_SET     obca.obca_mpc6   src/obca.py:1361-1562 (closed_loop.py:131,269,389)
+ *                    mode 2  FIXED_NOTERM  obca.obca_mpc8   src/obca.py:1564-1758 (closed_loop.py:137,275,395)
+ *                    mode 3  FREE_STACKED  obca.obca2 fixtime=0  src/obca.py:338-629 (closed_loop.py:170,263)
+ *                    mode 4  FIXED_OBCA2   obca.obca2 fixtime=1  (terminal set optional, obca.py:518-521)
+ *
+ * One call solves `batch` independent NLPs (one warp each).  All arrays are float64, C-contiguous,
+ * batch-major; the caller owns every buffer, the library owns only the context.  Functions return 0 on
+ * success and a negative code on argument / CUDA errors (obca_b200_strerror); they never throw and never
+ * exit.  The per-instance solver outcome is in `status` (>= 0  <=>  the reference's feas == True).
+ * There is no host fallback: without a CUDA device obca_b200_create fails with OBCA_E_NODEVICE.
+ */
+#ifndef OBCA_B200_H
+#define OBCA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBCA_B200_ABI_VERSION 1
+
+enum { OBCA_MODE_FREE = 0, OBCA_MODE_FIXED_SET = 1, OBCA_MODE_FIXED_NOTERM = 2, OBCA_MODE_FREE_STACKED = 3,
+       OBCA_MODE_FIXED_OBCA2 = 4 };
+/* start point: 0 = the reference's (every Opti variable 0, Topt = 1: obca.py:856), 1 = poses from xref,
+ * 2 = A* warm start (poses from xref, T from arc length, inputs by differences, duals from the most
+ * separating face) */
+enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
+/* per-instance status */
+enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,
+       OBCA_ST_LSFAIL = -4, OBCA_ST_STALL = -5 };
+/* return codes */
+enum { OBCA_OK = 0, OBCA_E_ARG = -1, OBCA_E_NODEVICE = -2, OBCA_E_CUDA = -3, OBCA_E_NOMEM = -4, OBCA_E_SIZE = -5 };
+
+#define OBCA_MAX_STAGES 32   /* N + 1 <= 32: one lane per stage */
+#define OBCA_MAX_OBS    12
+#define OBCA_MAX_ROWS   48   /* sum of edges per time step */
+
+typedef struct {
+  int32_t mode;            /* OBCA_MODE_*                                                              */
+  int32_t N;               /* horizon (N + 1 <= OBCA_MAX_STAGES)                                       */
+  int32_t n_obs;           /* obstacles per time step                                                  */
+  int32_t rows;            /* R = sum_i (vObs[i] - 1) half-space rows per time step                    */
+  int32_t init;            /* OBCA_INIT_*                                                              */
+  int32_t max_iter;        /* 3000 (mpc4, IPOPT default) / 1000 (mpc6/8: obca.py:1538)                 */
+  int32_t has_term;        /* terminal set present (always for FIXED_SET)                              */
+  int32_t acceptable_iter; /* 15 (IPOPT default)                                                       */
+  double  Ts, dmin, ego[4];
+  double  Q[9], P[9], R1[4], R2[4];
+  double  xL[2], xU[2], uL[2], uU[2];
+  double  acc_max[2];      /* {0.6, pi/6}  (obca.py:932-933)                                           */
+  double  time_cost[2];    /* {10, 1}      (obca.py:888)                                               */
+  double  T_min;           /* 1e-4         (obca.py:963)                                               */
+  double  tol;             /* 1e-8  (IPOPT default)                                                    */
+  double  acceptable_tol;  /* 1e-6 default; 1e-8 for mpc6/8 (obca.py:1538-1539)                        */
+  double  mu_init;         /* initial barrier parameter                                                */
+  double  bound_push;      /* slacks start at max(d(x0), bound_push)                                   */
+} obca_params;
+
+typedef struct obca_ctx obca_ctx;   /* opaque: device copies of params / obstacle rows + scratch */
+
+int  obca_b200_abi_version(void);
+/* device < 0 => current device.  max_batch sizes the per-instance scratch. */
+int  obca_b200_create (obca_ctx** out, int device, int max_batch, const obca_params* p);
+int  obca_b200_destroy(obca_ctx* ctx);
+/* bytes of device scratch held by the context (for memory budgeting) */
+int64_t obca_b200_scratch_bytes(const obca_ctx* ctx);
+
+/* All pointers are DEVICE pointers except edge_ptr (host).  Asynchronous on cuda_stream.
+ *   x0 [B,3]  u0 [B,2]  xref [B,N+1,3]  uref [B,N,2] or NULL
+ *   T_max [B] (free modes; obca.py:961-962) or NULL    term [B,3] = {xmin, ymin, ymax} (terminal set) or NULL
+ *   edge_ptr [n_obs+1] prefix sum of (vObs-1), shared by the batch
+ *   A [Bo,rows,2]  b0 [Bo,rows]  db [Bo,rows] or NULL (b_k = b0 + k*db; mode FREE ignores db: obca.py:969)
+ *   obstacles_shared != 0 => Bo = 1 (one scene broadcast to the batch), else Bo = B
+ * outputs
+ *   x [B,N+1,3]  u [B,N,2]  lam [B,N+1,rows]  mu [B,N+1,4*n_obs]  T [B] (time scale; 1 in fixed modes)
+ *   obj [B]  status [B]  iters [B]                                                                     */
+int  obca_b200_solve  (obca_ctx* ctx, int batch,
+                       const double* x0, const double* u0, const double* xref, const double* uref,
+                       const double* T_max, const double* term,
+                       const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
+                       int obstacles_shared,
+                       double* x, double* u, double* lam, double* mu, double* T, double* obj,
+                       int32_t* status, int32_t* iters, void* cuda_stream);
+/* Same call with HOST pointers: stages inputs to the device, solves, copies the results back and
+ * synchronises.  This is what the single-problem Python methods (obca.obca_mpc4 ...) use. */
+int  obca_b200_solve_host(obca_ctx* ctx, int batch,
+                       const double* x0, const double* u0, const double* xref, const double* uref,
+                       const double* T_max, const double* term,
+                       const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
+                       int obstacles_shared,
+                       double* x, double* u, double* lam, double* mu, double* T, double* obj,
+                       int32_t* status, int32_t* iters);
+/* kernel launches issued by this context so far (bench.py's gpu_launches) */
+int64_t obca_b200_launch_count(const obca_ctx* ctx);
+/* elapsed device time (ms) of the last solve's kernel, measured with CUDA events on its stream;
+ * valid after the stream was synchronised */
+float obca_b200_last_kernel_ms(obca_ctx* ctx);
+const char* obca_b200_strerror(int rc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -30,7 +30,7 @@ DEFAULT_OPTS = dict(tol=1e-8, max_iter=3000, mu_init=10.0, kappa_eps=10.0, kappa
                     tau_min=0.99, bound_push=0.1, s_max=100.0, kappa_sigma=1e10,
                     dw_first=1e-4, dw_min=1e-20, dw_max=1e20, kw_plus_first=100.0, kw_plus=8.0, kw_minus=1.0 / 3.0,
                     dc_min=1e-8, lm_cap=1e4, acceptable_tol=1e-6, acceptable_iter=15, filt_max=32,
-                    stall_alpha=1e-3, stall_iters=10,
+                    stall_alpha=1e-3, stall_iters=10, sig_min=1e-8,
                     init="warm", verbose=False, soc=True, dbg=False)
 
 # status codes (shared with oracle/obca_oracle.c and the CUDA kernel)
@@ -81,6 +81,7 @@ def solve(p: nlp.Problem, opts=None):
     n, m, q = lay.n, lay.m, lay.q
     res = dict(status=-1, iters=0, lay=lay)
     Mw = np.zeros(n); Mw[:lay.ntraj] = 1.0
+    sign_rows, sign_cols = nlp.sign_rows(p, lay)
 
     X = nlp.start_point(p, lay, o["init"])
     ev = nlp.evaluate(p, lay, X, want=("c", "d"))
@@ -149,6 +150,8 @@ def solve(p: nlp.Problem, opts=None):
         rd = d - S
         rhs_x = -(gr + Jm.T @ y - Jd.T @ (mu / S - Sig * rd))
         H0 = W + Jd.T @ (Sig[:, None] * Jd)
+        # primal regularisation of the OBCA duals: curvature of a sign row is max(Z/S, sig_min)
+        H0[sign_cols, sign_cols] += np.maximum(o["sig_min"] - Sig[sign_rows], 0.0)
         # terminal-equality regularisation (Levenberg-Marquardt: keeps the terminal multiplier step bounded
         # when the linearised dynamics cannot reach the terminal pose, e.g. theta = v = 0)
         Mc = np.zeros(m)

@@ -452,6 +452,17 @@ def evaluate(p: Problem, lay: Layout, X, y=None, zi=None, want=("f", "g", "c", "
     return out
 
 
+def sign_rows(p: Problem, lay: Layout):
+    """(inequality rows, variable columns) of the sign constraints lambda >= 0, mu >= 0."""
+    rows, cols = [], []
+    for k in range(p.N + 1):
+        for i in range(p.nobs):
+            E = int(p.edges[i])
+            rows += list(range(lay.g_w[k, i], lay.g_w[k, i] + E + 4))
+            cols += list(range(lay.lam[k, i], lay.lam[k, i] + E)) + list(range(lay.mu[k, i], lay.mu[k, i] + 4))
+    return np.asarray(rows, int), np.asarray(cols, int)
+
+
 def unpack(p: Problem, lay: Layout, X):
     """-> x (3,N+1), u (2,N), T, lam (N+1,R), mu (N+1,4*nobs)"""
     N = p.N

@@ -1,0 +1,1088 @@
+/* ORACLE (test infrastructure, not product code): scalar C restatement of the OBCA-MPC NLP solve.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may build, load
+ * or call this file.  The product path (csrc/ *.cu) never does.
+ *
+ * PARITY UNPINNED: the reference hands these NLPs to CasADi Opti + IPOPT (third party, unpinned, absent
+ * here: SURVEY.md 8(c)) and ships no tests or golden outputs.  This file restates the PROBLEM from
+ * /root/reference/src/obca.py line by line (same citations as oracle/obca_nlp.py):
+ *   variables 842-856, cost 859-897 (fixed 1385-1414), dynamics 902-911, bounds 916-923, accel 928-939,
+ *   init/terminal 944/951, duals >= 0 and T bounds 956-963, obstacle rows 968-1042 (mpc4: first time block
+ *   only, 969; mpc6/8/obca2: advance through the time stack, 1482/1677/538), terminal set 1465-1466.
+ * The SOLVER is the primal-dual interior-point method specified by oracle/ipm_dense.py (dense NumPy),
+ * here with structure-exploiting linear algebra: per (stage, obstacle) dual block eliminated through a
+ * 5x5 SPD system (diagonal + low rank), then a Riccati recursion over the augmented stage state
+ * (x, y, theta, v_prev, w_prev, T).  tests/test_oracle.py checks it against ipm_dense.py.
+ *
+ * Plain sequential loops, one instance at a time (pthreads over instances for the CPU baseline).
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/obca_b200.h"
+
+#define NS OBCA_MAX_STAGES
+#define RM OBCA_MAX_ROWS
+#define OM OBCA_MAX_OBS
+#define FILT_MAX 32
+
+typedef struct {
+  const obca_params* P;
+  int N, nobs, R, free_, has_term, stacked;
+  int eptr[OM + 1];
+  double Ts, Tmax, dmin, off, g[4];
+  double x0[3], u0[2], term[3];
+  const double *xref, *uref, *A, *b0, *db;
+} prob_t;
+
+/* iterate: primal X, slacks S, multipliers y (eq) and Z (ineq) */
+typedef struct {
+  double z[NS][3], u[NS][2], T;
+  double lam[NS][RM], mu[NS][4 * OM];
+  double yd[NS][3], yt[3], ye[NS][2 * OM];
+  /* inequality blocks: xy (k>=1) [x-xL,y-yL,xU-x,yU-y]; ub (k<N) [u-uL(2),uU-u(2),acc+amax(2),amax-acc(2)];
+   * Tb [T-Tmin,Tmax-T]; tm [xN-ts0,yN-ts1,ts2-yN]; per (k,i): lam rows, mu rows, norm, dist */
+  double Sxy[NS][4], Sub[NS][8], STb[2], Stm[3], Sl[NS][RM], Sm[NS][4 * OM], Sn[NS][OM], Sd[NS][OM];
+  double Zxy[NS][4], Zub[NS][8], ZTb[2], Ztm[3], Zl[NS][RM], Zm[NS][4 * OM], Zn[NS][OM], Zd[NS][OM];
+} iter_t;
+
+/* constraint values at a point */
+typedef struct {
+  double f;
+  double cd[NS][3], ct[3], ce[NS][2 * OM];
+  double dxy[NS][4], dub[NS][8], dTb[2], dtm[3], dn[NS][OM], dd[NS][OM]; /* d for lam/mu rows = the variable */
+} vals_t;
+
+typedef struct {
+  double thmax, thmin;
+  int n, wr, active;
+  double th[FILT_MAX], ph[FILT_MAX];
+} filt_t;
+
+static double bk(const prob_t* p, int k, int r) { return p->b0[r] + ((p->stacked && p->db) ? k * p->db[r] : 0.0); }
+
+/* ------------------------------------------------------------------------------------------------
+ * values: objective f, equality residuals c, inequality values d at (z,u,T,lam,mu)
+ * ---------------------------------------------------------------------------------------------- */
+static void eval_values(const prob_t* p, const iter_t* it, vals_t* v) {
+  const obca_params* P = p->P;
+  int N = p->N;
+  double T = p->free_ ? it->T : 1.0, h = T * p->Ts;
+  double f = 0.0;
+  for (int k = 0; k <= N; ++k) {
+    const double* z = it->z[k];
+    const double* M = (k < N) ? P->Q : P->P;
+    double e[3];
+    for (int j = 0; j < 3; ++j) e[j] = z[j] - p->xref[3 * k + j];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) f += e[a] * M[3 * a + b] * e[b];
+    if (k < N) {
+      double uu[2] = {it->u[k][0], it->u[k][1]};
+      if (p->uref) { uu[0] -= p->uref[2 * k]; uu[1] -= p->uref[2 * k + 1]; }
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b) f += uu[a] * P->R1[2 * a + b] * uu[b];
+      if (k >= 1) { /* (u_k - u_{k-1})^T R2 (..)/h^2, k = 1..N-1; the t == 0 term is identically 0 (Q4) */
+        double du[2] = {it->u[k][0] - it->u[k - 1][0], it->u[k][1] - it->u[k - 1][1]};
+        double s = 0;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) s += du[a] * P->R2[2 * a + b] * du[b];
+        f += s / (h * h);
+      }
+      double ct = cos(z[2]), st = sin(z[2]);
+      v->cd[k][0] = z[0] + h * it->u[k][0] * ct - it->z[k + 1][0];
+      v->cd[k][1] = z[1] + h * it->u[k][0] * st - it->z[k + 1][1];
+      v->cd[k][2] = z[2] + h * it->u[k][1] - it->z[k + 1][2];
+      const double* up = (k == 0) ? p->u0 : it->u[k - 1];
+      for (int j = 0; j < 2; ++j) {
+        double ga = (up[j] - it->u[k][j]) / h;
+        v->dub[k][j] = it->u[k][j] - P->uL[j];
+        v->dub[k][2 + j] = P->uU[j] - it->u[k][j];
+        v->dub[k][4 + j] = ga + P->acc_max[j];
+        v->dub[k][6 + j] = P->acc_max[j] - ga;
+      }
+    }
+    if (k >= 1)
+      for (int j = 0; j < 2; ++j) {
+        v->dxy[k][j] = z[j] - P->xL[j];
+        v->dxy[k][2 + j] = P->xU[j] - z[j];
+      }
+    double ct = cos(z[2]), st = sin(z[2]);
+    double tx = z[0] + p->off * ct, ty = z[1] + p->off * st;
+    for (int i = 0; i < p->nobs; ++i) {
+      double a1 = 0, a2 = 0, bl = 0;
+      for (int r = p->eptr[i]; r < p->eptr[i + 1]; ++r) {
+        a1 += p->A[2 * r] * it->lam[k][r];
+        a2 += p->A[2 * r + 1] * it->lam[k][r];
+        bl += bk(p, k, r) * it->lam[k][r];
+      }
+      const double* m = &it->mu[k][4 * i];
+      v->ce[k][2 * i] = m[0] - m[2] + ct * a1 + st * a2;
+      v->ce[k][2 * i + 1] = m[1] - m[3] - st * a1 + ct * a2;
+      v->dn[k][i] = 1.0 - a1 * a1 - a2 * a2;
+      v->dd[k][i] = -(p->g[0] * m[0] + p->g[1] * m[1] + p->g[2] * m[2] + p->g[3] * m[3]) + tx * a1 + ty * a2 - bl - p->dmin;
+    }
+  }
+  if (p->free_) {
+    f += (N + 1) * (P->time_cost[0] * T + P->time_cost[1] * T * T);
+    for (int j = 0; j < 3; ++j) v->ct[j] = it->z[N][j] - p->xref[3 * N + j];
+    v->dTb[0] = T - P->T_min;
+    v->dTb[1] = p->Tmax - T;
+  }
+  if (p->has_term) {
+    v->dtm[0] = it->z[N][0] - p->term[0];
+    v->dtm[1] = it->z[N][1] - p->term[1];
+    v->dtm[2] = p->term[2] - it->z[N][1];
+  }
+  v->f = f;
+}
+
+/* visit every inequality: fn(ctx, d, &S, &Z) */
+#define FOR_INEQ(p, it, v, BODY)                                                                   \
+  do {                                                                                             \
+    int N_ = (p)->N;                                                                               \
+    for (int k = 0; k <= N_; ++k) {                                                                \
+      if (k >= 1) for (int j = 0; j < 4; ++j) { double d_ = (v)->dxy[k][j]; double* S_ = &(it)->Sxy[k][j]; double* Z_ = &(it)->Zxy[k][j]; BODY } \
+      if (k < N_) for (int j = 0; j < 8; ++j) { double d_ = (v)->dub[k][j]; double* S_ = &(it)->Sub[k][j]; double* Z_ = &(it)->Zub[k][j]; BODY } \
+      for (int r = 0; r < (p)->R; ++r) { double d_ = (it)->lam[k][r]; double* S_ = &(it)->Sl[k][r]; double* Z_ = &(it)->Zl[k][r]; BODY } \
+      for (int r = 0; r < 4 * (p)->nobs; ++r) { double d_ = (it)->mu[k][r]; double* S_ = &(it)->Sm[k][r]; double* Z_ = &(it)->Zm[k][r]; BODY } \
+      for (int i = 0; i < (p)->nobs; ++i) { double d_ = (v)->dn[k][i]; double* S_ = &(it)->Sn[k][i]; double* Z_ = &(it)->Zn[k][i]; BODY } \
+      for (int i = 0; i < (p)->nobs; ++i) { double d_ = (v)->dd[k][i]; double* S_ = &(it)->Sd[k][i]; double* Z_ = &(it)->Zd[k][i]; BODY } \
+    }                                                                                              \
+    if ((p)->free_) for (int j = 0; j < 2; ++j) { double d_ = (v)->dTb[j]; double* S_ = &(it)->STb[j]; double* Z_ = &(it)->ZTb[j]; BODY } \
+    if ((p)->has_term) for (int j = 0; j < 3; ++j) { double d_ = (v)->dtm[j]; double* S_ = &(it)->Stm[j]; double* Z_ = &(it)->Ztm[j]; BODY } \
+  } while (0)
+
+static void theta_phi(const prob_t* p, const iter_t* it, const vals_t* v, double mu, double* th, double* ph,
+                      double* cmax) {
+  double t = 0, lg = 0, cm = 0;
+  int N = p->N;
+  for (int k = 0; k <= N; ++k) {
+    if (k < N) for (int j = 0; j < 3; ++j) { t += fabs(v->cd[k][j]); cm = fmax(cm, fabs(v->cd[k][j])); }
+    for (int j = 0; j < 2 * p->nobs; ++j) { t += fabs(v->ce[k][j]); cm = fmax(cm, fabs(v->ce[k][j])); }
+  }
+  if (p->free_) for (int j = 0; j < 3; ++j) { t += fabs(v->ct[j]); cm = fmax(cm, fabs(v->ct[j])); }
+  iter_t* itm = (iter_t*)it;
+  FOR_INEQ(p, itm, v, { (void)Z_; t += fabs(d_ - *S_); cm = fmax(cm, fabs(d_ - *S_)); lg += log(*S_); });
+  *th = t;
+  *ph = v->f - mu * lg;
+  if (cmax) *cmax = cm;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * start point (oracle/obca_nlp.py start_point)
+ * ---------------------------------------------------------------------------------------------- */
+static void start_point(const prob_t* p, iter_t* it) {
+  const obca_params* P = p->P;
+  int N = p->N, init = P->init;
+  memset(it, 0, sizeof(*it));
+  for (int j = 0; j < 3; ++j) it->z[0][j] = p->x0[j];
+  it->T = 1.0;
+  if (init >= OBCA_INIT_XREF)
+    for (int k = 1; k <= N; ++k)
+      for (int j = 0; j < 3; ++j) it->z[k][j] = p->xref[3 * k + j];
+  if (init == OBCA_INIT_WARM) {
+    double Pp[NS][3];
+    for (int j = 0; j < 3; ++j) Pp[0][j] = p->x0[j];
+    for (int k = 1; k <= N; ++k)
+      for (int j = 0; j < 3; ++j) Pp[k][j] = p->xref[3 * k + j];
+    double len = 0;
+    for (int k = 0; k < N; ++k) len += sqrt(pow(Pp[k + 1][0] - Pp[k][0], 2) + pow(Pp[k + 1][1] - Pp[k][1], 2));
+    double h = p->Ts;
+    if (p->free_) {
+      double T0 = len / (N * P->uU[0] * p->Ts);
+      T0 = fmin(fmax(T0, 1.0), fmax(p->Tmax, P->T_min));
+      it->T = T0;
+      h = T0 * p->Ts;
+    }
+    for (int k = 0; k < N; ++k) {
+      double dth = Pp[k + 1][2] - Pp[k][2];
+      dth = dth + M_PI;
+      dth = dth - 2 * M_PI * floor(dth / (2 * M_PI)) - M_PI;
+      double fwd = cos(Pp[k][2]) * (Pp[k + 1][0] - Pp[k][0]) + sin(Pp[k][2]) * (Pp[k + 1][1] - Pp[k][1]);
+      it->u[k][0] = fmin(fmax(fwd / h, P->uL[0]), P->uU[0]);
+      it->u[k][1] = fmin(fmax(dth / h, P->uL[1]), P->uU[1]);
+    }
+    for (int k = 0; k <= N; ++k) {
+      double ct = cos(Pp[k][2]), st = sin(Pp[k][2]);
+      double tx = Pp[k][0] + p->off * ct, ty = Pp[k][1] + p->off * st;
+      for (int i = 0; i < p->nobs; ++i) {
+        int jb = -1;
+        double best = -1e300, nb = 1;
+        for (int r = p->eptr[i]; r < p->eptr[i + 1]; ++r) {
+          double nr = sqrt(p->A[2 * r] * p->A[2 * r] + p->A[2 * r + 1] * p->A[2 * r + 1]);
+          double sep = (p->A[2 * r] * tx + p->A[2 * r + 1] * ty - bk(p, k, r)) / nr;
+          if (sep > best) { best = sep; jb = r; nb = nr; }
+        }
+        if (jb < 0) continue;
+        double l = 0.9 / nb;
+        it->lam[k][jb] = l;
+        double a1 = p->A[2 * jb] * l, a2 = p->A[2 * jb + 1] * l;
+        double r1 = -(ct * a1 + st * a2), r2 = -(-st * a1 + ct * a2);
+        double* m = &it->mu[k][4 * i];
+        m[0] = fmax(r1, 0); m[1] = fmax(r2, 0); m[2] = fmax(-r1, 0); m[3] = fmax(-r2, 0);
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * per (stage, obstacle) dual block.  Rows j = lambda rows then the 4 mu rows; every row has a sign
+ * constraint with slack (D_j = Z_j/S_j).  H_ww = D + U C3 U^T with U = [alpha0 alpha1 q];
+ * Y = [U je1 je2];  M = Y^T D^-1 Y + blockdiag(C3^-1, 0)  is 5x5 SPD.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double M0[5][5], g0[5], L[5][5]; /* L: Cholesky factor of M */
+  double a1, a2, ct, st, tx, ty;
+  double h0[5], hc[3][3], jt[2];   /* rhs in Y basis; pose columns (x,y,theta) in U basis; Je_p[:,theta] */
+  double zeta[4][5];               /* M^-1 rho for columns (0, x, y, theta) */
+  double dpose[3];                 /* grad of dist wrt pose */
+} blk_t;
+
+static void row_y(const prob_t* p, const blk_t* b, int k, int i, int j, int E, double yv[5]) {
+  if (j < E) {
+    int r = p->eptr[i] + j;
+    double A0 = p->A[2 * r], A1 = p->A[2 * r + 1];
+    yv[0] = A0; yv[1] = A1;
+    yv[2] = b->tx * A0 + b->ty * A1 - bk(p, k, r);
+    yv[3] = b->ct * A0 + b->st * A1;
+    yv[4] = -b->st * A0 + b->ct * A1;
+  } else {
+    int m = j - E;
+    yv[0] = 0; yv[1] = 0; yv[2] = -p->g[m];
+    yv[3] = (m == 0) ? 1.0 : (m == 2) ? -1.0 : 0.0;
+    yv[4] = (m == 1) ? 1.0 : (m == 3) ? -1.0 : 0.0;
+  }
+}
+
+/* pivots are floored at CHOL_FLOOR * (largest diagonal entry): a vanishing dual regularisation that only
+ * acts when rounding in the Gram matrix swamps a direction (extreme Z/S ratios near convergence) */
+#define CHOL_FLOOR 1e-14
+#define SIG_MIN 1e-8 /* primal regularisation of the OBCA duals: curvature of a sign row is max(Z/S, SIG_MIN) */
+static int chol5(double M[5][5], double L[5][5]) {
+  double dmax = 0;
+  for (int i = 0; i < 5; ++i) dmax = fmax(dmax, M[i][i]);
+  if (!(dmax > 0) || !isfinite(dmax)) return -1;
+  double flo = CHOL_FLOOR * dmax;
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = M[i][j];
+      for (int q = 0; q < j; ++q) s -= L[i][q] * L[j][q];
+      if (i == j) {
+        if (!(s > flo)) s = flo;
+        L[i][i] = sqrt(s);
+      } else
+        L[i][j] = s / L[j][j];
+    }
+  return 0;
+}
+static void chol5_solve(double L[5][5], const double* r, double* x) {
+  double t[5];
+  for (int i = 0; i < 5; ++i) {
+    double s = r[i];
+    for (int q = 0; q < i; ++q) s -= L[i][q] * t[q];
+    t[i] = s / L[i][i];
+  }
+  for (int i = 4; i >= 0; --i) {
+    double s = t[i];
+    for (int q = i + 1; q < 5; ++q) s -= L[q][i] * x[q];
+    x[i] = s / L[i][i];
+  }
+}
+
+/* builds the block factorisation; if Hp/rp != NULL adds this block's Schur complement to the pose
+ * Hessian (3x3) and reduced gradient (3) */
+static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, blk_t* b,
+                       double Hp[3][3], double rp[3]) {
+  int E = p->eptr[i + 1] - p->eptr[i], r0 = p->eptr[i];
+  const double* z = it->z[k];
+  b->ct = cos(z[2]); b->st = sin(z[2]);
+  b->tx = z[0] + p->off * b->ct; b->ty = z[1] + p->off * b->st;
+  double a1 = 0, a2 = 0;
+  for (int r = r0; r < r0 + E; ++r) { a1 += p->A[2 * r] * it->lam[k][r]; a2 += p->A[2 * r + 1] * it->lam[k][r]; }
+  b->a1 = a1; b->a2 = a2;
+  memset(b->M0, 0, sizeof(b->M0)); memset(b->g0, 0, sizeof(b->g0));
+  for (int j = 0; j < E + 4; ++j) {
+    double w, S, Z;
+    if (j < E) { w = it->lam[k][r0 + j]; S = it->Sl[k][r0 + j]; Z = it->Zl[k][r0 + j]; }
+    else { w = it->mu[k][4 * i + j - E]; S = it->Sm[k][4 * i + j - E]; Z = it->Zm[k][4 * i + j - E]; }
+    double sig = Z / S, t = mu / S - sig * (w - S), yv[5];
+    row_y(p, b, k, i, j, E, yv);
+    double di = 1.0 / fmax(sig, SIG_MIN);
+    for (int a = 0; a < 5; ++a) {
+      b->g0[a] += yv[a] * t * di;
+      for (int c = 0; c <= a; ++c) b->M0[a][c] += yv[a] * yv[c] * di;
+    }
+  }
+  for (int a = 0; a < 5; ++a)
+    for (int c = a + 1; c < 5; ++c) b->M0[a][c] = b->M0[c][a];
+  double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
+  double sn = Zn / Sn, sd = Zd / Sd;
+  double tn = mu / Sn - sn * (v->dn[k][i] - Sn), td = mu / Sd - sd * (v->dd[k][i] - Sd);
+  /* Cn = 2 Zn I + 4 sn a a^T ;  C3^-1 = blockdiag(Cn^-1, 1/sd) */
+  double c00 = 2 * Zn + 4 * sn * a1 * a1, c01 = 4 * sn * a1 * a2, c11 = 2 * Zn + 4 * sn * a2 * a2;
+  double det = c00 * c11 - c01 * c01;
+  double M[5][5];
+  memcpy(M, b->M0, sizeof(M));
+  M[0][0] += c11 / det; M[1][1] += c00 / det; M[0][1] -= c01 / det; M[1][0] -= c01 / det;
+  M[2][2] += 1.0 / sd;
+  if (chol5(M, b->L)) return -1;
+  /* the dist row stays in augmented form (its own unknown tau_d with -1/sd on the diagonal, coupled to the
+   * pose through grad_pose dist) so nothing of size sd = Zd/Sd enters a difference */
+  double tds = mu / Zd - (v->dd[k][i] - Sd); /* = td / sd */
+  b->h0[0] = -2 * tn * a1; b->h0[1] = -2 * tn * a2; b->h0[2] = 0; b->h0[3] = 0; b->h0[4] = 0;
+  double rho[5];
+  for (int a = 0; a < 5; ++a) rho[a] = b->g0[a] + b->M0[a][0] * b->h0[0] + b->M0[a][1] * b->h0[1];
+  rho[2] -= tds; rho[3] += v->ce[k][2 * i]; rho[4] += v->ce[k][2 * i + 1];
+  chol5_solve(b->L, rho, b->zeta[0]);
+  double offt = p->off * (-b->st * a1 + b->ct * a2);
+  b->dpose[0] = a1; b->dpose[1] = a2; b->dpose[2] = offt;
+  if (k == 0) return 0; /* pose fixed */
+  double y1 = it->ye[k][2 * i], y2 = it->ye[k][2 * i + 1], yd = -Zd;
+  double c1 = y1 + yd * p->off;
+  /* H_wp columns (x, y, theta) in the (alpha0, alpha1) basis: W cross terms only */
+  b->hc[0][0] = yd; b->hc[0][1] = 0; b->hc[0][2] = 0;
+  b->hc[1][0] = 0; b->hc[1][1] = yd; b->hc[1][2] = 0;
+  b->hc[2][0] = -c1 * b->st - y2 * b->ct; b->hc[2][1] = c1 * b->ct - y2 * b->st; b->hc[2][2] = 0;
+  b->jt[0] = -b->st * a1 + b->ct * a2; b->jt[1] = -b->ct * a1 - b->st * a2;
+  double rhoc[3][5];
+  for (int c = 0; c < 3; ++c) {
+    for (int a = 0; a < 5; ++a) rhoc[c][a] = -(b->M0[a][0] * b->hc[c][0] + b->M0[a][1] * b->hc[c][1]);
+    rhoc[c][2] += b->dpose[c];
+    if (c == 2) { rhoc[c][3] += b->jt[0]; rhoc[c][4] += b->jt[1]; }
+    chol5_solve(b->L, rhoc[c], b->zeta[1 + c]);
+  }
+  if (Hp) {
+    /* own pose term of this block: W (theta,theta) */
+    Hp[2][2] += y1 * (-b->ct * a1 - b->st * a2) + y2 * (b->st * a1 - b->ct * a2) + yd * p->off * (-b->ct * a1 - b->st * a2);
+    /* Schur complement: Gamma(c',c) = h^c'^T M0[0:2,0:2] h^c - rho^c'^T zeta^c */
+    for (int cp = 0; cp < 3; ++cp) {
+      for (int c = 0; c < 3; ++c) {
+        double G = 0;
+        for (int a = 0; a < 2; ++a)
+          for (int q = 0; q < 2; ++q) G += b->hc[cp][a] * b->M0[a][q] * b->hc[c][q];
+        for (int a = 0; a < 5; ++a) G -= rhoc[cp][a] * b->zeta[1 + c][a];
+        Hp[cp][c] -= G;
+      }
+      double G0 = 0;
+      for (int a = 0; a < 2; ++a) G0 -= b->hc[cp][a] * (b->g0[a] + b->M0[a][0] * b->h0[0] + b->M0[a][1] * b->h0[1]);
+      for (int a = 0; a < 5; ++a) G0 -= rhoc[cp][a] * b->zeta[0][a];
+      rp[cp] += G0;
+    }
+  }
+  (void)td;
+  return 0;
+}
+
+/* search direction */
+typedef struct {
+  double z[NS][3], u[NS][2], T;
+  double lam[NS][RM], mu[NS][4 * OM];
+  double yd[NS][3], yt[3], ye[NS][2 * OM]; /* NEW multipliers y+ (the step is y+ - y) */
+  double Sxy[NS][4], Sub[NS][8], STb[2], Stm[3], Sl[NS][RM], Sm[NS][4 * OM], Sn[NS][OM], Sd[NS][OM];
+} dir_t;
+
+static void block_backsub(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, const blk_t* b,
+                          const double dp[3], dir_t* d) {
+  int E = p->eptr[i + 1] - p->eptr[i], r0 = p->eptr[i];
+  double zt[5], ht[5];
+  for (int a = 0; a < 5; ++a) {
+    zt[a] = b->zeta[0][a];
+    ht[a] = b->h0[a];
+  }
+  if (k >= 1)
+    for (int c = 0; c < 3; ++c) {
+      for (int a = 0; a < 5; ++a) zt[a] += b->zeta[1 + c][a] * dp[c];
+      for (int a = 0; a < 3; ++a) ht[a] -= b->hc[c][a] * dp[c];
+    }
+  double da1 = 0, da2 = 0, qdw = 0;
+  for (int j = 0; j < E + 4; ++j) {
+    double w, S, Z;
+    if (j < E) { w = it->lam[k][r0 + j]; S = it->Sl[k][r0 + j]; Z = it->Zl[k][r0 + j]; }
+    else { w = it->mu[k][4 * i + j - E]; S = it->Sm[k][4 * i + j - E]; Z = it->Zm[k][4 * i + j - E]; }
+    double sig = Z / S, t = mu / S - sig * (w - S), yv[5];
+    row_y(p, b, k, i, j, E, yv);
+    double s = t;
+    for (int a = 0; a < 5; ++a) s += yv[a] * (ht[a] - zt[a]);
+    double dw = s / fmax(sig, SIG_MIN);
+    if (j < E) {
+      d->lam[k][r0 + j] = dw; d->Sl[k][r0 + j] = dw + (w - S);
+      da1 += yv[0] * dw; da2 += yv[1] * dw;
+    } else {
+      d->mu[k][4 * i + j - E] = dw; d->Sm[k][4 * i + j - E] = dw + (w - S);
+    }
+    qdw += yv[2] * dw;
+  }
+  d->ye[k][2 * i] = zt[3]; d->ye[k][2 * i + 1] = zt[4];
+  /* Rows kept in augmented form (norm, dist): when the row is active (sigma = Z/S >= 1) its new multiplier
+   * comes from the solve (tau) and the slack step from the linearised complementarity, so that the
+   * stationarity rows stay consistent without multiplying a rounding error by sigma; when inactive the
+   * slack step comes from the primal direction.  (dZ = mu/S - Z - sigma dS is applied by the caller.) */
+  double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
+  double sn = Zn / Sn, sd = Zd / Sd;
+  double ada = b->a1 * da1 + b->a2 * da2;
+  if (sn >= 1.0) ada = (b->a1 * zt[0] + b->a2 * zt[1]) / (2 * Zn + 4 * sn * (b->a1 * b->a1 + b->a2 * b->a2));
+  d->Sn[k][i] = -2 * ada + (v->dn[k][i] - Sn);
+  if (sd >= 1.0) {
+    double dZ = -zt[2] - Zd;
+    d->Sd[k][i] = (mu - Sd * Zd - Sd * dZ) / Zd;
+  } else {
+    double s = qdw + (v->dd[k][i] - Sd);
+    if (k >= 1) for (int c = 0; c < 3; ++c) s += b->dpose[c] * dp[c];
+    d->Sd[k][i] = s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * stage QP data over (xi, u) = (x, y, th, v_prev, w_prev, T | v, w):  H (8x8), reduced gradient r
+ * (without J^T y: the linear solve returns the new multipliers), gradient of the Lagrangian gL (for the
+ * optimality error) and objective gradient gf (for the directional derivative of the barrier function)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double H[NS][8][8], r[NS][8], gL[NS][8], gf[NS][8];
+  double A[NS][3][2];  /* hF_z theta column (2) and Ts*F (3) are kept explicit below */
+  double Fth[NS][2], FT[NS][3], Bv[NS][2], Bw[NS]; /* d z+/d theta (x,y), d z+/d T, d z+/d v (x,y), d th+/d w */
+} stageqp_t;
+
+static void sig_t(double S, double Z, double d, double mu, double* sig, double* t) {
+  *sig = Z / S;
+  *t = mu / S - (*sig) * (d - S);
+}
+
+static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double mu, stageqp_t* q, blk_t (*blk)[OM]) {
+  const obca_params* P = p->P;
+  int N = p->N;
+  double T = p->free_ ? it->T : 1.0, h = T * p->Ts;
+  memset(q->H, 0, sizeof(q->H)); memset(q->r, 0, sizeof(q->r)); memset(q->gL, 0, sizeof(q->gL));
+  memset(q->gf, 0, sizeof(q->gf));
+  for (int k = 0; k <= N; ++k) {
+    double (*H)[8] = q->H[k];
+    double* r = q->r[k];
+    double* gL = q->gL[k];
+    double* gf = q->gf[k];
+    const double* z = it->z[k];
+    double ct = cos(z[2]), st = sin(z[2]);
+    /* (1) tracking */
+    const double* M = (k < N) ? P->Q : P->P;
+    double e[3];
+    for (int j = 0; j < 3; ++j) e[j] = z[j] - p->xref[3 * k + j];
+    for (int a = 0; a < 3; ++a) {
+      double s = 0;
+      for (int b = 0; b < 3; ++b) {
+        s += (M[3 * a + b] + M[3 * b + a]) * e[b];
+        H[a][b] += M[3 * a + b] + M[3 * b + a];
+      }
+      gf[a] += s;
+    }
+    if (k < N) {
+      const double* u = it->u[k];
+      /* (2) input cost */
+      double uu[2] = {u[0], u[1]};
+      if (p->uref) { uu[0] -= p->uref[2 * k]; uu[1] -= p->uref[2 * k + 1]; }
+      for (int a = 0; a < 2; ++a) {
+        double s = 0;
+        for (int b = 0; b < 2; ++b) {
+          s += (P->R1[2 * a + b] + P->R1[2 * b + a]) * uu[b];
+          H[6 + a][6 + b] += P->R1[2 * a + b] + P->R1[2 * b + a];
+        }
+        gf[6 + a] += s;
+      }
+      /* (3) acceleration cost between u_{k-1} (state 3,4) and u_k, k >= 1 */
+      if (k >= 1) {
+        double du[2] = {u[0] - it->u[k - 1][0], u[1] - it->u[k - 1][1]}, qv[2], Aacc = 0;
+        for (int a = 0; a < 2; ++a) {
+          qv[a] = 0;
+          for (int b = 0; b < 2; ++b) qv[a] += 0.5 * (P->R2[2 * a + b] + P->R2[2 * b + a]) * du[b];
+          Aacc += du[a] * qv[a];
+        }
+        Aacc /= h * h;
+        for (int a = 0; a < 2; ++a) {
+          gf[6 + a] += 2 * qv[a] / (h * h);
+          gf[3 + a] -= 2 * qv[a] / (h * h);
+          for (int b = 0; b < 2; ++b) {
+            double m = (P->R2[2 * a + b] + P->R2[2 * b + a]) / (h * h);
+            H[6 + a][6 + b] += m; H[3 + a][3 + b] += m; H[6 + a][3 + b] -= m; H[3 + a][6 + b] -= m;
+          }
+          if (p->free_) {
+            double c = 4 * qv[a] / (h * h * T);
+            H[5][6 + a] -= c; H[6 + a][5] -= c; H[5][3 + a] += c; H[3 + a][5] += c;
+          }
+        }
+        if (p->free_) { gf[5] -= 2 * Aacc / T; H[5][5] += 6 * Aacc / (T * T); }
+      }
+      /* (5) dynamics: linearisation and Hessian-of-Lagrangian terms */
+      double vv = u[0], ww = u[1];
+      q->Fth[k][0] = -h * vv * st; q->Fth[k][1] = h * vv * ct;
+      q->Bv[k][0] = h * ct; q->Bv[k][1] = h * st; q->Bw[k] = h;
+      q->FT[k][0] = p->free_ ? p->Ts * vv * ct : 0; q->FT[k][1] = p->free_ ? p->Ts * vv * st : 0;
+      q->FT[k][2] = p->free_ ? p->Ts * ww : 0;
+      const double* y = it->yd[k];
+      H[2][2] += h * vv * (-y[0] * ct - y[1] * st);
+      H[2][6] += h * (-y[0] * st + y[1] * ct); H[6][2] = H[2][6];
+      if (p->free_) {
+        double a = p->Ts * vv * (-y[0] * st + y[1] * ct);
+        H[5][2] += a; H[2][5] += a;
+        a = p->Ts * (y[0] * ct + y[1] * st);
+        H[5][6] += a; H[6][5] += a;
+        a = p->Ts * y[2];
+        H[5][7] += a; H[7][5] += a;
+      }
+      /* J^T y for the Lagrangian gradient: c_k depends on z_k, u_k, T */
+      gL[0] += y[0]; gL[1] += y[1]; gL[2] += y[2] + q->Fth[k][0] * y[0] + q->Fth[k][1] * y[1];
+      gL[6] += q->Bv[k][0] * y[0] + q->Bv[k][1] * y[1]; gL[7] += h * y[2];
+      gL[5] += q->FT[k][0] * y[0] + q->FT[k][1] * y[1] + q->FT[k][2] * y[2];
+      /* (7) input bounds and acceleration rows */
+      const double* up = (k == 0) ? p->u0 : it->u[k - 1];
+      for (int j = 0; j < 2; ++j) {
+        double sg, t;
+        sig_t(it->Sub[k][j], it->Zub[k][j], v->dub[k][j], mu, &sg, &t);
+        H[6 + j][6 + j] += sg; r[6 + j] += t; gL[6 + j] -= it->Zub[k][j];
+        sig_t(it->Sub[k][2 + j], it->Zub[k][2 + j], v->dub[k][2 + j], mu, &sg, &t);
+        H[6 + j][6 + j] += sg; r[6 + j] -= t; gL[6 + j] += it->Zub[k][2 + j];
+        double ga = (up[j] - u[j]) / h;
+        double s4, t4, s6, t6;
+        sig_t(it->Sub[k][4 + j], it->Zub[k][4 + j], v->dub[k][4 + j], mu, &s4, &t4);
+        sig_t(it->Sub[k][6 + j], it->Zub[k][6 + j], v->dub[k][6 + j], mu, &s6, &t6);
+        /* Jacobian of (ga) wrt (up_j, u_j, T) */
+        double jv[3] = {(k >= 1) ? 1.0 / h : 0.0, -1.0 / h, p->free_ ? -ga / T : 0.0};
+        int ix[3] = {3 + j, 6 + j, 5};
+        double ss = s4 + s6, tt = t4 - t6, zz = it->Zub[k][4 + j] - it->Zub[k][6 + j];
+        for (int a = 0; a < 3; ++a) {
+          r[ix[a]] += tt * jv[a];
+          gL[ix[a]] -= zz * jv[a];
+          for (int b = 0; b < 3; ++b) H[ix[a]][ix[b]] += ss * jv[a] * jv[b];
+        }
+        if (p->free_) {
+          double yj = -zz; /* W -= Z * d2(+-ga) */
+          double c = yj / (h * T);
+          H[5][6 + j] += c; H[6 + j][5] += c;
+          if (k >= 1) { H[5][3 + j] -= c; H[3 + j][5] -= c; }
+          H[5][5] += yj * 2 * ga / (T * T);
+        }
+      }
+    }
+    /* -y_{k-1} on z_k */
+    if (k >= 1) for (int j = 0; j < 3; ++j) gL[j] -= it->yd[k - 1][j];
+    /* (6) state bounds, k >= 1 */
+    if (k >= 1)
+      for (int j = 0; j < 2; ++j) {
+        double sg, t;
+        sig_t(it->Sxy[k][j], it->Zxy[k][j], v->dxy[k][j], mu, &sg, &t);
+        H[j][j] += sg; r[j] += t; gL[j] -= it->Zxy[k][j];
+        sig_t(it->Sxy[k][2 + j], it->Zxy[k][2 + j], v->dxy[k][2 + j], mu, &sg, &t);
+        H[j][j] += sg; r[j] -= t; gL[j] += it->Zxy[k][2 + j];
+      }
+    if (k == 0 && p->free_) {
+      /* (4) time cost and (8) T bounds live in stage 0 */
+      gf[5] += (N + 1) * (P->time_cost[0] + 2 * P->time_cost[1] * T);
+      H[5][5] += 2 * (N + 1) * P->time_cost[1];
+      double sg, t;
+      sig_t(it->STb[0], it->ZTb[0], v->dTb[0], mu, &sg, &t);
+      H[5][5] += sg; r[5] += t; gL[5] -= it->ZTb[0];
+      sig_t(it->STb[1], it->ZTb[1], v->dTb[1], mu, &sg, &t);
+      H[5][5] += sg; r[5] -= t; gL[5] += it->ZTb[1];
+    }
+    if (k == N && p->has_term) {
+      double sg, t;
+      sig_t(it->Stm[0], it->Ztm[0], v->dtm[0], mu, &sg, &t);
+      H[0][0] += sg; r[0] += t; gL[0] -= it->Ztm[0];
+      sig_t(it->Stm[1], it->Ztm[1], v->dtm[1], mu, &sg, &t);
+      H[1][1] += sg; r[1] += t; gL[1] -= it->Ztm[1];
+      sig_t(it->Stm[2], it->Ztm[2], v->dtm[2], mu, &sg, &t);
+      H[1][1] += sg; r[1] -= t; gL[1] += it->Ztm[2];
+    }
+    if (k == N && p->free_) for (int j = 0; j < 3; ++j) gL[j] += it->yt[j];
+    /* (11) obstacle blocks: Schur complement onto the pose + Lagrangian gradient wrt pose */
+    double Hp[3][3] = {{0}}, rp[3] = {0};
+    for (int i = 0; i < p->nobs; ++i) {
+      if (block_setup(p, it, v, mu, k, i, &blk[k][i], Hp, rp)) return -1;
+      const blk_t* b = &blk[k][i];
+      double y1 = it->ye[k][2 * i], y2 = it->ye[k][2 * i + 1];
+      gL[2] += y1 * (-st * b->a1 + ct * b->a2) + y2 * (-ct * b->a1 - st * b->a2);
+      for (int a = 0; a < 3; ++a) gL[a] -= it->Zd[k][i] * b->dpose[a];
+    }
+    for (int a = 0; a < 3; ++a) {
+      r[a] += rp[a];
+      for (int b = 0; b < 3; ++b) H[a][b] += Hp[a][b];
+    }
+    /* objective gradient enters both r (negated) and gL */
+    for (int a = 0; a < 8; ++a) { r[a] -= gf[a]; gL[a] += gf[a]; }
+  }
+  return 0;
+}
+
+/* Riccati recursion; returns 0 if every pivot is positive definite (inertia (n, m, 0)) */
+typedef struct {
+  double P[NS][6][6], p[NS][6], K[NS][2][6], kap[NS][2];
+} ricc_t;
+
+static int riccati(const prob_t* p, const iter_t* it, const stageqp_t* q, const vals_t* v, double dw, double dc, ricc_t* R) {
+  int N = p->N;
+  /* terminal */
+  for (int a = 0; a < 6; ++a) {
+    for (int b = 0; b < 6; ++b) R->P[N][a][b] = q->H[N][a][b];
+    R->p[N][a] = q->r[N][a];
+  }
+  for (int a = 0; a < 3; ++a) {
+    R->P[N][a][a] += dw;
+    /* regularised terminal equality  dz_N - dc (y+ - y) = -c  =>  y+ = y + (dz_N + c)/dc */
+    if (p->free_) { R->P[N][a][a] += 1.0 / dc; R->p[N][a] -= v->ct[a] / dc + it->yt[a]; }
+  }
+  for (int k = N - 1; k >= 0; --k) {
+    /* At = [A B] (6x8): next xi = At (xi,u) + c */
+    double At[6][8];
+    memset(At, 0, sizeof(At));
+    At[0][0] = 1; At[1][1] = 1; At[2][2] = 1;
+    At[0][2] = q->Fth[k][0]; At[1][2] = q->Fth[k][1];
+    At[0][5] = q->FT[k][0]; At[1][5] = q->FT[k][1]; At[2][5] = q->FT[k][2];
+    At[5][5] = 1;
+    At[0][6] = q->Bv[k][0]; At[1][6] = q->Bv[k][1]; At[2][7] = q->Bw[k];
+    At[3][6] = 1; At[4][7] = 1;
+    double PA[6][8], F[8][8], f[8], pc[6];
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 8; ++b) {
+        double s = 0;
+        for (int c = 0; c < 6; ++c) s += R->P[k + 1][a][c] * At[c][b];
+        PA[a][b] = s;
+      }
+    for (int a = 0; a < 6; ++a) {
+      double s = R->p[k + 1][a];
+      for (int c = 0; c < 3; ++c) s -= R->P[k + 1][a][c] * v->cd[k][c];
+      pc[a] = s;
+    }
+    for (int a = 0; a < 8; ++a) {
+      for (int b = 0; b < 8; ++b) {
+        double s = q->H[k][a][b];
+        for (int c = 0; c < 6; ++c) s += At[c][a] * PA[c][b];
+        F[a][b] = s;
+      }
+      double s = q->r[k][a];
+      for (int c = 0; c < 6; ++c) s += At[c][a] * pc[c];
+      f[a] = s;
+    }
+    /* regularisation on the real variables of this stage: z_k (k >= 1), u_k, T (once, stage 0) */
+    if (k >= 1) for (int a = 0; a < 3; ++a) F[a][a] += dw;
+    F[6][6] += dw; F[7][7] += dw;
+    if (k == 0 && p->free_) F[5][5] += dw;
+    double q00 = F[6][6], q01 = 0.5 * (F[6][7] + F[7][6]), q11 = F[7][7];
+    double det = q00 * q11 - q01 * q01;
+    if (!(q00 > 0) || !(det > 0)) return -1;
+    double i00 = q11 / det, i01 = -q01 / det, i11 = q00 / det;
+    for (int b = 0; b < 6; ++b) {
+      R->K[k][0][b] = -(i00 * F[6][b] + i01 * F[7][b]);
+      R->K[k][1][b] = -(i01 * F[6][b] + i11 * F[7][b]);
+    }
+    R->kap[k][0] = i00 * f[6] + i01 * f[7];
+    R->kap[k][1] = i01 * f[6] + i11 * f[7];
+    for (int a = 0; a < 6; ++a) {
+      for (int b = 0; b < 6; ++b) R->P[k][a][b] = F[a][b] + F[a][6] * R->K[k][0][b] + F[a][7] * R->K[k][1][b];
+      R->p[k][a] = f[a] - F[a][6] * R->kap[k][0] - F[a][7] * R->kap[k][1];
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int b = a + 1; b < 6; ++b) R->P[k][a][b] = R->P[k][b][a] = 0.5 * (R->P[k][a][b] + R->P[k][b][a]);
+  }
+  if (p->free_ && !(R->P[0][5][5] > 0)) return -1;
+  return 0;
+}
+
+static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const vals_t* v, const ricc_t* R, double dc,
+                    dir_t* d) {
+  int N = p->N;
+  double xi[6] = {0, 0, 0, 0, 0, 0};
+  if (p->free_) xi[5] = R->p[0][5] / R->P[0][5][5];
+  d->T = xi[5];
+  for (int j = 0; j < 3; ++j) d->z[0][j] = 0;
+  for (int k = 0; k < N; ++k) {
+    double du[2];
+    for (int a = 0; a < 2; ++a) {
+      double s = R->kap[k][a];
+      for (int b = 0; b < 6; ++b) s += R->K[k][a][b] * xi[b];
+      du[a] = s;
+    }
+    d->u[k][0] = du[0]; d->u[k][1] = du[1];
+    double xn[6];
+    xn[0] = xi[0] + q->Fth[k][0] * xi[2] + q->FT[k][0] * xi[5] + q->Bv[k][0] * du[0] + v->cd[k][0];
+    xn[1] = xi[1] + q->Fth[k][1] * xi[2] + q->FT[k][1] * xi[5] + q->Bv[k][1] * du[0] + v->cd[k][1];
+    xn[2] = xi[2] + q->FT[k][2] * xi[5] + q->Bw[k] * du[1] + v->cd[k][2];
+    xn[3] = du[0]; xn[4] = du[1]; xn[5] = xi[5];
+    for (int a = 0; a < 3; ++a) {
+      double s = -R->p[k + 1][a];
+      for (int b = 0; b < 6; ++b) s += R->P[k + 1][a][b] * xn[b];
+      d->yd[k][a] = s; /* y_k+ */
+    }
+    /* the dw / 1/dc terms were folded into P[N] only; for k+1 < N the regularisation dw on z_{k+1} was
+     * added to F at stage k+1 (inside P[k+1] already) */
+    memcpy(xi, xn, sizeof(xi));
+    for (int j = 0; j < 3; ++j) d->z[k + 1][j] = xn[j];
+  }
+  if (p->free_) for (int j = 0; j < 3; ++j) d->yt[j] = it->yt[j] + (d->z[N][j] + v->ct[j]) / dc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * the interior-point loop (oracle/ipm_dense.py solve(), soc = False)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  iter_t it, tr;
+  vals_t v, vt;
+  stageqp_t q;
+  blk_t blk[NS][OM];
+  ricc_t R;
+  dir_t d;
+} work_t;
+
+typedef void (*trace_fn)(int it, double f, double th, double E0, double mu, double dw, double alpha);
+static trace_fn g_trace = 0;
+void obca_oracle_set_trace(trace_fn fn) { g_trace = fn; }
+
+static void apply_step(const prob_t* p, const iter_t* it, const dir_t* d, double a, iter_t* o) {
+  int N = p->N;
+  if (o != it) memcpy(o, it, sizeof(*o));
+  for (int k = 0; k <= N; ++k) {
+    if (k >= 1) for (int j = 0; j < 3; ++j) o->z[k][j] = it->z[k][j] + a * d->z[k][j];
+    if (k < N) for (int j = 0; j < 2; ++j) o->u[k][j] = it->u[k][j] + a * d->u[k][j];
+    for (int r = 0; r < p->R; ++r) { o->lam[k][r] = it->lam[k][r] + a * d->lam[k][r]; o->Sl[k][r] = it->Sl[k][r] + a * d->Sl[k][r]; }
+    for (int r = 0; r < 4 * p->nobs; ++r) { o->mu[k][r] = it->mu[k][r] + a * d->mu[k][r]; o->Sm[k][r] = it->Sm[k][r] + a * d->Sm[k][r]; }
+    for (int i = 0; i < p->nobs; ++i) { o->Sn[k][i] = it->Sn[k][i] + a * d->Sn[k][i]; o->Sd[k][i] = it->Sd[k][i] + a * d->Sd[k][i]; }
+    if (k >= 1) for (int j = 0; j < 4; ++j) o->Sxy[k][j] = it->Sxy[k][j] + a * d->Sxy[k][j];
+    if (k < N) for (int j = 0; j < 8; ++j) o->Sub[k][j] = it->Sub[k][j] + a * d->Sub[k][j];
+  }
+  if (p->free_) {
+    o->T = it->T + a * d->T;
+    for (int j = 0; j < 2; ++j) o->STb[j] = it->STb[j] + a * d->STb[j];
+  }
+  if (p->has_term) for (int j = 0; j < 3; ++j) o->Stm[j] = it->Stm[j] + a * d->Stm[j];
+}
+
+static double objective_of(const prob_t* p, const iter_t* it) {
+  vals_t* v = (vals_t*)malloc(sizeof(vals_t));
+  eval_values(p, it, v);
+  double f = v->f;
+  free(v);
+  return f;
+}
+
+static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out) {
+  const obca_params* P = p->P;
+  int N = p->N;
+  iter_t* it = &w->it;
+  vals_t* v = &w->v;
+  dir_t* d = &w->d;
+  const double s_max = 100.0, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, kappa_sigma = 1e10;
+  const double dw_first = 1e-4, dw_min = 1e-20, dw_max = 1e20, kw_plus_first = 100.0, kw_plus = 8.0, kw_minus = 1.0 / 3.0;
+  const double dc_min = 1e-8, lm_cap = 1e4, stall_alpha = 1e-3;
+  const int stall_iters = 10;
+  const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta_ph = 1e-8;
+  double tol = P->tol;
+
+  start_point(p, it);
+  eval_values(p, it, v);
+  FOR_INEQ(p, it, v, { *S_ = fmax(d_, P->bound_push); *Z_ = 1.0; });
+  double mu = P->mu_init;
+  filt_t F;
+  memset(&F, 0, sizeof(F));
+  int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
+  double dw_last = 0.0, E0 = 0;
+  int m_eq = 3 * N + (p->free_ ? 3 : 0) + 2 * p->nobs * (N + 1);
+  int q_in = 4 * N + 8 * N + (p->free_ ? 2 : 0) + (p->has_term ? 3 : 0) + (p->R + 6 * p->nobs) * (N + 1);
+
+  for (;;) {
+    eval_values(p, it, v);
+    /* assemble at the CURRENT mu first for the optimality error (gL, c, d do not depend on mu) */
+    if (assemble(p, it, v, mu, &w->q, w->blk)) { status = OBCA_ST_REGFAIL; break; }
+    /* optimality error pieces */
+    double e1 = 0, e2 = 0, sumy = 0, sumz = 0, szmax = 0, szmin = 1e300, th, ph0, cmax;
+    {
+      double gT = 0;
+      for (int k = 0; k <= N; ++k) {
+        if (k >= 1) for (int j = 0; j < 3; ++j) e1 = fmax(e1, fabs(w->q.gL[k][j]));
+        if (k < N) for (int j = 0; j < 2; ++j) e1 = fmax(e1, fabs(w->q.gL[k][6 + j] + ((k + 1 < N) ? w->q.gL[k + 1][3 + j] : 0.0)));
+        gT += w->q.gL[k][5];
+        if (k < N) for (int j = 0; j < 3; ++j) sumy += fabs(it->yd[k][j]);
+        for (int j = 0; j < 2 * p->nobs; ++j) sumy += fabs(it->ye[k][j]);
+        /* Lagrangian gradient wrt the block variables */
+        const double* z = it->z[k];
+        double ct = cos(z[2]), st = sin(z[2]), tx = z[0] + p->off * ct, ty = z[1] + p->off * st;
+        for (int i = 0; i < p->nobs; ++i) {
+          const blk_t* b = &w->blk[k][i];
+          double y1 = it->ye[k][2 * i], y2 = it->ye[k][2 * i + 1];
+          for (int r = p->eptr[i]; r < p->eptr[i + 1]; ++r) {
+            double A0 = p->A[2 * r], A1 = p->A[2 * r + 1];
+            double gl = y1 * (ct * A0 + st * A1) + y2 * (-st * A0 + ct * A1) - it->Zl[k][r] + it->Zn[k][i] * 2 * (b->a1 * A0 + b->a2 * A1) -
+                        it->Zd[k][i] * (tx * A0 + ty * A1 - bk(p, k, r));
+            e1 = fmax(e1, fabs(gl));
+          }
+          for (int m = 0; m < 4; ++m) {
+            double je1 = (m == 0) ? 1.0 : (m == 2) ? -1.0 : 0.0, je2 = (m == 1) ? 1.0 : (m == 3) ? -1.0 : 0.0;
+            double gl = y1 * je1 + y2 * je2 - it->Zm[k][4 * i + m] + it->Zd[k][i] * p->g[m];
+            e1 = fmax(e1, fabs(gl));
+          }
+        }
+      }
+      if (p->free_) { e1 = fmax(e1, fabs(gT)); for (int j = 0; j < 3; ++j) sumy += fabs(it->yt[j]); }
+      FOR_INEQ(p, it, v, { (void)d_; sumz += *Z_; double sz = (*S_) * (*Z_); szmax = fmax(szmax, sz); szmin = fmin(szmin, sz); });
+      theta_phi(p, it, v, mu, &th, &ph0, &cmax);
+      e2 = cmax;
+    }
+    double sd = fmax(s_max, (sumy + sumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, sumz / q_in) / s_max;
+    E0 = fmax(fmax(e1 / sd, e2), szmax / sc);
+    if (E0 <= tol) { status = OBCA_ST_OK; break; }
+    if (E0 <= P->acceptable_tol) {
+      if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
+    } else
+      acc_count = 0;
+    if (iter >= P->max_iter) { status = OBCA_ST_MAXITER; break; }
+    /* barrier update */
+    int changed = 0;
+    for (;;) {
+      double e3 = fmax(szmax - mu, mu - szmin) / sc;
+      double Emu = fmax(fmax(e1 / sd, e2), e3);
+      if (Emu <= kappa_eps * mu && mu > tol / 10) {
+        mu = fmax(tol / 10, fmin(kappa_mu * mu, pow(mu, theta_mu)));
+        changed = 1;
+      } else
+        break;
+    }
+    if (changed) {
+      if (F.active) { F.n = 0; F.wr = 0; }
+      if (assemble(p, it, v, mu, &w->q, w->blk)) { status = OBCA_ST_REGFAIL; break; }
+      theta_phi(p, it, v, mu, &th, &ph0, &cmax);
+    }
+    double tau = fmax(tau_min, 1 - mu);
+    double dc = 0.0;
+    if (p->free_) {
+      double cm = fmax(fabs(v->ct[0]), fmax(fabs(v->ct[1]), fabs(v->ct[2])));
+      dc = fmax(dc_min, cm / lm_cap);
+    }
+    /* inertia correction */
+    double dw = 0.0;
+    int regfail = 0;
+    for (;;) {
+      if (riccati(p, it, &w->q, v, dw, dc, &w->R) == 0) break;
+      if (dw == 0.0)
+        dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
+      else
+        dw = dw * ((dw_last == 0.0) ? kw_plus_first : kw_plus);
+      if (dw > dw_max) { regfail = 1; break; }
+    }
+    if (regfail) { status = OBCA_ST_REGFAIL; break; }
+    if (dw > 0) dw_last = dw;
+    forward(p, it, &w->q, v, &w->R, dc, d);
+    /* back-substitute the blocks; slack directions */
+    double Dphi = 0;
+    for (int k = 0; k <= N; ++k) {
+      for (int i = 0; i < p->nobs; ++i) block_backsub(p, it, v, mu, k, i, &w->blk[k][i], d->z[k], d);
+      if (k >= 1)
+        for (int j = 0; j < 2; ++j) {
+          d->Sxy[k][j] = d->z[k][j] + (v->dxy[k][j] - it->Sxy[k][j]);
+          d->Sxy[k][2 + j] = -d->z[k][j] + (v->dxy[k][2 + j] - it->Sxy[k][2 + j]);
+        }
+      if (k < N) {
+        double T = p->free_ ? it->T : 1.0, h = T * p->Ts;
+        const double* up = (k == 0) ? p->u0 : it->u[k - 1];
+        for (int j = 0; j < 2; ++j) {
+          d->Sub[k][j] = d->u[k][j] + (v->dub[k][j] - it->Sub[k][j]);
+          d->Sub[k][2 + j] = -d->u[k][j] + (v->dub[k][2 + j] - it->Sub[k][2 + j]);
+          double ga = (up[j] - it->u[k][j]) / h;
+          double dga = (((k >= 1) ? d->u[k - 1][j] : 0.0) - d->u[k][j]) / h - (p->free_ ? ga / T * d->T : 0.0);
+          d->Sub[k][4 + j] = dga + (v->dub[k][4 + j] - it->Sub[k][4 + j]);
+          d->Sub[k][6 + j] = -dga + (v->dub[k][6 + j] - it->Sub[k][6 + j]);
+        }
+      }
+      /* objective directional derivative: gf over (z_k, u_{k-1}, T, u_k) */
+      const double* gf = w->q.gf[k];
+      if (k >= 1) for (int j = 0; j < 3; ++j) Dphi += gf[j] * d->z[k][j];
+      if (k >= 1 && k < N) for (int j = 0; j < 2; ++j) Dphi += gf[3 + j] * d->u[k - 1][j];
+      if (p->free_) Dphi += gf[5] * d->T;
+      if (k < N) for (int j = 0; j < 2; ++j) Dphi += gf[6 + j] * d->u[k][j];
+    }
+    if (p->free_) {
+      d->STb[0] = d->T + (v->dTb[0] - it->STb[0]);
+      d->STb[1] = -d->T + (v->dTb[1] - it->STb[1]);
+    }
+    if (p->has_term) {
+      d->Stm[0] = d->z[N][0] + (v->dtm[0] - it->Stm[0]);
+      d->Stm[1] = d->z[N][1] + (v->dtm[1] - it->Stm[1]);
+      d->Stm[2] = -d->z[N][1] + (v->dtm[2] - it->Stm[2]);
+    }
+    /* fraction to the boundary on S and Z;  dZ = mu/S - Z - Sigma dS  (not stored) */
+    double a_max = 1.0, a_z = 1.0, sls = 0;
+    {
+      iter_t* dS = (iter_t*)0; (void)dS;
+      /* walk S/Z and the matching dS entries in the same order */
+#define STEP_INEQ(Sarr, Zarr, dSarr)                                           \
+      do { double S_ = (Sarr), Z_ = (Zarr), dS_ = (dSarr);                     \
+        double dZ_ = mu / S_ - Z_ - (Z_ / S_) * dS_;                            \
+        if (dS_ < 0) a_max = fmin(a_max, -tau * S_ / dS_);                      \
+        if (dZ_ < 0) a_z = fmin(a_z, -tau * Z_ / dZ_);                          \
+        sls += dS_ / S_; } while (0)
+      for (int k = 0; k <= N; ++k) {
+        if (k >= 1) for (int j = 0; j < 4; ++j) STEP_INEQ(it->Sxy[k][j], it->Zxy[k][j], d->Sxy[k][j]);
+        if (k < N) for (int j = 0; j < 8; ++j) STEP_INEQ(it->Sub[k][j], it->Zub[k][j], d->Sub[k][j]);
+        for (int r = 0; r < p->R; ++r) STEP_INEQ(it->Sl[k][r], it->Zl[k][r], d->Sl[k][r]);
+        for (int r = 0; r < 4 * p->nobs; ++r) STEP_INEQ(it->Sm[k][r], it->Zm[k][r], d->Sm[k][r]);
+        for (int i = 0; i < p->nobs; ++i) STEP_INEQ(it->Sn[k][i], it->Zn[k][i], d->Sn[k][i]);
+        for (int i = 0; i < p->nobs; ++i) STEP_INEQ(it->Sd[k][i], it->Zd[k][i], d->Sd[k][i]);
+      }
+      if (p->free_) for (int j = 0; j < 2; ++j) STEP_INEQ(it->STb[j], it->ZTb[j], d->STb[j]);
+      if (p->has_term) for (int j = 0; j < 3; ++j) STEP_INEQ(it->Stm[j], it->Ztm[j], d->Stm[j]);
+    }
+    Dphi -= mu * sls;
+    if (!F.active) {
+      F.thmax = 1e4 * fmax(1.0, th); F.thmin = 1e-4 * fmax(1.0, th);
+      F.active = 1; F.n = 0; F.wr = 0;
+    }
+    double a_min;
+    if (Dphi < 0 && th <= F.thmin)
+      a_min = fmin(g_th, fmin(g_ph * th / (-Dphi), (th > 0) ? pow(th, s_th) / pow(-Dphi, s_ph) : g_th));
+    else if (Dphi < 0)
+      a_min = fmin(g_th, g_ph * th / (-Dphi));
+    else
+      a_min = g_th;
+    a_min *= 0.05;
+    double a = a_max;
+    int accepted = 0;
+    while (a >= a_min * (1 - 1e-12)) {
+      apply_step(p, it, d, a, &w->tr);
+      eval_values(p, &w->tr, &w->vt);
+      double tht, pht;
+      theta_phi(p, &w->tr, &w->vt, mu, &tht, &pht, 0);
+      accepted = 0;
+      if (isfinite(pht) && tht < F.thmax) {
+        int dominated = 0;
+        for (int i = 0; i < F.n; ++i)
+          if (tht >= F.th[i] && pht >= F.ph[i]) { dominated = 1; break; }
+        if (!dominated) {
+          int sw = (Dphi < 0) && (a * pow(-Dphi, s_ph) > pow(th, s_th));
+          if (th <= F.thmin && sw) {
+            if (pht <= ph0 + eta_ph * a * Dphi + 10 * 2.220446049250313e-16 * fabs(ph0)) accepted = 2;
+          } else if (tht <= (1 - g_th) * th || pht <= ph0 - g_ph * th)
+            accepted = 1;
+        }
+      }
+      if (accepted) break;
+      a *= 0.5;
+    }
+    if (g_trace) g_trace(iter, v->f, th, E0, mu, dw, accepted ? a : -1.0);
+    if (!accepted) { status = OBCA_ST_LSFAIL; break; }
+    nstall = (a < stall_alpha) ? nstall + 1 : 0;
+    if (nstall >= stall_iters) { status = OBCA_ST_STALL; break; }
+    if (accepted == 1) {
+      int slot = (F.n < FILT_MAX) ? F.n++ : (F.wr % FILT_MAX);
+      F.th[slot] = (1 - g_th) * th; F.ph[slot] = ph0 - g_ph * th;
+      F.wr++;
+    }
+    /* update: primal + slacks with a, equality multipliers towards y+ with a, Z with a_z */
+    {
+#define UPD_Z(Sarr, Zarr, dSarr, Snew)                                         \
+      do { double S_ = (Sarr), Z_ = (Zarr), dS_ = (dSarr);                     \
+        double dZ_ = mu / S_ - Z_ - (Z_ / S_) * dS_;                            \
+        double Zn_ = Z_ + a_z * dZ_, Sn_ = (Snew);                              \
+        Zn_ = fmin(fmax(Zn_, mu / (kappa_sigma * Sn_)), kappa_sigma * mu / Sn_); \
+        (Zarr) = Zn_; } while (0)
+      iter_t* tr = &w->tr; /* holds X + a dX, S + a dS of the accepted trial */
+      for (int k = 0; k <= N; ++k) {
+        if (k >= 1) for (int j = 0; j < 4; ++j) UPD_Z(it->Sxy[k][j], it->Zxy[k][j], d->Sxy[k][j], tr->Sxy[k][j]);
+        if (k < N) for (int j = 0; j < 8; ++j) UPD_Z(it->Sub[k][j], it->Zub[k][j], d->Sub[k][j], tr->Sub[k][j]);
+        for (int r = 0; r < p->R; ++r) UPD_Z(it->Sl[k][r], it->Zl[k][r], d->Sl[k][r], tr->Sl[k][r]);
+        for (int r = 0; r < 4 * p->nobs; ++r) UPD_Z(it->Sm[k][r], it->Zm[k][r], d->Sm[k][r], tr->Sm[k][r]);
+        for (int i = 0; i < p->nobs; ++i) UPD_Z(it->Sn[k][i], it->Zn[k][i], d->Sn[k][i], tr->Sn[k][i]);
+        for (int i = 0; i < p->nobs; ++i) UPD_Z(it->Sd[k][i], it->Zd[k][i], d->Sd[k][i], tr->Sd[k][i]);
+        if (k < N) for (int j = 0; j < 3; ++j) it->yd[k][j] += a * (d->yd[k][j] - it->yd[k][j]);
+        for (int j = 0; j < 2 * p->nobs; ++j) it->ye[k][j] += a * (d->ye[k][j] - it->ye[k][j]);
+      }
+      if (p->free_) {
+        for (int j = 0; j < 2; ++j) UPD_Z(it->STb[j], it->ZTb[j], d->STb[j], tr->STb[j]);
+        for (int j = 0; j < 3; ++j) it->yt[j] += a * (d->yt[j] - it->yt[j]);
+      }
+      if (p->has_term) for (int j = 0; j < 3; ++j) UPD_Z(it->Stm[j], it->Ztm[j], d->Stm[j], tr->Stm[j]);
+      apply_step(p, it, d, a, it);
+    }
+    iter++;
+  }
+  *iters_out = iter;
+  if (err_out) *err_out = E0;
+  return status;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * batch driver with the same argument list as obca_b200_solve (host pointers)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const obca_params* P;
+  int batch, t0, t1;
+  const double *x0, *u0, *xref, *uref, *T_max, *term, *A, *b0, *db;
+  const int32_t* edge_ptr;
+  int shared;
+  double *x, *u, *lam, *mu, *T, *obj;
+  int32_t *status, *iters;
+} job_t;
+
+static void* worker(void* arg) {
+  job_t* J = (job_t*)arg;
+  const obca_params* P = J->P;
+  int N = P->N, R = P->rows, no = P->n_obs;
+  work_t* w = (work_t*)malloc(sizeof(work_t));
+  for (int b = J->t0; b < J->t1; ++b) {
+    prob_t p;
+    memset(&p, 0, sizeof(p));
+    p.P = P; p.N = N; p.nobs = no; p.R = R;
+    p.free_ = (P->mode == OBCA_MODE_FREE || P->mode == OBCA_MODE_FREE_STACKED);
+    p.has_term = (P->mode == OBCA_MODE_FIXED_SET) || (P->mode == OBCA_MODE_FIXED_OBCA2 && P->has_term);
+    p.stacked = (P->mode != OBCA_MODE_FREE);
+    for (int i = 0; i <= no; ++i) p.eptr[i] = J->edge_ptr[i];
+    p.Ts = P->Ts; p.dmin = P->dmin;
+    double L = P->ego[0] + P->ego[2], W = P->ego[1] + P->ego[3];
+    p.g[0] = L / 2; p.g[1] = W / 2; p.g[2] = L / 2; p.g[3] = W / 2;
+    p.off = L / 2 - P->ego[2];
+    for (int j = 0; j < 3; ++j) p.x0[j] = J->x0[3 * b + j];
+    for (int j = 0; j < 2; ++j) p.u0[j] = J->u0[2 * b + j];
+    p.xref = J->xref + (size_t)b * 3 * (N + 1);
+    p.uref = J->uref ? J->uref + (size_t)b * 2 * N : 0;
+    p.Tmax = (p.free_ && J->T_max) ? J->T_max[b] : 1.0;
+    if (p.has_term) for (int j = 0; j < 3; ++j) p.term[j] = J->term[3 * b + j];
+    size_t ob = J->shared ? 0 : (size_t)b;
+    p.A = J->A + ob * 2 * R; p.b0 = J->b0 + ob * R; p.db = J->db ? J->db + ob * R : 0;
+    int iters = 0;
+    int st = solve_one(&p, w, &iters, 0);
+    const iter_t* it = &w->it;
+    for (int k = 0; k <= N; ++k) {
+      for (int j = 0; j < 3; ++j) J->x[((size_t)b * (N + 1) + k) * 3 + j] = it->z[k][j];
+      if (k < N) for (int j = 0; j < 2; ++j) J->u[((size_t)b * N + k) * 2 + j] = it->u[k][j];
+      for (int r = 0; r < R; ++r) J->lam[((size_t)b * (N + 1) + k) * R + r] = it->lam[k][r];
+      for (int r = 0; r < 4 * no; ++r) J->mu[((size_t)b * (N + 1) + k) * 4 * no + r] = it->mu[k][r];
+    }
+    J->T[b] = p.free_ ? it->T : 1.0;
+    J->obj[b] = objective_of(&p, it);
+    J->status[b] = st;
+    J->iters[b] = iters;
+  }
+  free(w);
+  return 0;
+}
+
+int obca_oracle_solve(const obca_params* P, int batch, const double* x0, const double* u0, const double* xref,
+                      const double* uref, const double* T_max, const double* term, const int32_t* edge_ptr,
+                      const double* A, const double* b0, const double* db, int obstacles_shared, double* x, double* u,
+                      double* lam, double* mu, double* T, double* obj, int32_t* status, int32_t* iters, int nthreads) {
+  if (!P || P->N + 1 > NS || P->N < 1 || P->rows > RM || P->n_obs > OM) return OBCA_E_SIZE;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > batch) nthreads = batch > 0 ? batch : 1;
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  job_t jobs[256];
+  for (int t = 0; t < nthreads; ++t) {
+    job_t* J = &jobs[t];
+    J->P = P; J->batch = batch;
+    J->t0 = (int)((long long)batch * t / nthreads); J->t1 = (int)((long long)batch * (t + 1) / nthreads);
+    J->x0 = x0; J->u0 = u0; J->xref = xref; J->uref = uref; J->T_max = T_max; J->term = term;
+    J->A = A; J->b0 = b0; J->db = db; J->edge_ptr = edge_ptr; J->shared = obstacles_shared;
+    J->x = x; J->u = u; J->lam = lam; J->mu = mu; J->T = T; J->obj = obj; J->status = status; J->iters = iters;
+    if (nthreads == 1) worker(J);
+    else pthread_create(&th[t], 0, worker, J);
+  }
+  if (nthreads > 1) for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+  return OBCA_OK;
+}
