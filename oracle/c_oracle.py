@@ -32,8 +32,7 @@ TRACE_FN = C.CFUNCTYPE(None, C.c_int, C.c_double, C.c_double, C.c_double, C.c_do
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()
         _lib = C.CDLL(LIB)
         _lib.obca_oracle_solve.restype = C.c_int
         _lib.obca_oracle_solve.argtypes = [C.POINTER(_abi.ObcaParams)] + _abi.SOLVE_ARGTYPES_HOST + [C.c_int]

@@ -267,11 +267,11 @@ def solve(p: nlp.Problem, opts=None):
             a *= 0.5
             nbt += 1
         if not accepted:
-            status = ST_LSFAIL
+            status = ST_ACCEPTABLE if E0 <= o["acceptable_tol"] else ST_LSFAIL
             break
         nstall = nstall + 1 if a < o["stall_alpha"] else 0
         if nstall >= o["stall_iters"]:
-            status = ST_STALL
+            status = ST_ACCEPTABLE if E0 <= o["acceptable_tol"] else ST_STALL
             break
         if accepted == 1:
             if len(filt) < o["filt_max"]:

@@ -230,15 +230,29 @@ static void start_point(const prob_t* p, iter_t* it) {
 }
 
 /* ------------------------------------------------------------------------------------------------
- * per (stage, obstacle) dual block.  Rows j = lambda rows then the 4 mu rows; every row has a sign
- * constraint with slack (D_j = Z_j/S_j).  H_ww = D + U C3 U^T with U = [alpha0 alpha1 q];
- * Y = [U je1 je2];  M = Y^T D^-1 Y + blockdiag(C3^-1, 0)  is 5x5 SPD.
+ * per (stage, obstacle) dual block, solved in STEP form (all unknowns are Newton steps, every right-hand
+ * side is a residual, so rounding errors scale with the step and vanish at convergence).
+ * Unknowns: dw (rows j = lambda rows then the 4 mu rows; each row has a sign constraint with slack, so its
+ * curvature is sigma_j = Z_j/S_j) and dzeta = (tau_a (2), delta_d, dye (2)):
+ *     tau_a   = Cn (alpha^T dw)        Cn = 2 Zn I + 4 sn a a^T   (Hessian + Sigma term of the norm row)
+ *     delta_d = sd (grad dist . dv) - (td - Zd)  = -(step of the dist-row multiplier), kept in augmented form
+ *     dye     = step of the multipliers of the two equalities
+ * Block KKT with Y = [alpha0 alpha1 q je1 je2] (one 5-vector per row), C = blockdiag(Cn^-1, 1/sd, 0, 0):
+ *     sigma_j dw_j + y_j . dzeta = t'_j + y_j . h       (h: right-hand sides living in span(alpha0, alpha1))
+ *     Y^T dw - C dzeta           = -kappa               (kappa: coupling to the pose / constraint residuals)
+ * With eta = dzeta - h:   M eta = g0 + kappa - C h,   M = Y^T D^-1 Y + C,   dw_j = (t'_j - y_j . eta)/sigma_j.
+ * M = R^T R is factorised in square-root form (Givens row insertion), never as a Gram matrix: sigma_j
+ * spans 1e-9 .. 1e+16 near convergence and cond(M) must not be squared.
  * ---------------------------------------------------------------------------------------------- */
+#define SIG_MIN 1e-8 /* primal regularisation of the OBCA duals: curvature of a sign row is max(Z/S, SIG_MIN) */
+
 typedef struct {
-  double M0[5][5], g0[5], L[5][5]; /* L: Cholesky factor of M */
+  double L[5][5];                  /* R^T */
+  double g0[5];                    /* Y^T D^-1 t' */
   double a1, a2, ct, st, tx, ty;
-  double h0[5], hc[3][3], jt[2];   /* rhs in Y basis; pose columns (x,y,theta) in U basis; Je_p[:,theta] */
-  double zeta[4][5];               /* M^-1 rho for columns (0, x, y, theta) */
+  double Ci[2];                    /* Cn^-1 v = (v - Ci1 a (a.v)) Ci0 */
+  double h0[2], hc[3][2], jt[2];   /* rhs / pose columns (x,y,theta) in the (alpha0, alpha1) basis; Je_p[:,theta] */
+  double eta[4][5];                /* M^-1 b for columns (0, x, y, theta) */
   double dpose[3];                 /* grad of dist wrt pose */
 } blk_t;
 
@@ -258,28 +272,7 @@ static void row_y(const prob_t* p, const blk_t* b, int k, int i, int j, int E, d
   }
 }
 
-/* pivots are floored at CHOL_FLOOR * (largest diagonal entry): a vanishing dual regularisation that only
- * acts when rounding in the Gram matrix swamps a direction (extreme Z/S ratios near convergence) */
-#define CHOL_FLOOR 1e-14
-#define SIG_MIN 1e-8 /* primal regularisation of the OBCA duals: curvature of a sign row is max(Z/S, SIG_MIN) */
-static int chol5(double M[5][5], double L[5][5]) {
-  double dmax = 0;
-  for (int i = 0; i < 5; ++i) dmax = fmax(dmax, M[i][i]);
-  if (!(dmax > 0) || !isfinite(dmax)) return -1;
-  double flo = CHOL_FLOOR * dmax;
-  for (int i = 0; i < 5; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double s = M[i][j];
-      for (int q = 0; q < j; ++q) s -= L[i][q] * L[j][q];
-      if (i == j) {
-        if (!(s > flo)) s = flo;
-        L[i][i] = sqrt(s);
-      } else
-        L[i][j] = s / L[j][j];
-    }
-  return 0;
-}
-static void chol5_solve(double L[5][5], const double* r, double* x) {
+static void tri5_solve(const double L[5][5], const double* r, double* x) { /* (L L^T) x = r */
   double t[5];
   for (int i = 0; i < 5; ++i) {
     double s = r[i];
@@ -293,6 +286,40 @@ static void chol5_solve(double L[5][5], const double* r, double* x) {
   }
 }
 
+static void qr5_insert(double L[5][5], double row[5]) {
+  for (int c = 0; c < 5; ++c) {
+    double a = L[c][c], b = row[c];
+    if (b == 0.0) continue;
+    double r = sqrt(a * a + b * b), cs = a / r, sn = b / r;
+    L[c][c] = r;
+    for (int q = c + 1; q < 5; ++q) {
+      double u = L[q][c], w = row[q];
+      L[q][c] = cs * u + sn * w;
+      row[q] = -sn * u + cs * w;
+    }
+  }
+}
+
+/* step-form right-hand side of row j:  (t_j - Z_j) - (d L / d w_j)  with the CURRENT multipliers */
+static double row_rhs(const iter_t* it, int k, int i, const blk_t* b, double mu, double w, double S, double Z,
+                      const double yv[5]) {
+  double sig = Z / S;
+  double gl = it->ye[k][2 * i] * yv[3] + it->ye[k][2 * i + 1] * yv[4] - Z + 2 * it->Zn[k][i] * (b->a1 * yv[0] + b->a2 * yv[1]) -
+              it->Zd[k][i] * yv[2];
+  return (mu - S * Z) / S - sig * (w - S) - gl;
+}
+
+static void row_szw(const iter_t* it, int k, int i, int r0, int E, int j, double* w, double* S, double* Z) {
+  if (j < E) { *w = it->lam[k][r0 + j]; *S = it->Sl[k][r0 + j]; *Z = it->Zl[k][r0 + j]; }
+  else { *w = it->mu[k][4 * i + j - E]; *S = it->Sm[k][4 * i + j - E]; *Z = it->Zm[k][4 * i + j - E]; }
+}
+
+static void cn_inv(const blk_t* b, const double v[2], double o[2]) {
+  double av = b->a1 * v[0] + b->a2 * v[1];
+  o[0] = (v[0] - b->Ci[1] * b->a1 * av) * b->Ci[0];
+  o[1] = (v[1] - b->Ci[1] * b->a2 * av) * b->Ci[0];
+}
+
 /* builds the block factorisation; if Hp/rp != NULL adds this block's Schur complement to the pose
  * Hessian (3x3) and reduced gradient (3) */
 static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, blk_t* b,
@@ -304,76 +331,82 @@ static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, doubl
   double a1 = 0, a2 = 0;
   for (int r = r0; r < r0 + E; ++r) { a1 += p->A[2 * r] * it->lam[k][r]; a2 += p->A[2 * r + 1] * it->lam[k][r]; }
   b->a1 = a1; b->a2 = a2;
-  memset(b->M0, 0, sizeof(b->M0)); memset(b->g0, 0, sizeof(b->g0));
+  memset(b->g0, 0, sizeof(b->g0)); memset(b->L, 0, sizeof(b->L));
   for (int j = 0; j < E + 4; ++j) {
-    double w, S, Z;
-    if (j < E) { w = it->lam[k][r0 + j]; S = it->Sl[k][r0 + j]; Z = it->Zl[k][r0 + j]; }
-    else { w = it->mu[k][4 * i + j - E]; S = it->Sm[k][4 * i + j - E]; Z = it->Zm[k][4 * i + j - E]; }
-    double sig = Z / S, t = mu / S - sig * (w - S), yv[5];
+    double w, S, Z, yv[5], yh[5];
+    row_szw(it, k, i, r0, E, j, &w, &S, &Z);
     row_y(p, b, k, i, j, E, yv);
-    double di = 1.0 / fmax(sig, SIG_MIN);
-    for (int a = 0; a < 5; ++a) {
-      b->g0[a] += yv[a] * t * di;
-      for (int c = 0; c <= a; ++c) b->M0[a][c] += yv[a] * yv[c] * di;
-    }
+    double sig = Z / S, t = row_rhs(it, k, i, b, mu, w, S, Z, yv);
+    double di = 1.0 / fmax(sig, SIG_MIN), sq = sqrt(di);
+    for (int a = 0; a < 5; ++a) { b->g0[a] += yv[a] * t * di; yh[a] = yv[a] * sq; }
+    qr5_insert(b->L, yh);
   }
-  for (int a = 0; a < 5; ++a)
-    for (int c = a + 1; c < 5; ++c) b->M0[a][c] = b->M0[c][a];
   double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
   double sn = Zn / Sn, sd = Zd / Sd;
-  double tn = mu / Sn - sn * (v->dn[k][i] - Sn), td = mu / Sd - sd * (v->dd[k][i] - Sd);
-  /* Cn = 2 Zn I + 4 sn a a^T ;  C3^-1 = blockdiag(Cn^-1, 1/sd) */
-  double c00 = 2 * Zn + 4 * sn * a1 * a1, c01 = 4 * sn * a1 * a2, c11 = 2 * Zn + 4 * sn * a2 * a2;
-  double det = c00 * c11 - c01 * c01;
-  double M[5][5];
-  memcpy(M, b->M0, sizeof(M));
-  M[0][0] += c11 / det; M[1][1] += c00 / det; M[0][1] -= c01 / det; M[1][0] -= c01 / det;
-  M[2][2] += 1.0 / sd;
-  if (chol5(M, b->L)) return -1;
-  /* the dist row stays in augmented form (its own unknown tau_d with -1/sd on the diagonal, coupled to the
-   * pose through grad_pose dist) so nothing of size sd = Zd/Sd enters a difference */
-  double tds = mu / Zd - (v->dd[k][i] - Sd); /* = td / sd */
-  b->h0[0] = -2 * tn * a1; b->h0[1] = -2 * tn * a2; b->h0[2] = 0; b->h0[3] = 0; b->h0[4] = 0;
-  double rho[5];
-  for (int a = 0; a < 5; ++a) rho[a] = b->g0[a] + b->M0[a][0] * b->h0[0] + b->M0[a][1] * b->h0[1];
-  rho[2] -= tds; rho[3] += v->ce[k][2 * i]; rho[4] += v->ce[k][2 * i + 1];
-  chol5_solve(b->L, rho, b->zeta[0]);
+  double tn = (mu - Sn * Zn) / Sn - sn * (v->dn[k][i] - Sn); /* step form: t - Z */
+  double tds = (mu - Sd * Zd) / Zd - (v->dd[k][i] - Sd);     /* (td - Zd) / sd */
+  {
+    /* Cn = 2 Zn I + 4 sn a a^T has eigenpairs (2 Zn + 4 sn |a|^2, a/|a|) and (2 Zn, a_perp); when the norm
+     * row is active sn ~ 1e10 and Cn^-1 is numerically singular, so it is only ever used in this spectral
+     * form:  Cn^-1 v = (v - kn a (a.v)) / (2 Zn),  kn = 4 sn / (2 Zn + 4 sn |a|^2). */
+    double aa = a1 * a1 + a2 * a2, lam1 = 2 * Zn + 4 * sn * aa;
+    b->Ci[0] = 1.0 / (2 * Zn); b->Ci[1] = 4 * sn / lam1;
+    double r1[5] = {0, 0, 0, 0, 0}, r2[5] = {0, 0, 0, 0, 0}, r3[5] = {0, 0, sqrt(1.0 / sd), 0, 0};
+    if (aa > 0) {
+      double na = sqrt(aa), e1 = a1 / na, e2 = a2 / na, s1 = sqrt(1.0 / lam1), s2 = sqrt(b->Ci[0]);
+      r1[0] = s1 * e1; r1[1] = s1 * e2; r2[0] = -s2 * e2; r2[1] = s2 * e1;
+    } else {
+      r1[0] = sqrt(b->Ci[0]); r2[1] = r1[0];
+    }
+    qr5_insert(b->L, r1); qr5_insert(b->L, r2); qr5_insert(b->L, r3);
+    for (int a = 0; a < 5; ++a) {
+      if (b->L[a][a] < 0) for (int q = a; q < 5; ++q) b->L[q][a] = -b->L[q][a];
+      if (!(b->L[a][a] > 0) || !isfinite(b->L[a][a])) return -1;
+    }
+  }
+  /* column 0: eta0 = M^-1 (g0 + kappa0 - C h0),  kappa0 = (0, 0, -(td - Zd)/sd, e1, e2),  h0 = -2 (tn - Zn) a */
+  b->h0[0] = -2 * tn * a1; b->h0[1] = -2 * tn * a2;
+  double rhs[5], ch[2];
+  cn_inv(b, b->h0, ch);
+  rhs[0] = b->g0[0] - ch[0];
+  rhs[1] = b->g0[1] - ch[1];
+  rhs[2] = b->g0[2] - tds;
+  rhs[3] = b->g0[3] + v->ce[k][2 * i];
+  rhs[4] = b->g0[4] + v->ce[k][2 * i + 1];
+  tri5_solve(b->L, rhs, b->eta[0]);
   double offt = p->off * (-b->st * a1 + b->ct * a2);
   b->dpose[0] = a1; b->dpose[1] = a2; b->dpose[2] = offt;
   if (k == 0) return 0; /* pose fixed */
   double y1 = it->ye[k][2 * i], y2 = it->ye[k][2 * i + 1], yd = -Zd;
   double c1 = y1 + yd * p->off;
-  /* H_wp columns (x, y, theta) in the (alpha0, alpha1) basis: W cross terms only */
-  b->hc[0][0] = yd; b->hc[0][1] = 0; b->hc[0][2] = 0;
-  b->hc[1][0] = 0; b->hc[1][1] = yd; b->hc[1][2] = 0;
-  b->hc[2][0] = -c1 * b->st - y2 * b->ct; b->hc[2][1] = c1 * b->ct - y2 * b->st; b->hc[2][2] = 0;
+  /* -H_wp columns are -U h^c (W cross terms only); kappa^c = (0, 0, dpose_c, Je_p[:,c]) */
+  b->hc[0][0] = yd; b->hc[0][1] = 0;
+  b->hc[1][0] = 0; b->hc[1][1] = yd;
+  b->hc[2][0] = -c1 * b->st - y2 * b->ct; b->hc[2][1] = c1 * b->ct - y2 * b->st;
   b->jt[0] = -b->st * a1 + b->ct * a2; b->jt[1] = -b->ct * a1 - b->st * a2;
-  double rhoc[3][5];
+  double bc[3][5];
   for (int c = 0; c < 3; ++c) {
-    for (int a = 0; a < 5; ++a) rhoc[c][a] = -(b->M0[a][0] * b->hc[c][0] + b->M0[a][1] * b->hc[c][1]);
-    rhoc[c][2] += b->dpose[c];
-    if (c == 2) { rhoc[c][3] += b->jt[0]; rhoc[c][4] += b->jt[1]; }
-    chol5_solve(b->L, rhoc[c], b->zeta[1 + c]);
+    cn_inv(b, b->hc[c], bc[c]);
+    bc[c][2] = b->dpose[c];
+    bc[c][3] = (c == 2) ? b->jt[0] : 0.0;
+    bc[c][4] = (c == 2) ? b->jt[1] : 0.0;
+    tri5_solve(b->L, bc[c], b->eta[1 + c]); /* dzeta^c = eta^c - h^c */
   }
   if (Hp) {
     /* own pose term of this block: W (theta,theta) */
     Hp[2][2] += y1 * (-b->ct * a1 - b->st * a2) + y2 * (b->st * a1 - b->ct * a2) + yd * p->off * (-b->ct * a1 - b->st * a2);
-    /* Schur complement: Gamma(c',c) = h^c'^T M0[0:2,0:2] h^c - rho^c'^T zeta^c */
+    /* Schur complement  Gamma(c',c) = h^c'^T Cn^-1 h^c - b^c'^T M^-1 b^c ;  Gamma(c',0) = -b^c' . eta0 - (Cn^-1 h^c') . h0 */
     for (int cp = 0; cp < 3; ++cp) {
       for (int c = 0; c < 3; ++c) {
-        double G = 0;
-        for (int a = 0; a < 2; ++a)
-          for (int q = 0; q < 2; ++q) G += b->hc[cp][a] * b->M0[a][q] * b->hc[c][q];
-        for (int a = 0; a < 5; ++a) G -= rhoc[cp][a] * b->zeta[1 + c][a];
+        double G = b->hc[cp][0] * bc[c][0] + b->hc[cp][1] * bc[c][1];
+        for (int a = 0; a < 5; ++a) G -= bc[cp][a] * b->eta[1 + c][a];
         Hp[cp][c] -= G;
       }
-      double G0 = 0;
-      for (int a = 0; a < 2; ++a) G0 -= b->hc[cp][a] * (b->g0[a] + b->M0[a][0] * b->h0[0] + b->M0[a][1] * b->h0[1]);
-      for (int a = 0; a < 5; ++a) G0 -= rhoc[cp][a] * b->zeta[0][a];
+      double G0 = -(bc[cp][0] * b->h0[0] + bc[cp][1] * b->h0[1]);
+      for (int a = 0; a < 5; ++a) G0 -= bc[cp][a] * b->eta[0][a];
       rp[cp] += G0;
     }
   }
-  (void)td;
   return 0;
 }
 
@@ -381,32 +414,27 @@ static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, doubl
 typedef struct {
   double z[NS][3], u[NS][2], T;
   double lam[NS][RM], mu[NS][4 * OM];
-  double yd[NS][3], yt[3], ye[NS][2 * OM]; /* NEW multipliers y+ (the step is y+ - y) */
+  double yd[NS][3], yt[3], ye[NS][2 * OM]; /* NEW multipliers y + dy (the step is this minus y) */
   double Sxy[NS][4], Sub[NS][8], STb[2], Stm[3], Sl[NS][RM], Sm[NS][4 * OM], Sn[NS][OM], Sd[NS][OM];
 } dir_t;
 
 static void block_backsub(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, const blk_t* b,
                           const double dp[3], dir_t* d) {
   int E = p->eptr[i + 1] - p->eptr[i], r0 = p->eptr[i];
-  double zt[5], ht[5];
-  for (int a = 0; a < 5; ++a) {
-    zt[a] = b->zeta[0][a];
-    ht[a] = b->h0[a];
-  }
+  double et[5], ht[2] = {b->h0[0], b->h0[1]};
+  for (int a = 0; a < 5; ++a) et[a] = b->eta[0][a];
   if (k >= 1)
     for (int c = 0; c < 3; ++c) {
-      for (int a = 0; a < 5; ++a) zt[a] += b->zeta[1 + c][a] * dp[c];
-      for (int a = 0; a < 3; ++a) ht[a] -= b->hc[c][a] * dp[c];
+      for (int a = 0; a < 5; ++a) et[a] += b->eta[1 + c][a] * dp[c];
+      ht[0] -= b->hc[c][0] * dp[c]; ht[1] -= b->hc[c][1] * dp[c];
     }
   double da1 = 0, da2 = 0, qdw = 0;
   for (int j = 0; j < E + 4; ++j) {
-    double w, S, Z;
-    if (j < E) { w = it->lam[k][r0 + j]; S = it->Sl[k][r0 + j]; Z = it->Zl[k][r0 + j]; }
-    else { w = it->mu[k][4 * i + j - E]; S = it->Sm[k][4 * i + j - E]; Z = it->Zm[k][4 * i + j - E]; }
-    double sig = Z / S, t = mu / S - sig * (w - S), yv[5];
+    double w, S, Z, yv[5];
+    row_szw(it, k, i, r0, E, j, &w, &S, &Z);
     row_y(p, b, k, i, j, E, yv);
-    double s = t;
-    for (int a = 0; a < 5; ++a) s += yv[a] * (ht[a] - zt[a]);
+    double sig = Z / S, s = row_rhs(it, k, i, b, mu, w, S, Z, yv);
+    for (int a = 0; a < 5; ++a) s -= yv[a] * et[a];
     double dw = s / fmax(sig, SIG_MIN);
     if (j < E) {
       d->lam[k][r0 + j] = dw; d->Sl[k][r0 + j] = dw + (w - S);
@@ -416,18 +444,19 @@ static void block_backsub(const prob_t* p, const iter_t* it, const vals_t* v, do
     }
     qdw += yv[2] * dw;
   }
-  d->ye[k][2 * i] = zt[3]; d->ye[k][2 * i + 1] = zt[4];
-  /* Rows kept in augmented form (norm, dist): when the row is active (sigma = Z/S >= 1) its new multiplier
-   * comes from the solve (tau) and the slack step from the linearised complementarity, so that the
+  d->ye[k][2 * i] = it->ye[k][2 * i] + et[3]; d->ye[k][2 * i + 1] = it->ye[k][2 * i + 1] + et[4];
+  /* Rows kept in augmented form (norm, dist): when the row is active (sigma = Z/S >= 1) the step of its
+   * multiplier comes from the solve and the slack step from the linearised complementarity, so that the
    * stationarity rows stay consistent without multiplying a rounding error by sigma; when inactive the
    * slack step comes from the primal direction.  (dZ = mu/S - Z - sigma dS is applied by the caller.) */
   double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
   double sn = Zn / Sn, sd = Zd / Sd;
   double ada = b->a1 * da1 + b->a2 * da2;
-  if (sn >= 1.0) ada = (b->a1 * zt[0] + b->a2 * zt[1]) / (2 * Zn + 4 * sn * (b->a1 * b->a1 + b->a2 * b->a2));
+  if (sn >= 1.0) /* tau_a = eta_a + h_a = Cn (alpha^T dw)  =>  a . (alpha^T dw) = a . tau_a / (2 Zn + 4 sn |a|^2) */
+    ada = (b->a1 * (et[0] + ht[0]) + b->a2 * (et[1] + ht[1])) / (2 * Zn + 4 * sn * (b->a1 * b->a1 + b->a2 * b->a2));
   d->Sn[k][i] = -2 * ada + (v->dn[k][i] - Sn);
   if (sd >= 1.0) {
-    double dZ = -zt[2] - Zd;
+    double dZ = -et[2];
     d->Sd[k][i] = (mu - Sd * Zd - Sd * dZ) / Zd;
   } else {
     double s = qdw + (v->dd[k][i] - Sd);
@@ -447,9 +476,10 @@ typedef struct {
   double Fth[NS][2], FT[NS][3], Bv[NS][2], Bw[NS]; /* d z+/d theta (x,y), d z+/d T, d z+/d v (x,y), d th+/d w */
 } stageqp_t;
 
+/* sigma = Z/S and the step-form right-hand side  t - Z = (mu - S Z)/S - sigma (d - S)  of one inequality */
 static void sig_t(double S, double Z, double d, double mu, double* sig, double* t) {
   *sig = Z / S;
-  *t = mu / S - (*sig) * (d - S);
+  *t = (mu - S * Z) / S - (*sig) * (d - S);
 }
 
 static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double mu, stageqp_t* q, blk_t (*blk)[OM]) {
@@ -608,8 +638,8 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
       r[a] += rp[a];
       for (int b = 0; b < 3; ++b) H[a][b] += Hp[a][b];
     }
-    /* objective gradient enters both r (negated) and gL */
-    for (int a = 0; a < 8; ++a) { r[a] -= gf[a]; gL[a] += gf[a]; }
+    /* step form: r = -grad L + Jd^T (t - Z)  (the dist rows are carried by their own unknown in the blocks) */
+    for (int a = 0; a < 8; ++a) { gL[a] += gf[a]; r[a] -= gL[a]; }
   }
   return 0;
 }
@@ -619,7 +649,7 @@ typedef struct {
   double P[NS][6][6], p[NS][6], K[NS][2][6], kap[NS][2];
 } ricc_t;
 
-static int riccati(const prob_t* p, const iter_t* it, const stageqp_t* q, const vals_t* v, double dw, double dc, ricc_t* R) {
+static int riccati(const prob_t* p, const stageqp_t* q, const vals_t* v, double dw, double dc, ricc_t* R) {
   int N = p->N;
   /* terminal */
   for (int a = 0; a < 6; ++a) {
@@ -628,8 +658,8 @@ static int riccati(const prob_t* p, const iter_t* it, const stageqp_t* q, const 
   }
   for (int a = 0; a < 3; ++a) {
     R->P[N][a][a] += dw;
-    /* regularised terminal equality  dz_N - dc (y+ - y) = -c  =>  y+ = y + (dz_N + c)/dc */
-    if (p->free_) { R->P[N][a][a] += 1.0 / dc; R->p[N][a] -= v->ct[a] / dc + it->yt[a]; }
+    /* regularised terminal equality  dz_N - dc dy = -c  =>  dy = (dz_N + c)/dc */
+    if (p->free_) { R->P[N][a][a] += 1.0 / dc; R->p[N][a] -= v->ct[a] / dc; }
   }
   for (int k = N - 1; k >= 0; --k) {
     /* At = [A B] (6x8): next xi = At (xi,u) + c */
@@ -711,7 +741,7 @@ static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const
     for (int a = 0; a < 3; ++a) {
       double s = -R->p[k + 1][a];
       for (int b = 0; b < 6; ++b) s += R->P[k + 1][a][b] * xn[b];
-      d->yd[k][a] = s; /* y_k+ */
+      d->yd[k][a] = it->yd[k][a] + s; /* y_k + dy_k */
     }
     /* the dw / 1/dc terms were folded into P[N] only; for k+1 < N the regularisation dw on z_{k+1} was
      * added to F at stage k+1 (inside P[k+1] already) */
@@ -860,7 +890,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     double dw = 0.0;
     int regfail = 0;
     for (;;) {
-      if (riccati(p, it, &w->q, v, dw, dc, &w->R) == 0) break;
+      if (riccati(p, &w->q, v, dw, dc, &w->R) == 0) break;
       if (dw == 0.0)
         dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
       else
@@ -966,9 +996,12 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       a *= 0.5;
     }
     if (g_trace) g_trace(iter, v->f, th, E0, mu, dw, accepted ? a : -1.0);
-    if (!accepted) { status = OBCA_ST_LSFAIL; break; }
+    /* IPOPT returns Solved_To_Acceptable_Level when it cannot make progress from a point that meets the
+     * acceptable tolerance; near a degenerate vertex of the OBCA dual polytope the step noise floor is
+     * above tol, so this is how such instances end */
+    if (!accepted) { status = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
-    if (nstall >= stall_iters) { status = OBCA_ST_STALL; break; }
+    if (nstall >= stall_iters) { status = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
     if (accepted == 1) {
       int slot = (F.n < FILT_MAX) ? F.n++ : (F.wr % FILT_MAX);
       F.th[slot] = (1 - g_th) * th; F.ph[slot] = ph0 - g_ph * th;
