@@ -266,12 +266,13 @@ def solve(p: nlp.Problem, opts=None):
                     break
             a *= 0.5
             nbt += 1
+        at_floor = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
         if not accepted:
-            status = ST_ACCEPTABLE if E0 <= o["acceptable_tol"] else ST_LSFAIL
+            status = ST_ACCEPTABLE if at_floor else ST_LSFAIL
             break
         nstall = nstall + 1 if a < o["stall_alpha"] else 0
         if nstall >= o["stall_iters"]:
-            status = ST_ACCEPTABLE if E0 <= o["acceptable_tol"] else ST_STALL
+            status = ST_ACCEPTABLE if at_floor else ST_STALL
             break
         if accepted == 1:
             if len(filt) < o["filt_max"]:

@@ -998,10 +998,13 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     if (g_trace) g_trace(iter, v->f, th, E0, mu, dw, accepted ? a : -1.0);
     /* IPOPT returns Solved_To_Acceptable_Level when it cannot make progress from a point that meets the
      * acceptable tolerance; near a degenerate vertex of the OBCA dual polytope the step noise floor is
-     * above tol, so this is how such instances end */
-    if (!accepted) { status = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
+     * above tol, so this is how such instances end
+     * (second clause: at the final barrier parameter, primal feasible to 1e-6 and complementary, with only
+     * the dual infeasibility sitting on the rounding-noise floor of the degenerate-vertex linear algebra) */
+    int at_floor = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
+    if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
-    if (nstall >= stall_iters) { status = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
     if (accepted == 1) {
       int slot = (F.n < FILT_MAX) ? F.n++ : (F.wr % FILT_MAX);
       F.th[slot] = (1 - g_th) * th; F.ph[slot] = ph0 - g_ph * th;

@@ -1,0 +1,18 @@
+import sys, time, numpy as np
+sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import obca_testlib as common
+from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om, scenario as sc
+import torch
+cfg=int(sys.argv[1]); B=int(sys.argv[2])
+b=sc.make_batch(cfg,B)
+prm,a=common.batch_arrays(b)
+s=om.BatchSolver(prm,a['edge_ptr'],B)
+t=lambda v: None if v is None else torch.as_tensor(v,dtype=torch.float64,device='cuda').contiguous()
+dv={k:t(a[k]) for k in ('x0','u0','xref','A','b0','db','T_max','term')}
+out=s.alloc_outputs(B,'cuda')
+for i in range(3):
+    s.solve(dv['x0'],dv['u0'],dv['xref'],dv['A'],dv['b0'],dv['db'],T_max=dv['T_max'],term=dv['term'],out=out)
+    torch.cuda.synchronize()
+    print('cfg',cfg,'B',B,'kernel ms %.2f -> %.0f solves/s'%(s.last_kernel_ms(),B/s.last_kernel_ms()*1e3), 'scratch MB %.1f'%(s.scratch_bytes/1e6))
+st=out['status'].cpu().numpy(); it=out['iters'].cpu().numpy()
+print('status',{int(v):int((st==v).sum()) for v in np.unique(st)},'iters mean %.1f max %d'%(it.mean(),it.max()))

@@ -1,0 +1,84 @@
+"""Build + load the CUDA shared library (csrc/libobca_b200.so, C-ABI of include/obca_b200.h).
+
+The library is built in-tree with nvcc for sm_100a.  There is no CPU fallback: if it cannot be built or
+loaded, or no CUDA device is present at solve time, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from . import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libobca_b200.so")
+SOURCES = ["obca_b200.cu"]
+HEADERS = ["obca_kernel.cuh", "obca_phases.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.exists(os.path.join(CSRC, f)) and os.path.getmtime(os.path.join(CSRC, f)) > t
+               for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> csrc/libobca_b200.so (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+_lib = None
+EXPORTS = ["obca_b200_abi_version", "obca_b200_create", "obca_b200_destroy", "obca_b200_scratch_bytes",
+           "obca_b200_solve", "obca_b200_solve_host", "obca_b200_launch_count", "obca_b200_last_kernel_ms",
+           "obca_b200_strerror"]
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        try:
+            build()
+        except Exception as e:  # no nvcc on this box: a prebuilt .so is still fine if present
+            if not os.path.exists(LIB):
+                raise RuntimeError("libobca_b200.so is missing and could not be built: %r" % (e,))
+    L = C.CDLL(LIB)
+    L.obca_b200_abi_version.restype = C.c_int
+    L.obca_b200_create.restype = C.c_int
+    L.obca_b200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(_abi.ObcaParams)]
+    L.obca_b200_destroy.restype = C.c_int
+    L.obca_b200_destroy.argtypes = [C.c_void_p]
+    L.obca_b200_scratch_bytes.restype = C.c_int64
+    L.obca_b200_scratch_bytes.argtypes = [C.c_void_p]
+    L.obca_b200_launch_count.restype = C.c_int64
+    L.obca_b200_launch_count.argtypes = [C.c_void_p]
+    L.obca_b200_last_kernel_ms.restype = C.c_float
+    L.obca_b200_last_kernel_ms.argtypes = [C.c_void_p]
+    L.obca_b200_strerror.restype = C.c_char_p
+    L.obca_b200_strerror.argtypes = [C.c_int]
+    vp = C.c_void_p
+    L.obca_b200_solve.restype = C.c_int
+    L.obca_b200_solve.argtypes = [vp, C.c_int] + [vp] * 6 + [C.POINTER(C.c_int32)] + [vp] * 3 + [C.c_int] + [vp] * 8 + [vp]
+    L.obca_b200_solve_host.restype = C.c_int
+    L.obca_b200_solve_host.argtypes = [vp] + _abi.SOLVE_ARGTYPES_HOST
+    if L.obca_b200_abi_version() != 1:
+        raise RuntimeError("libobca_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("obca_b200: %s (rc=%d)" % (lib().obca_b200_strerror(rc).decode(), rc))
