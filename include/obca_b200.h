@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define OBCA_B200_ABI_VERSION 1
+#define OBCA_B200_ABI_VERSION 2
 
 enum { OBCA_MODE_FREE = 0, OBCA_MODE_FIXED_SET = 1, OBCA_MODE_FIXED_NOTERM = 2, OBCA_MODE_FREE_STACKED = 3,
        OBCA_MODE_FIXED_OBCA2 = 4 };
@@ -76,6 +76,8 @@ int64_t obca_b200_scratch_bytes(const obca_ctx* ctx);
 /* All pointers are DEVICE pointers except edge_ptr (host).  Asynchronous on cuda_stream.
  *   x0 [B,3]  u0 [B,2]  xref [B,N+1,3]  uref [B,N,2] or NULL
  *   T_max [B] (free modes; obca.py:961-962) or NULL    term [B,3] = {xmin, ymin, ymax} (terminal set) or NULL
+ *   Ts_inst [B] per-instance sampling time or NULL (=> params.Ts).  The receding-horizon loop hands every
+ *           scenario its own inherited step (closed_loop.py:586-587), so a lock-step batch needs one per instance
  *   edge_ptr [n_obs+1] prefix sum of (vObs-1), shared by the batch
  *   A [Bo,rows,2]  b0 [Bo,rows]  db [Bo,rows] or NULL (b_k = b0 + k*db; mode FREE ignores db: obca.py:969)
  *   obstacles_shared != 0 => Bo = 1 (one scene broadcast to the batch), else Bo = B
@@ -84,7 +86,7 @@ int64_t obca_b200_scratch_bytes(const obca_ctx* ctx);
  *   obj [B]  status [B]  iters [B]                                                                     */
 int  obca_b200_solve  (obca_ctx* ctx, int batch,
                        const double* x0, const double* u0, const double* xref, const double* uref,
-                       const double* T_max, const double* term,
+                       const double* T_max, const double* term, const double* Ts_inst,
                        const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
                        int obstacles_shared,
                        double* x, double* u, double* lam, double* mu, double* T, double* obj,
@@ -93,7 +95,7 @@ int  obca_b200_solve  (obca_ctx* ctx, int batch,
  * synchronises.  This is what the single-problem Python methods (obca.obca_mpc4 ...) use. */
 int  obca_b200_solve_host(obca_ctx* ctx, int batch,
                        const double* x0, const double* u0, const double* xref, const double* uref,
-                       const double* T_max, const double* term,
+                       const double* T_max, const double* term, const double* Ts_inst,
                        const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
                        int obstacles_shared,
                        double* x, double* u, double* lam, double* mu, double* T, double* obj,

@@ -40,11 +40,12 @@ def lib():
     return _lib
 
 
-def solve(params, x0, u0, xref, edge_ptr, A, b0, db=None, T_max=None, term=None, uref=None, nthreads=1, trace=None):
+def solve(params, x0, u0, xref, edge_ptr, A, b0, db=None, T_max=None, term=None, uref=None, nthreads=1, trace=None,
+          Ts=None):
     """ABI-level arrays (see include/obca_b200.h) -> dict of outputs.  x0 (B,3), u0 (B,2), xref (B,N+1,3)."""
     L = lib()
     f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
-    x0, u0, xref, uref, T_max, term, A, b0, db = map(f64, (x0, u0, xref, uref, T_max, term, A, b0, db))
+    x0, u0, xref, uref, T_max, term, A, b0, db, Ts = map(f64, (x0, u0, xref, uref, T_max, term, A, b0, db, Ts))
     B = x0.shape[0]
     N, R, no = params.N, params.rows, params.n_obs
     shared = int(A.ndim == 2)
@@ -55,7 +56,7 @@ def solve(params, x0, u0, xref, edge_ptr, A, b0, db=None, T_max=None, term=None,
     cb = TRACE_FN(trace) if trace else C.cast(None, TRACE_FN)
     L.obca_oracle_set_trace(cb)
     rc = L.obca_oracle_solve(C.byref(params), B, _abi.ptr(x0), _abi.ptr(u0), _abi.ptr(xref), _abi.ptr(uref),
-                             _abi.ptr(T_max), _abi.ptr(term), _abi.ptr(ep, C.c_int32), _abi.ptr(A), _abi.ptr(b0),
+                             _abi.ptr(T_max), _abi.ptr(term), _abi.ptr(Ts), _abi.ptr(ep, C.c_int32), _abi.ptr(A), _abi.ptr(b0),
                              _abi.ptr(db), shared, _abi.ptr(out["x"]), _abi.ptr(out["u"]), _abi.ptr(out["lam"]),
                              _abi.ptr(out["mu"]), _abi.ptr(out["T"]), _abi.ptr(out["obj"]),
                              _abi.ptr(out["status"], C.c_int32), _abi.ptr(out["iters"], C.c_int32), nthreads)

@@ -17,7 +17,8 @@ Algorithm (IPOPT-flavoured, Waechter & Biegler 2006):
   chosen Levenberg-Marquardt style so that the terminal multiplier step stays bounded;
   fraction-to-boundary tau = max(0.99, 1-mu) on S and Z; filter line search with second-order correction;
   monotone barrier update mu <- max(tol/10, min(0.2 mu, mu^1.5)) when E_mu <= 10 mu;
-  stop when IPOPT's scaled optimality error E_0 <= tol (1e-8).
+  stop when IPOPT's scaled optimality error E_0 <= tol (1e-8); the best iterate with E_0 <= acceptable_tol is
+  stored and becomes the result ("Solved To Acceptable Level") if the run later ends in a failure.
 """
 from __future__ import annotations
 
@@ -95,6 +96,7 @@ def solve(p: nlp.Problem, opts=None):
     dw_last = 0.0
     tol = o["tol"]
     acc_count = 0
+    best = None
     status = ST_MAXITER
 
     def err(gr, Jm, Jd, c, d, S, y, Z, mu_t):
@@ -123,6 +125,8 @@ def solve(p: nlp.Problem, opts=None):
             status = 0
             break
         if E0 <= o["acceptable_tol"]:
+            if best is None or E0 < best[0]:       # IPOPT stores the best acceptable point ...
+                best = (E0, X.copy(), S.copy(), y.copy(), Z.copy())
             acc_count += 1
             if acc_count >= o["acceptable_iter"]:
                 status = 1
@@ -291,6 +295,9 @@ def solve(p: nlp.Problem, opts=None):
         Z = np.clip(Z, mu / (ks * S), ks * mu / S)
         it += 1
 
+    if status < 0 and best is not None:            # ... and ends there when the run fails later on
+        E0, X, S, y, Z = best
+        status = ST_ACCEPTABLE
     x, u, T, lam, mu_d = nlp.unpack(p, lay, X)
     res.update(status=status, iters=it, X=X, S=S, y=y, Z=Z, x=x, u=u, T=T, lam=lam, mu_dual=mu_d,
                obj=nlp.objective_of(p, x, u, T), err=E0, mu=mu, hist=hist)

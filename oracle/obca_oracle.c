@@ -755,7 +755,7 @@ static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const
  * the interior-point loop (oracle/ipm_dense.py solve(), soc = False)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  iter_t it, tr;
+  iter_t it, tr, best; /* best: stored acceptable point */
   vals_t v, vt;
   stageqp_t q;
   blk_t blk[NS][OM];
@@ -814,7 +814,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   filt_t F;
   memset(&F, 0, sizeof(F));
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
-  double dw_last = 0.0, E0 = 0;
+  double dw_last = 0.0, E0 = 0, best_E0 = 1e300;
   int m_eq = 3 * N + (p->free_ ? 3 : 0) + 2 * p->nobs * (N + 1);
   int q_in = 4 * N + 8 * N + (p->free_ ? 2 : 0) + (p->has_term ? 3 : 0) + (p->R + 6 * p->nobs) * (N + 1);
 
@@ -860,6 +860,9 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     E0 = fmax(fmax(e1 / sd, e2), szmax / sc);
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
     if (E0 <= P->acceptable_tol) {
+      /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
+       * ("Solved To Acceptable Level") */
+      if (E0 < best_E0) { best_E0 = E0; w->best = *it; }
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
       acc_count = 0;
@@ -1038,6 +1041,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     }
     iter++;
   }
+  if (status < 0 && best_E0 < 1e300) { *it = w->best; status = OBCA_ST_ACCEPTABLE; E0 = best_E0; }
   *iters_out = iter;
   if (err_out) *err_out = E0;
   return status;
@@ -1049,7 +1053,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
 typedef struct {
   const obca_params* P;
   int batch, t0, t1;
-  const double *x0, *u0, *xref, *uref, *T_max, *term, *A, *b0, *db;
+  const double *x0, *u0, *xref, *uref, *T_max, *term, *Ts_inst, *A, *b0, *db;
   const int32_t* edge_ptr;
   int shared;
   double *x, *u, *lam, *mu, *T, *obj;
@@ -1069,7 +1073,7 @@ static void* worker(void* arg) {
     p.has_term = (P->mode == OBCA_MODE_FIXED_SET) || (P->mode == OBCA_MODE_FIXED_OBCA2 && P->has_term);
     p.stacked = (P->mode != OBCA_MODE_FREE);
     for (int i = 0; i <= no; ++i) p.eptr[i] = J->edge_ptr[i];
-    p.Ts = P->Ts; p.dmin = P->dmin;
+    p.Ts = J->Ts_inst ? J->Ts_inst[b] : P->Ts; p.dmin = P->dmin;
     double L = P->ego[0] + P->ego[2], W = P->ego[1] + P->ego[3];
     p.g[0] = L / 2; p.g[1] = W / 2; p.g[2] = L / 2; p.g[3] = W / 2;
     p.off = L / 2 - P->ego[2];
@@ -1100,7 +1104,8 @@ static void* worker(void* arg) {
 }
 
 int obca_oracle_solve(const obca_params* P, int batch, const double* x0, const double* u0, const double* xref,
-                      const double* uref, const double* T_max, const double* term, const int32_t* edge_ptr,
+                      const double* uref, const double* T_max, const double* term, const double* Ts_inst,
+                      const int32_t* edge_ptr,
                       const double* A, const double* b0, const double* db, int obstacles_shared, double* x, double* u,
                       double* lam, double* mu, double* T, double* obj, int32_t* status, int32_t* iters, int nthreads) {
   if (!P || P->N + 1 > NS || P->N < 1 || P->rows > RM || P->n_obs > OM) return OBCA_E_SIZE;
@@ -1113,7 +1118,7 @@ int obca_oracle_solve(const obca_params* P, int batch, const double* x0, const d
     job_t* J = &jobs[t];
     J->P = P; J->batch = batch;
     J->t0 = (int)((long long)batch * t / nthreads); J->t1 = (int)((long long)batch * (t + 1) / nthreads);
-    J->x0 = x0; J->u0 = u0; J->xref = xref; J->uref = uref; J->T_max = T_max; J->term = term;
+    J->x0 = x0; J->u0 = u0; J->xref = xref; J->uref = uref; J->T_max = T_max; J->term = term; J->Ts_inst = Ts_inst;
     J->A = A; J->b0 = b0; J->db = db; J->edge_ptr = edge_ptr; J->shared = obstacles_shared;
     J->x = x; J->u = u; J->lam = lam; J->mu = mu; J->T = T; J->obj = obj; J->status = status; J->iters = iters;
     if (nthreads == 1) worker(J);

@@ -49,3 +49,86 @@ def batch_arrays(b, init=_abi.INIT_WARM, **opts):
 
 def rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+# ---- oracle-backed stand-ins (CPU tests only): same interfaces as BatchSolver / obca, C oracle underneath ----------
+class OracleSolver:
+    """BatchSolver look-alike (``solve_host`` / ``params`` / ``close``) that runs the C oracle.  Lets the host-side
+    orchestration (closed loops, sharding) be tested without a GPU; never used by the product."""
+
+    def __init__(self, params, edge_ptr, max_batch, device=-1, nthreads=4):
+        self.params = params
+        self.edge_ptr = np.ascontiguousarray(edge_ptr, dtype=np.int32)
+        self.max_batch = max_batch
+        self.nthreads = nthreads
+        self.launches = 0
+
+    def solve_host(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, Ts=None):
+        from oracle import c_oracle
+        self.launches += 1
+        r = c_oracle.solve(self.params, x0, u0, xref, self.edge_ptr, A, b0, db, T_max=T_max, term=term, uref=uref,
+                           nthreads=self.nthreads, Ts=Ts)
+        if out is not None:
+            for k in r:
+                out[k][...] = r[k]
+            return out
+        return r
+
+    def close(self):
+        pass
+
+
+def oracle_obca():
+    """The product's ``obca`` class with its GPU context swapped for the oracle (monkeypatched BatchSolver)."""
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om
+
+    class _Obca(om.obca):
+        def _one(self, *a, **k):
+            saved = om.BatchSolver
+            om.BatchSolver = OracleSolver
+            try:
+                return super()._one(*a, **k)
+            finally:
+                om.BatchSolver = saved
+    return _Obca()
+
+
+# ---- host emulation of the CUDA kernel's phase code (tools/emu) -------------------------------------------------
+_emu = None
+
+
+def emu_lib():
+    """g++ build of tools/emu/obca_emu.cpp: csrc/obca_cta.cuh compiled for the host, block threads run serially."""
+    global _emu
+    if _emu is None:
+        import ctypes as C
+        import subprocess
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        src = os.path.join(root, "tools", "emu", "obca_emu.cpp")
+        hdr = os.path.join(root, "vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200", "csrc", "obca_cta.cuh")
+        lib = os.path.join(root, "tools", "emu", "libobca_emu.so")
+        if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", lib, src])
+        _emu = C.CDLL(lib)
+        _emu.obca_emu_solve.restype = C.c_int
+        _emu.obca_emu_solve.argtypes = [C.POINTER(_abi.ObcaParams)] + _abi.SOLVE_ARGTYPES_HOST + [C.c_int]
+    return _emu
+
+
+def emu_solve(params, a, Ts=None, uref=None):
+    import ctypes as C
+    L = emu_lib()
+    f64 = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64)
+    x0, u0, xref, T_max, term, A, b0, db, Ts, uref = map(f64, (a["x0"], a["u0"], a["xref"], a["T_max"], a["term"], a["A"],
+                                                                a["b0"], a["db"], Ts, uref))
+    B = x0.shape[0]; N, R, no = params.N, params.rows, params.n_obs
+    out = dict(x=np.zeros((B, N + 1, 3)), u=np.zeros((B, N, 2)), lam=np.zeros((B, N + 1, R)), mu=np.zeros((B, N + 1, 4 * no)),
+               T=np.zeros(B), obj=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
+    ep = np.ascontiguousarray(a["edge_ptr"], dtype=np.int32)
+    p = _abi.ptr
+    rc = L.obca_emu_solve(C.byref(params), B, p(x0), p(u0), p(xref), p(uref), p(T_max), p(term), p(Ts), p(ep, C.c_int32),
+                          p(A), p(b0), p(db), int(A.ndim == 2), p(out["x"]), p(out["u"]), p(out["lam"]), p(out["mu"]),
+                          p(out["T"]), p(out["obj"]), p(out["status"], C.c_int32), p(out["iters"], C.c_int32), 1)
+    if rc != 0:
+        raise RuntimeError("obca_emu_solve rc=%d" % rc)
+    return out

@@ -1,0 +1,85 @@
+"""The CUDA kernel's phase code (csrc/obca_cta.cuh) compiled for the HOST and run with the threads of a block
+executed one after the other (tools/emu), against the C oracle.  This checks the kernel's mapping (thread per
+(obstacle, stage) block + stage warp), its shared-memory layout, the cooperative Riccati sweep, the roll-out and the
+block reductions on a box without a GPU.  The GPU parity tests (-m gpu) run the same code on the device."""
+import numpy as np
+import pytest
+
+import obca_testlib as common
+from oracle import c_oracle
+from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import _abi, scenario as sc
+
+PRIMAL_RTOL, OBJ_RTOL = 1e-4, 1e-6
+
+
+def _oracle(prm, a, **kw):
+    return c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], T_max=a["T_max"],
+                          term=a["term"], nthreads=4, **kw)
+
+
+@pytest.mark.parametrize("name", common.FEASIBLE)
+@pytest.mark.parametrize("init", [_abi.INIT_ZERO, _abi.INIT_WARM])
+def test_fixtures(name, init):
+    prm, a, d = common.fixture_arrays(name, init=init)
+    c = _oracle(prm, a); e = common.emu_solve(prm, a)
+    assert (c["status"][0] >= 0) == (e["status"][0] >= 0)
+    if c["status"][0] < 0:
+        return
+    assert common.rel(e["x"], c["x"]) <= 1e-9 and common.rel(e["u"], c["u"]) <= 1e-9
+    assert abs(e["T"][0] - c["T"][0]) <= 1e-9 * max(1, c["T"][0])
+    assert abs(e["obj"][0] - c["obj"][0]) <= 1e-9 * max(1, abs(c["obj"][0]))
+    assert e["iters"][0] == c["iters"][0]
+
+
+def test_infeasible():
+    prm, a, d = common.fixture_arrays("demo1_N5_astar_free")
+    assert common.emu_solve(prm, a)["status"][0] < 0
+
+
+@pytest.mark.parametrize("cfg,B", [(2, 96), (3, 48), (5, 32)])
+def test_batches(cfg, B):
+    b = sc.make_batch(cfg, B)
+    prm, a = common.batch_arrays(b)
+    c = _oracle(prm, a); e = common.emu_solve(prm, a)
+    both = (c["status"] >= 0) & (e["status"] >= 0)
+    assert ((c["status"] >= 0) == (e["status"] >= 0)).mean() >= 0.97
+    assert both.sum() >= 0.5 * B
+    r = lambda x, y: np.abs(x - y).reshape(len(x), -1).max(1) / np.maximum(1, np.abs(y).reshape(len(y), -1).max(1))
+    assert (r(e["x"][both], c["x"][both]) <= PRIMAL_RTOL).all() and (r(e["u"][both], c["u"][both]) <= PRIMAL_RTOL).all()
+    assert (r(e["T"][both], c["T"][both]) <= PRIMAL_RTOL).all() and (r(e["obj"][both], c["obj"][both]) <= OBJ_RTOL).all()
+
+
+def test_per_instance_Ts_and_obstacles():
+    """per-instance sampling time and per-instance obstacle rows (the closed-loop batch needs both)"""
+    prm, a, d = common.fixture_arrays("demo9_N5_fixed")
+    B = 3
+    rep = lambda v: None if v is None else np.repeat(v, B, axis=0)
+    a3 = dict(a, x0=rep(a["x0"]), u0=rep(a["u0"]), xref=rep(a["xref"]), term=rep(a["term"]),
+              A=np.repeat(a["A"][None], B, 0), b0=np.repeat(a["b0"][None], B, 0), db=np.repeat(a["db"][None], B, 0))
+    Ts = np.array([2.0, 1.5, 2.5])
+    a3["db"] = a3["db"] * (Ts / 2.0)[:, None]          # obstacle displacement per step scales with the step length
+    c = c_oracle.solve(prm, a3["x0"], a3["u0"], a3["xref"], a3["edge_ptr"], a3["A"], a3["b0"], a3["db"], term=a3["term"], Ts=Ts)
+    e = common.emu_solve(prm, a3, Ts=Ts)
+    assert np.array_equal(c["status"] >= 0, e["status"] >= 0) and c["status"][0] >= 0 and c["status"][2] >= 0
+    ok = c["status"] >= 0
+    assert np.abs(e["x"][ok] - c["x"][ok]).max() <= 1e-8 and np.abs(e["obj"][ok] - c["obj"][ok]).max() <= 1e-10
+    assert abs(c["obj"][0] - 0.06455441) < 1e-7 and abs(c["obj"][2] - c["obj"][0]) > 1e-6
+
+
+def test_uref_tracking_obca2():
+    """obca2 free mode with a uref (obca.py:421-424): MODE_FREE_STACKED"""
+    mode, d = common.load_fixture("demo1_N6_astar_free")
+    N, nObs = int(d["N"]), int(d["nObs"])
+    ep, A, b0, db = _abi.pack_obstacles(_abi.MODE_FREE_STACKED, N, nObs, d["vObs"], d["AObs"], d["bObs"])
+    prm = _abi.make_params(_abi.MODE_FREE_STACKED, N, nObs, int(ep[-1]), float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]],
+                           d["xL"], d["xU"], d["uL"], d["uU"], float(d["dmin"]), d["ego"])
+    a = dict(x0=d["x0"].reshape(1, 3), u0=d["u0"].reshape(1, 2), xref=np.ascontiguousarray(d["xref"].T).reshape(1, N + 1, 3),
+             edge_ptr=ep, A=A, b0=b0, db=db, term=None,
+             T_max=np.array([_abi.tmax_of(d["xref"][:, N], d["x0"], N, d["uU"][0], float(d["Ts"]))]))
+    uref = np.tile(np.array([[0.5, 0.0]]), (1, N, 1))
+    c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], ep, A, b0, db, T_max=a["T_max"], uref=uref)
+    e = common.emu_solve(prm, a, uref=uref)
+    assert c["status"][0] >= 0 and e["status"][0] >= 0
+    assert np.abs(e["x"] - c["x"]).max() <= 1e-8 and abs(e["obj"][0] - c["obj"][0]) <= 1e-8
+    c0 = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], ep, A, b0, db, T_max=a["T_max"])
+    assert abs(c0["obj"][0] - c["obj"][0]) > 1e-6          # the uref term is really in the cost

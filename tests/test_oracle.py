@@ -1,0 +1,132 @@
+"""CPU tests of the oracle itself: the structured C restatement against the dense NumPy specification, KKT
+certificates, an independent SciPy cross-check, and the regression values recorded in tests/golden.
+
+PARITY UNPINNED: the reference ships no golden outputs and CasADi/IPOPT cannot be installed
+here, so these tests pin the oracle against (i) an independent dense implementation of the same algorithm,
+(ii) first-order optimality certificates evaluated with the NumPy restatement of the NLP, and (iii) SciPy's SLSQP
+on the same NLP.  Inputs are the reference's own (tests/golden/make_reference_fixtures.py ran its host code)."""
+import numpy as np
+import pytest
+
+import obca_testlib as common
+from oracle import c_oracle, ipm_dense, obca_nlp as nlp
+from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import _abi
+
+
+def _problem(name):
+    mode, d = common.load_fixture(name)
+    ts = d["terminal_set"] if "terminal_set" in d else None
+    return nlp.build_problem(mode, float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], int(d["N"]), d["x0"], d["xL"],
+                             d["xU"], d["uL"], d["uU"], d["xref"], int(d["nObs"]), d["vObs"], d["AObs"], d["bObs"],
+                             float(d["dmin"]), d["ego"], d["u0"], terminal_set=ts)
+
+
+def _c(name, init):
+    prm, a, d = common.fixture_arrays(name, init=init)
+    return prm, a, c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"],
+                                  T_max=a["T_max"], term=a["term"])
+
+
+@pytest.mark.parametrize("name,init", [("demo1_N6_astar_free", "zero"), ("demo1_N6_astar_free", "warm"),
+                                       ("demo1_N6_fixed", "warm"), ("demo9_N5_astar_free", "warm")])
+def test_c_oracle_matches_dense_spec(name, init):
+    p = _problem(name)
+    r = ipm_dense.solve(p, dict(init=init, max_iter=3000 if p.free else 1000, acceptable_tol=1e-6 if p.free else 1e-8))
+    _, _, c = _c(name, _abi.INIT_ZERO if init == "zero" else _abi.INIT_WARM)
+    assert r["status"] == 0 and c["status"][0] == 0
+    assert np.abs(r["x"].T - c["x"][0]).max() <= 1e-9
+    assert np.abs(r["u"].T - c["u"][0]).max() <= 1e-9
+    assert abs(r["T"] - c["T"][0]) <= 1e-9
+    assert abs(r["obj"] - c["obj"][0]) <= 1e-9 * max(1, abs(r["obj"]))
+
+
+@pytest.mark.parametrize("name", common.FEASIBLE)
+def test_kkt_certificate(name):
+    """primal feasibility, dual feasibility of a least-squares multiplier estimate and complementarity at the
+    oracle's solution, evaluated with the independent NumPy restatement of the NLP"""
+    p = _problem(name)
+    lay = nlp.Layout(p)
+    prm, a, c = _c(name, _abi.INIT_WARM)
+    assert c["status"][0] >= 0
+    X = np.zeros(lay.n)
+    N = p.N
+    for k in range(1, N + 1):
+        X[lay.iz(k):lay.iz(k) + 3] = c["x"][0, k]
+    X[lay.u:lay.u + 2 * N] = c["u"][0].reshape(-1)
+    if p.free:
+        X[lay.T] = c["T"][0]
+    for k in range(N + 1):
+        for i in range(p.nobs):
+            E = int(p.edges[i]); o = lay.eoff[i]
+            X[lay.lam[k, i]:lay.lam[k, i] + E] = c["lam"][0, k, o:o + E]
+            X[lay.mu[k, i]:lay.mu[k, i] + 4] = c["mu"][0, k, 4 * i:4 * i + 4]
+    ev = nlp.evaluate(p, lay, X, want=("f", "g", "c", "J", "d", "Jd"))
+    assert np.abs(ev["c"]).max() <= 1e-7                       # equalities
+    assert ev["d"].min() >= -1e-7                              # inequalities d(X) >= 0
+    assert abs(ev["f"] - c["obj"][0]) <= 1e-8 * max(1, abs(ev["f"]))
+    # multipliers: least squares on the active set, grad f + J^T y - Jd_A^T z = 0 with z >= 0
+    act = ev["d"] <= 1e-5
+    M = np.hstack([ev["J"].T, -ev["Jd"][act].T])
+    sol = np.linalg.lstsq(M, -ev["g"], rcond=None)[0]
+    res = M @ sol + ev["g"]
+    assert np.abs(res).max() <= 1e-4 * max(1.0, np.abs(ev["g"]).max())
+    z = sol[lay.m:]
+    assert z.min() >= -1e-3 * max(1.0, np.abs(z).max())
+
+
+def test_scipy_cross_check():
+    """SLSQP (independent SQP code) started near the oracle's solution converges to the same objective"""
+    from scipy.optimize import minimize
+    name = "demo1_N6_astar_free"
+    p = _problem(name)
+    lay = nlp.Layout(p)
+    r = ipm_dense.solve(p, dict(init="warm"))
+    X0 = r["X"].copy()
+    rng = np.random.default_rng(0)
+    X0[:lay.ntraj] += 1e-3 * rng.standard_normal(lay.ntraj)
+    f = lambda X: nlp.evaluate(p, lay, X, want=("f", "g"))["f"]
+    g = lambda X: nlp.evaluate(p, lay, X, want=("f", "g"))["g"]
+    cons = [dict(type="eq", fun=lambda X: nlp.evaluate(p, lay, X, want=("c", "J"))["c"],
+                 jac=lambda X: nlp.evaluate(p, lay, X, want=("c", "J"))["J"]),
+            dict(type="ineq", fun=lambda X: nlp.evaluate(p, lay, X, want=("d", "Jd"))["d"],
+                 jac=lambda X: nlp.evaluate(p, lay, X, want=("d", "Jd"))["Jd"])]
+    s = minimize(f, X0, jac=g, constraints=cons, method="SLSQP", options=dict(maxiter=200, ftol=1e-12))
+    assert abs(s.fun - r["obj"]) <= 1e-6 * abs(r["obj"]), (s.fun, r["obj"], s.message)
+    assert abs(s.x[lay.T] - r["T"]) <= 1e-4 * r["T"]
+
+
+def test_regression_values():
+    """objective / time scale recorded when the oracle was frozen (SURVEY Appendix C quotes the SLSQP values)"""
+    want = {"demo1_N6_astar_free": (4334.19729465, 20.378865), "demo2_N6_astar_free": (4007.99042717, 19.444444),
+            "demo9_N5_astar_free": (7396.13450351, 30.451764), "demo9_N6_astar_free": (7214.11928021, 27.474406),
+            "demo1_N6_fixed": (0.02347928, 1.0), "demo9_N5_fixed": (0.06455441, 1.0)}
+    for name, (obj, T) in want.items():
+        for init in (_abi.INIT_ZERO, _abi.INIT_WARM):
+            if name == "demo9_N5_fixed" and init == _abi.INIT_ZERO:
+                continue
+            _, _, c = _c(name, init)
+            assert c["status"][0] >= 0, (name, init)
+            assert abs(c["obj"][0] - obj) <= 1e-6 * max(1, abs(obj)), (name, init, c["obj"][0])
+            assert abs(c["T"][0] - T) <= 1e-5 * max(1, T)
+
+
+def test_infeasible_is_reported():
+    """demo1 with N = 5 puts the terminal pose in collision: feas must be False"""
+    _, _, c = _c("demo1_N5_astar_free", _abi.INIT_WARM)
+    assert c["status"][0] < 0
+
+
+def test_per_instance_Ts_equals_param_Ts():
+    prm, a, d = common.fixture_arrays("demo1_N6_astar_free")
+    c0 = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], T_max=a["T_max"])
+    c1 = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], T_max=a["T_max"],
+                        Ts=np.array([float(d["Ts"])]))
+    assert np.array_equal(c0["x"], c1["x"]) and np.array_equal(c0["obj"], c1["obj"])
+
+
+def test_objective_restatement():
+    """objective_of (obca.py:859-895 written out) equals the f the solver minimised"""
+    p = _problem("demo9_N6_astar_free")
+    _, _, c = _c("demo9_N6_astar_free", _abi.INIT_WARM)
+    f = nlp.objective_of(p, c["x"][0].T, c["u"][0].T, c["T"][0])
+    assert abs(f - c["obj"][0]) <= 1e-9 * abs(f)

@@ -1,0 +1,93 @@
+"""Multi-rank path on CPU: world_size-2 ``gloo`` run of shard -> solve -> single gather -> unpack.  The solver
+inside each rank is the oracle-backed stand-in (tests only); what is under test is the partitioning, the packed
+result layout and the one-collective gather of vehicle_motion_planning..._b200/sharding.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import obca_testlib as common
+from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import scenario as sc, sharding
+
+
+def test_shard_range_covers_batch():
+    for B in (1, 7, 8, 1000, 8192, 65536):
+        for G in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(G):
+                lo, hi, per = sharding.shard_range(B, r, G)
+                assert hi - lo <= per and 0 <= lo <= hi <= B
+                seen += list(range(lo, hi))
+            assert seen == list(range(B))
+
+
+def test_packed_outputs_views_alias_one_buffer():
+    p = sharding.PackedOutputs(5, 6, 10, 3)
+    assert p.views["x"].shape == (5, 7, 3) and p.views["lam"].shape == (5, 7, 10) and p.views["mu"].shape == (5, 7, 12)
+    assert p.views["status"].dtype == torch.int32 and p.views["status"].shape == (5,)
+    for k, v in p.views.items():
+        assert v.is_contiguous()
+        v.fill_(3 if v.dtype == torch.int32 else 1.5)
+    # every word of the buffer is covered by exactly the views (tail padding of the int32 pairs aside)
+    assert (p.buf[:p.offsets["status"]] == 1.5).all()
+    assert p.nbytes == p.words * 8
+    assert (p.views_of(p.buf)["iters"] == 3).all()
+
+
+class _TorchOracleSolver(common.OracleSolver):
+    """``solve`` with torch CPU tensors in / packed views out (what BatchSolver.solve does on the GPU)."""
+
+    def solve(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, stream=None, Ts=None):
+        n = lambda t: None if t is None else t.numpy()
+        r = self.solve_host(n(x0), n(u0), n(xref), n(A), n(b0), n(db), T_max=n(T_max), term=n(term))
+        for k, v in r.items():
+            out[k].copy_(torch.as_tensor(v))
+        return out
+
+
+def _worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = sc.make_batch(2, B)
+        prm, a = common.batch_arrays(b)
+        solver = _TorchOracleSolver(prm, a["edge_ptr"], B, nthreads=2)
+        out, packed = sharding.solve_sharded(solver, a, B, rank, world, "cpu", dst=0)
+        if rank == 0:
+            q.put({k: v.numpy().copy() for k, v in out.items()})
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+@pytest.mark.parametrize("B", [10, 13])
+def test_two_rank_gloo_equals_single_rank(B):
+    """sharded result == single-rank result bit for bit (instances are independent), ragged last shard included"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = sc.make_batch(2, B)
+    prm, a = common.batch_arrays(b)
+    ref = common.OracleSolver(prm, a["edge_ptr"], B).solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"],
+                                                                T_max=a["T_max"])
+    for k in ("x", "u", "lam", "mu", "T", "obj", "status", "iters"):
+        assert got[k].shape == ref[k].shape, k
+        assert np.array_equal(got[k], ref[k]), k

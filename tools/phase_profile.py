@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Developer tool (GPU box): per-phase cycle shares of the solver kernel.
+
+Builds csrc/libobca_b200_prof.so with -DOBCA_PROFILE (clock64 around every phase of the interior-point loop),
+runs one batch and prints cycles per phase summed over warps.  Not part of the product path or the bench.
+
+    python tools/phase_profile.py [cfg] [batch]
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import _lib  # noqa: E402
+
+PROF = os.path.join(_lib.CSRC, "libobca_b200_prof.so")
+
+
+def build():
+    cmd = ["nvcc"] + _lib.NVCC_FLAGS + ["-DOBCA_PROFILE", "-o", PROF] + _lib.SOURCES
+    subprocess.check_call(cmd, cwd=_lib.CSRC)
+
+
+def main():
+    cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    if not os.path.exists(PROF) or os.path.getmtime(PROF) < max(
+            os.path.getmtime(os.path.join(_lib.CSRC, f)) for f in _lib.SOURCES + _lib.HEADERS[:1]):
+        build()
+    _lib.LIB = PROF
+    _lib._stale = lambda: False
+    import torch
+    import obca_testlib as common
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om, scenario as sc
+    b = sc.make_batch(cfg, B)
+    prm, a = common.batch_arrays(b)
+    s = om.BatchSolver(prm, a["edge_ptr"], B)
+    L = _lib.lib()
+    t = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
+    dv = {k: t(a[k]) for k in ("x0", "u0", "xref", "A", "b0", "db", "T_max", "term")}
+    out = s.alloc_outputs(B, "cuda")
+    buf = (C.c_ulonglong * 16)()
+    for i in range(2):
+        L.obca_b200_prof_read(buf, 1)
+        s.solve(dv["x0"], dv["u0"], dv["xref"], dv["A"], dv["b0"], dv["db"], T_max=dv["T_max"], term=dv["term"], out=out)
+        torch.cuda.synchronize()
+    L.obca_b200_prof_read(buf, 0)
+    names = ["start", "assemble", "riccati", "rollout", "steps", "linesearch", "update", "exit"]
+    tot = float(sum(buf[:8]))
+    it = out["iters"].cpu().numpy()
+    print("cfg %d B %d kernel %.2f ms -> %.0f solves/s, iters mean %.1f max %d" % (cfg, B, s.last_kernel_ms(), B / s.last_kernel_ms() * 1e3, it.mean(), it.max()))
+    for n, v in zip(names, buf[:8]):
+        print("  %-10s %6.2f %%  %10.0f cycles/iteration-block" % (n, 100.0 * v / tot, v / max(1, it.sum())))
+
+
+if __name__ == "__main__":
+    main()

@@ -121,5 +121,5 @@ def ptr(a, ctype=C.c_double):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
-SOLVE_ARGTYPES_HOST = [C.c_int] + [C.POINTER(C.c_double)] * 6 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 3 + \
+SOLVE_ARGTYPES_HOST = [C.c_int] + [C.POINTER(C.c_double)] * 7 + [C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 3 + \
     [C.c_int] + [C.POINTER(C.c_double)] * 6 + [C.POINTER(C.c_int32)] * 2

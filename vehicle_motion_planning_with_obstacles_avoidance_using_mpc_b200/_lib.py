@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libobca_b200.so")
 SOURCES = ["obca_b200.cu"]
-HEADERS = ["obca_kernel.cuh", "obca_phases.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
+HEADERS = ["obca_cta.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -70,10 +70,10 @@ def lib():
     L.obca_b200_strerror.argtypes = [C.c_int]
     vp = C.c_void_p
     L.obca_b200_solve.restype = C.c_int
-    L.obca_b200_solve.argtypes = [vp, C.c_int] + [vp] * 6 + [C.POINTER(C.c_int32)] + [vp] * 3 + [C.c_int] + [vp] * 8 + [vp]
+    L.obca_b200_solve.argtypes = [vp, C.c_int] + [vp] * 7 + [C.POINTER(C.c_int32)] + [vp] * 3 + [C.c_int] + [vp] * 8 + [vp]
     L.obca_b200_solve_host.restype = C.c_int
     L.obca_b200_solve_host.argtypes = [vp] + _abi.SOLVE_ARGTYPES_HOST
-    if L.obca_b200_abi_version() != 1:
+    if L.obca_b200_abi_version() != 2:
         raise RuntimeError("libobca_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -1,0 +1,1551 @@
+// obca_cta.cuh - batched OBCA-MPC interior-point solver for sm_100a, one thread block per NLP instance.
+//
+// The NLP is the reference's (src/obca.py: obca_mpc4 828-1071, obca_mpc6 1361-1562, obca_mpc8 1564-1758,
+// obca2 338-629) in the compact variable set of SURVEY.md Appendix A; the algorithm is the primal-dual
+// interior-point method specified by oracle/ipm_dense.py.  Nothing here is shared with oracle/.
+//
+// Mapping (why: ncu on the first, warp-per-instance kernel showed 80 % of the issue slots lost to instruction
+// fetch and the rest to L2 latency on a 73 KB per-warp workspace; see profiles/ and DESIGN.md):
+//   * thread t < nb = n_obs*(N+1) owns the OBCA dual block of (obstacle i = t/(N+1), stage k = t%(N+1)):
+//     lambda, mu, their slacks and multipliers live in REGISTERS for the whole solve
+//   * the last warp is the "stage warp": lane k owns stage k's pose/input/bound state in SHARED memory, and
+//     the 32 lanes share the entries of the 8x8 stage matrices during the (sequential) Riccati sweep
+//   * everything an iteration touches is on-chip; HBM is read once (inputs) and written once (results)
+// Per iteration:  block assemble (square-root 5x5 factorisation per thread, Schur complement onto the 3x3 pose
+// block) || stage assemble -> combine -> Riccati (lanes = matrix entries) -> roll-out -> block/stage steps,
+// fraction to the boundary -> filter line search -> update.  Control flow is uniform across the block; all
+// decisions are taken on block-reduced scalars.
+//
+// The file compiles for the device (nvcc) and for the host (g++): tools/emu runs the very same phase code
+// with the threads of a block executed one after the other, so the kernel logic is testable without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/obca_b200.h"
+
+#if defined(__CUDACC__)
+#define OB_HD __host__ __device__ __forceinline__
+#else
+#define OB_HD inline
+#endif
+
+namespace obca {
+
+constexpr int FILT_MAX = 32;
+constexpr double SIG_MIN = 1e-8;  // primal regularisation of the OBCA duals (curvature floor of a sign row)
+constexpr int NPART = 12;
+constexpr int OBCA_ST_STORED = 100;  // internal: the result arrays already hold the (acceptable) answer         // per-thread partial results handed to the block reductions
+
+struct KParams {
+  obca_params P;
+  int32_t eptr[OBCA_MAX_OBS + 1];
+  int32_t batch, shared_obs, free_, has_term, stacked;
+  const double *x0, *u0, *xref, *uref, *Tmax, *term, *Ts_inst, *A, *b0, *db;
+  double *x, *u, *lam, *mu, *T, *obj;
+  int32_t *status, *iters;
+  unsigned int* counter;  // persistent-block work queue
+};
+
+// block-uniform scalar state of one instance (shared memory)
+struct Glob {
+  double T, STb[2], ZTb[2], Stm[3], Ztm[3], yt[3];
+  double dT, dSTb[2], dStm[3], dyt[3];
+  double Tmax, x0[3], u0[2], term[3];
+  double Ts, off, g[4];
+  double fth[FILT_MAX], fph[FILT_MAX];
+  int bad;
+};
+
+// shared-memory map of one instance; stage arrays are [element][stage], block arrays [element][block]
+struct Sm {
+  int N, S1, no, R, nb, T, nwarps, has_uref;
+  double *Z, *U, *YD, *SXY, *ZXY, *SUB, *ZUB;
+  double *DZ, *DU, *DYD, *DSXY, *DSUB;
+  double *H, *RA, *RB, *CD, *GF, *GL, *DYN;
+  double *K, *KAP, *PM, *PV, *XI;
+  double *ETA, *DLAM, *DMU, *DYE, *DSN, *DSD, *EX;
+  double *A, *B0, *DB, *XREF, *UREF;
+  double *RIC, *RED;
+  Glob* G;
+  OB_HD double& st(double* p, int e, int k) const { return p[e * S1 + k]; }
+  OB_HD double& bl(double* p, int e, int t) const { return p[e * nb + t]; }
+};
+
+constexpr int EX_N = 16;   // per block: G(6) Ga(3) Gb(3) gLz(3) h22(1)
+constexpr int RIC_N = 64;
+
+OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int has_uref) {
+  const int S1 = N + 1, nb = no * S1;
+  s.N = N; s.S1 = S1; s.no = no; s.R = R; s.nb = nb; s.nwarps = nwarps; s.T = 32 * nwarps; s.has_uref = has_uref;
+  size_t o = 0;
+  auto take = [&](size_t n) { double* p = base ? base + o : nullptr; o += n; return p; };
+  s.Z = take(3 * S1); s.U = take(2 * S1); s.YD = take(3 * S1);
+  s.SXY = take(4 * S1); s.ZXY = take(4 * S1); s.SUB = take(8 * S1); s.ZUB = take(8 * S1);
+  s.DZ = take(3 * S1); s.DU = take(2 * S1); s.DYD = take(3 * S1); s.DSXY = take(4 * S1); s.DSUB = take(8 * S1);
+  s.H = take(36 * S1); s.RA = take(8 * S1);   // H|RA (44 S1) is re-used by the roll-out as ACL(36)|CCL(6)
+  s.RB = take(8 * S1); s.CD = take(3 * S1); s.GF = take(8 * S1); s.GL = take(8 * S1); s.DYN = take(8 * S1);
+  s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1); s.XI = take(6 * S1);
+  s.ETA = take(25 * (size_t)nb); s.DLAM = take((size_t)R * S1); s.DMU = take(4 * (size_t)nb); s.DYE = take(2 * (size_t)nb);
+  s.DSN = take(nb); s.DSD = take(nb); s.EX = take(EX_N * (size_t)nb);
+  s.A = take(2 * R); s.B0 = take(R); s.DB = take(R); s.XREF = take(3 * S1); s.UREF = take(has_uref ? 2 * N : 0);
+  s.RIC = take(RIC_N); s.RED = take((size_t)NPART * nwarps);
+  s.G = (Glob*)(base ? base + o : nullptr); o += (sizeof(Glob) + 7) / 8;
+  return o;  // doubles
+}
+
+// registers of a block thread: the OBCA duals of one (stage, obstacle) pair
+template <int EMAX>
+struct BlockRegs {
+  double lam[EMAX], Sl[EMAX], Zl[EMAX];
+  double mu[4], Sm_[4], Zm[4];
+  double ye[2], Sn, Zn, Sd, Zd;
+};
+
+OB_HD void ob_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+
+// 5x5 square-root factor R^T (lower triangular, packed) with Givens row insertion
+struct Tri5 {
+  double l[15];
+  OB_HD void zero() {
+#pragma unroll
+    for (int i = 0; i < 15; ++i) l[i] = 0.0;
+  }
+  OB_HD double& at(int r, int c) { return l[r * (r + 1) / 2 + c]; }
+  OB_HD void insert(double row[5]) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      double a = at(c, c), b = row[c];
+      if (b != 0.0) {
+        double rr = sqrt(a * a + b * b), cs = a / rr, sn = b / rr;
+        at(c, c) = rr;
+#pragma unroll
+        for (int q = c + 1; q < 5; ++q) {
+          double u = at(q, c), w = row[q];
+          at(q, c) = cs * u + sn * w;
+          row[q] = -sn * u + cs * w;
+        }
+      }
+    }
+  }
+  OB_HD bool finish() {
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      if (at(a, a) < 0) {
+#pragma unroll
+        for (int q = a; q < 5; ++q) at(q, a) = -at(q, a);
+      }
+      ok = ok && (at(a, a) > 0) && isfinite(at(a, a));
+    }
+    return ok;
+  }
+  OB_HD void solve(const double r[5], double x[5]) {  // (L L^T) x = r
+    double t[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      double s = r[i];
+#pragma unroll
+      for (int q = 0; q < i; ++q) s -= at(i, q) * t[q];
+      t[i] = s / at(i, i);
+    }
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      double s = t[i];
+#pragma unroll
+      for (int q = i + 1; q < 5; ++q) s -= at(q, i) * x[q];
+      x[i] = s / at(i, i);
+    }
+  }
+};
+
+struct BlkGeo {  // geometry of one (stage, obstacle) block at the current point
+  double a1, a2, ct, st, tx, ty;
+};
+
+OB_HD int symi(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// statistics of one inequality (slack S, multiplier Z, value d); returns sigma and the mu-split of the
+// step-form right-hand side  t - Z = mu * ta + tb
+struct IneqAcc {
+  double th = 0, lg = 0, cmax = 0, sumz = 0, szmax = 0, szmin = 1e300;
+  OB_HD void add(double S, double Z, double d, double& sig, double& ta, double& tb) {
+    double rd = d - S;
+    sig = Z / S; ta = 1.0 / S; tb = -Z - sig * rd;
+    th += fabs(rd); cmax = fmax(cmax, fabs(rd)); lg += log(S); sumz += Z;
+    double sz = S * Z; szmax = fmax(szmax, sz); szmin = fmin(szmin, sz);
+  }
+};
+
+// partial-result slots (sum / max / min groups are reduced separately)
+enum { PS_F = 0, PS_TH, PS_LG, PS_SUMY, PS_SUMZ, PS_GT, PM_E1, PM_E2, PM_SZMAX, PM_CT, PM_BAD, PN_SZMIN };  // assemble
+enum { QS_DPHI = 0, QN_AMAX = 1, QN_AZ = 2 };                                                                 // backsub
+
+struct StageVals {
+  double f, cd[3], dxy[4], dub[8];
+};
+
+// ======================================================================================================
+// The solver: all phase code.  `Exec` supplies the execution model (device block or host emulation).
+// ======================================================================================================
+template <int EMAX>
+struct Solver {
+  const KParams& kp;
+  const obca_params& P;
+  Sm sm;
+  int N, S1, no, nb;
+  bool free_, has_term, stacked;
+
+  OB_HD Solver(const KParams& kp_, const Sm& sm_)
+      : kp(kp_), P(kp_.P), sm(sm_), N(kp_.P.N), S1(kp_.P.N + 1), no(kp_.P.n_obs), nb(kp_.P.n_obs * (kp_.P.N + 1)),
+        free_(kp_.free_ != 0), has_term(kp_.has_term != 0), stacked(kp_.stacked != 0) {}
+
+  // ---- thread roles
+  OB_HD bool is_block(int tid) const { return tid < nb; }
+  OB_HD int stage_lane(int tid) const { return tid - 32 * (sm.nwarps - 1); }   // >= 0 in the stage warp
+  OB_HD bool is_stage(int tid) const { int l = stage_lane(tid); return l >= 0 && l <= N; }
+
+  OB_HD double bk(int k, int r) const { return sm.B0[r] + (stacked ? k * sm.DB[r] : 0.0); }
+  OB_HD const double* xref(int k) const { return sm.XREF + 3 * k; }
+
+  OB_HD void row_y(const BlkGeo& b, int k, int r0, int E, int j, double yv[5]) const {
+    const Glob& G = *sm.G;
+    if (j < E) {
+      int r = r0 + j;
+      double A0 = sm.A[2 * r], A1 = sm.A[2 * r + 1];
+      yv[0] = A0; yv[1] = A1;
+      yv[2] = b.tx * A0 + b.ty * A1 - bk(k, r);
+      yv[3] = b.ct * A0 + b.st * A1;
+      yv[4] = -b.st * A0 + b.ct * A1;
+    } else {
+      int m = j - E;
+      yv[0] = 0; yv[1] = 0; yv[2] = -G.g[m];
+      yv[3] = (m == 0) ? 1.0 : (m == 2) ? -1.0 : 0.0;
+      yv[4] = (m == 1) ? 1.0 : (m == 3) ? -1.0 : 0.0;
+    }
+  }
+  // Cn^-1 v = (v - kn a (a.v)) / (2 Zn)
+  OB_HD static void cn_inv(const BlkGeo& b, double ci0, double ci1, const double v[2], double o[2]) {
+    double av = b.a1 * v[0] + b.a2 * v[1];
+    o[0] = (v[0] - ci1 * b.a1 * av) * ci0;
+    o[1] = (v[1] - ci1 * b.a2 * av) * ci0;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // instance load (all threads): inputs HBM -> shared, once
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void load(int tid, size_t b, bool load_obs) const {
+    Glob& G = *sm.G;
+    const int T = sm.T, R = sm.R;
+    for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = kp.xref[b * 3 * S1 + i];
+    if (sm.has_uref)
+      for (int i = tid; i < 2 * N; i += T) sm.UREF[i] = kp.uref[b * 2 * N + i];
+    if (load_obs) {
+      const size_t ob = kp.shared_obs ? 0 : b;
+      for (int i = tid; i < 2 * R; i += T) sm.A[i] = kp.A[ob * 2 * R + i];
+      for (int i = tid; i < R; i += T) {
+        sm.B0[i] = kp.b0[ob * R + i];
+        sm.DB[i] = kp.db ? kp.db[ob * R + i] : 0.0;
+      }
+    }
+    if (tid == 0) {
+      for (int j = 0; j < 3; ++j) G.x0[j] = kp.x0[3 * b + j];
+      for (int j = 0; j < 2; ++j) G.u0[j] = kp.u0[2 * b + j];
+      G.Tmax = (free_ && kp.Tmax) ? kp.Tmax[b] : 1.0;
+      G.Ts = kp.Ts_inst ? kp.Ts_inst[b] : P.Ts;
+      G.T = 1.0; G.dT = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        G.term[j] = (has_term && kp.term) ? kp.term[3 * b + j] : 0.0;
+        G.Stm[j] = G.Ztm[j] = 1.0; G.dStm[j] = 0.0; G.yt[j] = 0.0; G.dyt[j] = 0.0;
+      }
+      G.STb[0] = G.STb[1] = G.ZTb[0] = G.ZTb[1] = 1.0; G.dSTb[0] = G.dSTb[1] = 0.0;
+      const double Lc = P.ego[0] + P.ego[2], Wc = P.ego[1] + P.ego[3];
+      G.g[0] = Lc / 2; G.g[1] = Wc / 2; G.g[2] = Lc / 2; G.g[3] = Wc / 2;
+      G.off = Lc / 2 - P.ego[2];
+      G.bad = 0;
+    }
+  }
+
+  // pose of the start-point construction: x0 at stage 0, the reference window elsewhere
+  OB_HD void pp_of(int k, double pp[3]) const {
+    const Glob& G = *sm.G;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) pp[j] = (k == 0) ? G.x0[j] : xref(k)[j];
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // start point (oracle/obca_nlp.py start_point): init 0 = reference (all zero, T = 1: obca.py:856),
+  // 1 = poses from xref, 2 = A* warm start.   Pass 1: poses + path length partial.
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void start_a(int tid, double* part) const {
+    part[0] = 0.0;
+    if (!is_stage(tid)) return;
+    const int k = stage_lane(tid);
+    double pp[3];
+    pp_of(k, pp);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      sm.st(sm.Z, j, k) = (k == 0) ? pp[j] : (P.init >= OBCA_INIT_XREF ? pp[j] : 0.0);
+      sm.st(sm.YD, j, k) = 0.0;
+    }
+    if (P.init == OBCA_INIT_WARM && k < N) {
+      double pn[3];
+      pp_of(k + 1, pn);
+      part[0] = sqrt((pn[0] - pp[0]) * (pn[0] - pp[0]) + (pn[1] - pp[1]) * (pn[1] - pp[1]));
+    }
+  }
+  OB_HD double start_T(double len) const {
+    const Glob& G = *sm.G;
+    if (P.init != OBCA_INIT_WARM || !free_) return 1.0;
+    double T0 = len / (N * P.uU[0] * G.Ts);
+    return fmin(fmax(T0, 1.0), fmax(G.Tmax, P.T_min));
+  }
+  // Pass 2: inputs (stage lanes) and duals (block threads)
+  OB_HD void start_b(int tid, BlockRegs<EMAX>& br, double T0) const {
+    Glob& G = *sm.G;
+    if (is_stage(tid)) {
+      const int k = stage_lane(tid);
+      double u[2] = {0, 0};
+      if (P.init == OBCA_INIT_WARM && k < N) {
+        const double h = (free_ ? T0 : 1.0) * G.Ts;
+        double pp[3], pn[3];
+        pp_of(k, pp); pp_of(k + 1, pn);
+        double dth = pn[2] - pp[2] + M_PI;
+        dth = dth - 2 * M_PI * floor(dth / (2 * M_PI)) - M_PI;
+        double fwd = cos(pp[2]) * (pn[0] - pp[0]) + sin(pp[2]) * (pn[1] - pp[1]);
+        u[0] = fmin(fmax(fwd / h, P.uL[0]), P.uU[0]);
+        u[1] = fmin(fmax(dth / h, P.uL[1]), P.uU[1]);
+      }
+      sm.st(sm.U, 0, k) = u[0]; sm.st(sm.U, 1, k) = u[1];
+      if (k == 0) { G.T = T0; G.yt[0] = G.yt[1] = G.yt[2] = 0.0; }
+    }
+    if (is_block(tid)) {
+      const int i = tid / S1, k = tid % S1;
+      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+#pragma unroll
+      for (int j = 0; j < EMAX; ++j) br.lam[j] = 0.0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) br.mu[q] = 0.0;
+      br.ye[0] = br.ye[1] = 0.0;
+      if (P.init == OBCA_INIT_WARM) {
+        double pp[3];
+        pp_of(k, pp);
+        const double ct = cos(pp[2]), st = sin(pp[2]);
+        const double tx = pp[0] + G.off * ct, ty = pp[1] + G.off * st;
+        int jb = -1;
+        double best = -1e300, nbst = 1;
+#pragma unroll
+        for (int j = 0; j < EMAX; ++j) {
+          if (j < E) {
+            const int r = r0 + j;
+            const double A0 = sm.A[2 * r], A1 = sm.A[2 * r + 1];
+            const double nr = sqrt(A0 * A0 + A1 * A1);
+            const double sep = (A0 * tx + A1 * ty - bk(k, r)) / nr;
+            if (sep > best) { best = sep; jb = j; nbst = nr; }
+          }
+        }
+        if (jb >= 0) {
+          const double l = 0.9 / nbst;
+#pragma unroll
+          for (int j = 0; j < EMAX; ++j)
+            if (j == jb) br.lam[j] = l;
+          const double a1 = sm.A[2 * (r0 + jb)] * l, a2 = sm.A[2 * (r0 + jb) + 1] * l;
+          const double r1 = -(ct * a1 + st * a2), r2 = -(-st * a1 + ct * a2);
+          br.mu[0] = fmax(r1, 0.0); br.mu[1] = fmax(r2, 0.0); br.mu[2] = fmax(-r1, 0.0); br.mu[3] = fmax(-r2, 0.0);
+        }
+      }
+    }
+  }
+
+  // values of the stage's own (non-obstacle) constraints at a point
+  OB_HD void stage_vals(int k, const double z[3], const double u[2], const double up[2], const double zn[3], double T,
+                        StageVals& o) const {
+    const Glob& G = *sm.G;
+    const double h = T * G.Ts;
+    const double* M = (k < N) ? P.Q : P.P;
+    double e[3], f = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) e[j] = z[j] - xref(k)[j];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) f += e[a] * M[3 * a + b] * e[b];
+    if (k < N) {
+      double uu[2] = {u[0], u[1]};
+      if (sm.has_uref) { uu[0] -= sm.UREF[2 * k]; uu[1] -= sm.UREF[2 * k + 1]; }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) f += uu[a] * P.R1[2 * a + b] * uu[b];
+      if (k >= 1) {
+        double du[2] = {u[0] - up[0], u[1] - up[1]}, s = 0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) s += du[a] * P.R2[2 * a + b] * du[b];
+        f += s / (h * h);
+      }
+      double st, ct;
+      ob_sincos(z[2], &st, &ct);
+      o.cd[0] = z[0] + h * u[0] * ct - zn[0];
+      o.cd[1] = z[1] + h * u[0] * st - zn[1];
+      o.cd[2] = z[2] + h * u[1] - zn[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double ga = (up[j] - u[j]) / h;
+        o.dub[j] = u[j] - P.uL[j];
+        o.dub[2 + j] = P.uU[j] - u[j];
+        o.dub[4 + j] = ga + P.acc_max[j];
+        o.dub[6 + j] = P.acc_max[j] - ga;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      o.dxy[j] = z[j] - P.xL[j];
+      o.dxy[2 + j] = P.xU[j] - z[j];
+    }
+    if (k == 0 && free_) f += (N + 1) * (P.time_cost[0] * T + P.time_cost[1] * T * T);
+    o.f = f;
+  }
+
+  // stage k's pose / inputs and neighbours at step length a along the current direction (a = 0: the iterate)
+  OB_HD void stage_point(int k, double a, double z[3], double u[2], double up[2], double zn[3]) const {
+    const Glob& G = *sm.G;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      z[j] = sm.st(sm.Z, j, k) + ((a != 0.0 && k >= 1) ? a * sm.st(sm.DZ, j, k) : 0.0);
+      zn[j] = (k < N) ? sm.st(sm.Z, j, k + 1) + ((a != 0.0) ? a * sm.st(sm.DZ, j, k + 1) : 0.0) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      u[j] = sm.st(sm.U, j, k) + ((a != 0.0) ? a * sm.st(sm.DU, j, k) : 0.0);
+      up[j] = (k == 0) ? G.u0[j] : sm.st(sm.U, j, k - 1) + ((a != 0.0) ? a * sm.st(sm.DU, j, k - 1) : 0.0);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // slack / multiplier initialisation: S = max(d(x0), bound_push), Z = 1
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void init_slacks(int tid, BlockRegs<EMAX>& br) const {
+    Glob& G = *sm.G;
+    const double bp = P.bound_push;
+    const double T = free_ ? G.T : 1.0;
+    if (is_stage(tid)) {
+      const int k = stage_lane(tid);
+      double z[3], u[2], up[2], zn[3];
+      stage_point(k, 0.0, z, u, up, zn);
+      StageVals sv;
+      stage_vals(k, z, u, up, zn, T, sv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sm.st(sm.SXY, j, k) = fmax(sv.dxy[j], bp); sm.st(sm.ZXY, j, k) = 1.0; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm.st(sm.SUB, j, k) = (k < N) ? fmax(sv.dub[j], bp) : 1.0; sm.st(sm.ZUB, j, k) = 1.0; }
+      if (k == 0 && free_) {
+        G.STb[0] = fmax(T - P.T_min, bp); G.STb[1] = fmax(G.Tmax - T, bp);
+        G.ZTb[0] = G.ZTb[1] = 1.0;
+      }
+      if (k == N && has_term) {
+        G.Stm[0] = fmax(z[0] - G.term[0], bp); G.Stm[1] = fmax(z[1] - G.term[1], bp); G.Stm[2] = fmax(G.term[2] - z[1], bp);
+        G.Ztm[0] = G.Ztm[1] = G.Ztm[2] = 1.0;
+      }
+    }
+    if (is_block(tid)) {
+      const int i = tid / S1, k = tid % S1;
+      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
+      double st, ct;
+      ob_sincos(z2, &st, &ct);
+      const double tx = z0 + G.off * ct, ty = z1 + G.off * st;
+      double a1 = 0, a2 = 0, bl = 0;
+#pragma unroll
+      for (int j = 0; j < EMAX; ++j) {
+        if (j < E) {
+          const int r = r0 + j;
+          const double l = br.lam[j];
+          a1 += sm.A[2 * r] * l; a2 += sm.A[2 * r + 1] * l; bl += bk(k, r) * l;
+          br.Sl[j] = fmax(l, bp); br.Zl[j] = 1.0;
+        } else { br.Sl[j] = 1.0; br.Zl[j] = 1.0; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { br.Sm_[q] = fmax(br.mu[q], bp); br.Zm[q] = 1.0; }
+      br.Sn = fmax(1.0 - a1 * a1 - a2 * a2, bp); br.Zn = 1.0;
+      br.Sd = fmax(-(G.g[0] * br.mu[0] + G.g[1] * br.mu[1] + G.g[2] * br.mu[2] + G.g[3] * br.mu[3]) + tx * a1 + ty * a2 - bl - P.dmin, bp);
+      br.Zd = 1.0;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // assemble, stage part (lane k): everything that does not depend on the barrier parameter; right-hand
+  // sides are split as  mu * (a part) + (b part)  so that mu can be chosen from this pass's own error.
+  // Leaves H, RA, RB (without the Lagrangian gradient), GL, GF, CD, DYN in shared memory.
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void assemble_stage(int k, double* part) const {
+    const Glob& G = *sm.G;
+    double z[3], u[2], up[2], zn[3], yd[3], ydm[3];
+    stage_point(k, 0.0, z, u, up, zn);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { yd[j] = sm.st(sm.YD, j, k); ydm[j] = (k >= 1) ? sm.st(sm.YD, j, k - 1) : 0.0; }
+    const double T = free_ ? G.T : 1.0, h = T * G.Ts;
+    double st, ct;
+    ob_sincos(z[2], &st, &ct);
+    double H[36], ra[8], rb[8], gL[8], gf[8];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) H[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ra[i] = rb[i] = gL[i] = gf[i] = 0; }
+#define HH(a, b) H[((a) >= (b)) ? ((a) * ((a) + 1) / 2 + (b)) : ((b) * ((b) + 1) / 2 + (a))]
+    StageVals sv;
+    stage_vals(k, z, u, up, zn, T, sv);
+    IneqAcc acc;
+    double sumy = 0, ceq_th = 0, ceq_max = 0, ctmax = 0;
+    // (1) tracking cost
+    {
+      const double* M = (k < N) ? P.Q : P.P;
+      double e[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) e[j] = z[j] - xref(k)[j];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          double m = M[3 * a + b] + M[3 * b + a];
+          s += m * e[b];
+          if (b <= a) HH(a, b) += m;
+        }
+        gf[a] += s;
+      }
+    }
+    double dyn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (k < N) {
+      // (2) input cost
+      double uu[2] = {u[0], u[1]};
+      if (sm.has_uref) { uu[0] -= sm.UREF[2 * k]; uu[1] -= sm.UREF[2 * k + 1]; }
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        double s = 0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          double m = P.R1[2 * a + b] + P.R1[2 * b + a];
+          s += m * uu[b];
+          if (b <= a) HH(6 + a, 6 + b) += m;
+        }
+        gf[6 + a] += s;
+      }
+      // (3) acceleration cost between u_{k-1} (state 3,4) and u_k, k >= 1 (the t == 0 term is identically 0)
+      if (k >= 1) {
+        double du[2] = {u[0] - up[0], u[1] - up[1]}, qv[2], Aacc = 0;
+        const double ih2 = 1.0 / (h * h);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          qv[a] = 0;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) qv[a] += 0.5 * (P.R2[2 * a + b] + P.R2[2 * b + a]) * du[b];
+          Aacc += du[a] * qv[a];
+        }
+        Aacc *= ih2;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          gf[6 + a] += 2 * qv[a] * ih2;
+          gf[3 + a] -= 2 * qv[a] * ih2;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            double m = (P.R2[2 * a + b] + P.R2[2 * b + a]) * ih2;
+            if (b <= a) { HH(6 + a, 6 + b) += m; HH(3 + a, 3 + b) += m; }
+            HH(6 + a, 3 + b) -= m;
+          }
+          if (free_) {
+            double c = 4 * qv[a] * ih2 / T;
+            HH(6 + a, 5) -= c; HH(5, 3 + a) += c;
+          }
+        }
+        if (free_) { gf[5] -= 2 * Aacc / T; HH(5, 5) += 6 * Aacc / (T * T); }
+      }
+      // (5) dynamics: Hessian-of-Lagrangian terms and J^T y
+      const double vv = u[0], ww = u[1];
+      const double fth0 = -h * vv * st, fth1 = h * vv * ct;
+      const double fT0 = free_ ? G.Ts * vv * ct : 0.0, fT1 = free_ ? G.Ts * vv * st : 0.0, fT2 = free_ ? G.Ts * ww : 0.0;
+      dyn[0] = fth0; dyn[1] = fth1; dyn[2] = h * ct; dyn[3] = h * st; dyn[4] = h; dyn[5] = fT0; dyn[6] = fT1; dyn[7] = fT2;
+      HH(2, 2) += h * vv * (-yd[0] * ct - yd[1] * st);
+      HH(6, 2) += h * (-yd[0] * st + yd[1] * ct);
+      if (free_) {
+        HH(5, 2) += G.Ts * vv * (-yd[0] * st + yd[1] * ct);
+        HH(6, 5) += G.Ts * (yd[0] * ct + yd[1] * st);
+        HH(7, 5) += G.Ts * yd[2];
+      }
+      gL[0] += yd[0]; gL[1] += yd[1]; gL[2] += yd[2] + fth0 * yd[0] + fth1 * yd[1];
+      gL[6] += h * ct * yd[0] + h * st * yd[1]; gL[7] += h * yd[2];
+      gL[5] += fT0 * yd[0] + fT1 * yd[1] + fT2 * yd[2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { sumy += fabs(yd[j]); ceq_th += fabs(sv.cd[j]); ceq_max = fmax(ceq_max, fabs(sv.cd[j])); }
+      // (7) input bounds and acceleration rows
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double sg, ta, tb;
+        const double Z0 = sm.st(sm.ZUB, j, k), Z2 = sm.st(sm.ZUB, 2 + j, k);
+        acc.add(sm.st(sm.SUB, j, k), Z0, sv.dub[j], sg, ta, tb);
+        HH(6 + j, 6 + j) += sg; ra[6 + j] += ta; rb[6 + j] += tb; gL[6 + j] -= Z0;
+        acc.add(sm.st(sm.SUB, 2 + j, k), Z2, sv.dub[2 + j], sg, ta, tb);
+        HH(6 + j, 6 + j) += sg; ra[6 + j] -= ta; rb[6 + j] -= tb; gL[6 + j] += Z2;
+        double ga = (up[j] - u[j]) / h;
+        double s4, ta4, tb4, s6, ta6, tb6;
+        const double Z4 = sm.st(sm.ZUB, 4 + j, k), Z6 = sm.st(sm.ZUB, 6 + j, k);
+        acc.add(sm.st(sm.SUB, 4 + j, k), Z4, sv.dub[4 + j], s4, ta4, tb4);
+        acc.add(sm.st(sm.SUB, 6 + j, k), Z6, sv.dub[6 + j], s6, ta6, tb6);
+        const double jv[3] = {(k >= 1) ? 1.0 / h : 0.0, -1.0 / h, free_ ? -ga / T : 0.0};
+        const int ix[3] = {3 + j, 6 + j, 5};
+        const double ss = s4 + s6, tta = ta4 - ta6, ttb = tb4 - tb6, zz = Z4 - Z6;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          ra[ix[a]] += tta * jv[a]; rb[ix[a]] += ttb * jv[a];
+          gL[ix[a]] -= zz * jv[a];
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+            if (ix[b] <= ix[a]) HH(ix[a], ix[b]) += ss * jv[a] * jv[b];
+        }
+        if (free_) {
+          double yj = -zz, c = yj / (h * T);
+          HH(6 + j, 5) += c;
+          if (k >= 1) HH(5, 3 + j) -= c;
+          HH(5, 5) += yj * 2 * ga / (T * T);
+        }
+      }
+    }
+    if (k >= 1) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gL[j] -= ydm[j];
+      // (6) state bounds
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double sg, ta, tb;
+        const double Z0 = sm.st(sm.ZXY, j, k), Z2 = sm.st(sm.ZXY, 2 + j, k);
+        acc.add(sm.st(sm.SXY, j, k), Z0, sv.dxy[j], sg, ta, tb);
+        HH(j, j) += sg; ra[j] += ta; rb[j] += tb; gL[j] -= Z0;
+        acc.add(sm.st(sm.SXY, 2 + j, k), Z2, sv.dxy[2 + j], sg, ta, tb);
+        HH(j, j) += sg; ra[j] -= ta; rb[j] -= tb; gL[j] += Z2;
+      }
+    }
+    if (k == 0 && free_) {
+      // (4) time cost and (8) T bounds live in stage 0
+      gf[5] += (N + 1) * (P.time_cost[0] + 2 * P.time_cost[1] * T);
+      HH(5, 5) += 2 * (N + 1) * P.time_cost[1];
+      double sg, ta, tb;
+      acc.add(G.STb[0], G.ZTb[0], T - P.T_min, sg, ta, tb);
+      HH(5, 5) += sg; ra[5] += ta; rb[5] += tb; gL[5] -= G.ZTb[0];
+      acc.add(G.STb[1], G.ZTb[1], G.Tmax - T, sg, ta, tb);
+      HH(5, 5) += sg; ra[5] -= ta; rb[5] -= tb; gL[5] += G.ZTb[1];
+    }
+    if (k == N && has_term) {
+      double sg, ta, tb;
+      acc.add(G.Stm[0], G.Ztm[0], z[0] - G.term[0], sg, ta, tb);
+      HH(0, 0) += sg; ra[0] += ta; rb[0] += tb; gL[0] -= G.Ztm[0];
+      acc.add(G.Stm[1], G.Ztm[1], z[1] - G.term[1], sg, ta, tb);
+      HH(1, 1) += sg; ra[1] += ta; rb[1] += tb; gL[1] -= G.Ztm[1];
+      acc.add(G.Stm[2], G.Ztm[2], G.term[2] - z[1], sg, ta, tb);
+      HH(1, 1) += sg; ra[1] -= ta; rb[1] -= tb; gL[1] += G.Ztm[2];
+    }
+    if (k == N && free_) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        gL[j] += G.yt[j];
+        double c = z[j] - xref(N)[j];
+        ceq_th += fabs(c); ceq_max = fmax(ceq_max, fabs(c)); ctmax = fmax(ctmax, fabs(c));
+        sumy += fabs(G.yt[j]);
+      }
+    }
+#undef HH
+#pragma unroll
+    for (int i = 0; i < 36; ++i) sm.st(sm.H, i, k) = H[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sm.st(sm.RA, i, k) = ra[i]; sm.st(sm.RB, i, k) = rb[i]; sm.st(sm.GL, i, k) = gL[i] + gf[i];
+      sm.st(sm.GF, i, k) = gf[i]; sm.st(sm.DYN, i, k) = dyn[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sm.st(sm.CD, j, k) = (k < N) ? sv.cd[j] : 0.0;
+    part[PS_F] = sv.f; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg; part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
+    part[PS_GT] = 0.0; part[PM_E1] = 0.0; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
+    part[PM_CT] = ctmax; part[PM_BAD] = 0.0; part[PN_SZMIN] = acc.szmin;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // assemble, block part (thread = one (obstacle, stage) pair): square-root factorisation of the 5x5 block
+  // system, solves for the mu-split right-hand side and the three pose columns, Schur complement onto the pose
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void assemble_block(int tid, const BlockRegs<EMAX>& br, double* part) const {
+    const Glob& G = *sm.G;
+    const int i = tid / S1, k = tid % S1;
+    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
+    BlkGeo b;
+    ob_sincos(z2, &b.st, &b.ct);
+    const double st = b.st, ct = b.ct;
+    b.tx = z0 + G.off * ct; b.ty = z1 + G.off * st;
+    double a1 = 0, a2 = 0, bl = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX; ++j) {
+      if (j < E) {
+        const int r = r0 + j;
+        a1 += sm.A[2 * r] * br.lam[j]; a2 += sm.A[2 * r + 1] * br.lam[j]; bl += bk(k, r) * br.lam[j];
+      }
+    }
+    b.a1 = a1; b.a2 = a2;
+    const double m0 = br.mu[0], m1 = br.mu[1], m2 = br.mu[2], m3 = br.mu[3];
+    const double ce1 = m0 - m2 + ct * a1 + st * a2, ce2 = m1 - m3 - st * a1 + ct * a2;
+    const double dn = 1.0 - a1 * a1 - a2 * a2;
+    const double dd = -(G.g[0] * m0 + G.g[1] * m1 + G.g[2] * m2 + G.g[3] * m3) + b.tx * a1 + b.ty * a2 - bl - P.dmin;
+    const double y1 = br.ye[0], y2 = br.ye[1];
+    const double Sn = br.Sn, Zn = br.Zn, Sd = br.Sd, Zd = br.Zd;
+    IneqAcc acc;
+    double e1 = 0;
+    const double ceq_th = fabs(ce1) + fabs(ce2), ceq_max = fmax(fabs(ce1), fabs(ce2));
+    const double sumy = fabs(y1) + fabs(y2);
+    double sn, tna, tnb, sd, tda, tdb;
+    acc.add(Sn, Zn, dn, sn, tna, tnb);
+    acc.add(Sd, Zd, dd, sd, tda, tdb);
+    (void)tda; (void)tdb;
+    Tri5 Lf;
+    Lf.zero();
+    double g0a[5] = {0, 0, 0, 0, 0}, g0b[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < EMAX + 4; ++j) {
+      if (j < E || j >= EMAX) {
+        const int jj = (j < EMAX) ? j : E + (j - EMAX);   // logical row index: lambda rows then the 4 mu rows
+        double wv, S, Z, yv[5], yh[5];
+        if (j < EMAX) { wv = br.lam[j]; S = br.Sl[j]; Z = br.Zl[j]; }
+        else { wv = br.mu[j - EMAX]; S = br.Sm_[j - EMAX]; Z = br.Zm[j - EMAX]; }
+        row_y(b, k, r0, E, jj, yv);
+        double sig, ta, tb;
+        acc.add(S, Z, wv, sig, ta, tb);
+        const double gl = y1 * yv[3] + y2 * yv[4] - Z + 2 * Zn * (a1 * yv[0] + a2 * yv[1]) - Zd * yv[2];
+        e1 = fmax(e1, fabs(gl));
+        tb -= gl;
+        const double di = 1.0 / fmax(sig, SIG_MIN), sq = sqrt(di);
+#pragma unroll
+        for (int a = 0; a < 5; ++a) { g0a[a] += yv[a] * ta * di; g0b[a] += yv[a] * tb * di; yh[a] = yv[a] * sq; }
+        Lf.insert(yh);
+      }
+    }
+    const double aa = a1 * a1 + a2 * a2, lam1 = 2 * Zn + 4 * sn * aa;
+    const double ci0 = 1.0 / (2 * Zn), ci1 = 4 * sn / lam1;
+    bool ok;
+    {
+      double r1[5] = {0, 0, 0, 0, 0}, r2[5] = {0, 0, 0, 0, 0}, r3[5] = {0, 0, sqrt(1.0 / sd), 0, 0};
+      if (aa > 0) {
+        double na = sqrt(aa), e1_ = a1 / na, e2_ = a2 / na, s1 = sqrt(1.0 / lam1), s2 = sqrt(ci0);
+        r1[0] = s1 * e1_; r1[1] = s1 * e2_; r2[0] = -s2 * e2_; r2[1] = s2 * e1_;
+      } else {
+        r1[0] = sqrt(ci0); r2[1] = r1[0];
+      }
+      Lf.insert(r1); Lf.insert(r2); Lf.insert(r3);
+      ok = Lf.finish();
+    }
+    // column 0 (split in mu): h0 = -2 tn a,  rhs = (g0 - Cn^-1 h0, g0[2] - tds, g0[3] + e1, g0[4] + e2)
+    double h0a[2] = {-2 * tna * a1, -2 * tna * a2}, h0b[2] = {-2 * tnb * a1, -2 * tnb * a2};
+    double cha[2], chb[2], rhs[5], eta0a[5], eta0b[5];
+    cn_inv(b, ci0, ci1, h0a, cha);
+    cn_inv(b, ci0, ci1, h0b, chb);
+    rhs[0] = g0a[0] - cha[0]; rhs[1] = g0a[1] - cha[1]; rhs[2] = g0a[2] - 1.0 / Zd; rhs[3] = g0a[3]; rhs[4] = g0a[4];
+    Lf.solve(rhs, eta0a);
+    rhs[0] = g0b[0] - chb[0]; rhs[1] = g0b[1] - chb[1]; rhs[2] = g0b[2] + dd; rhs[3] = g0b[3] + ce1; rhs[4] = g0b[4] + ce2;
+    Lf.solve(rhs, eta0b);
+#pragma unroll
+    for (int a = 0; a < 5; ++a) { sm.bl(sm.ETA, a, tid) = eta0a[a]; sm.bl(sm.ETA, 5 + a, tid) = eta0b[a]; }
+    // Lagrangian gradient wrt the pose from this block
+    const double offt = G.off * (-st * a1 + ct * a2);
+    const double dpose[3] = {a1, a2, offt};
+    const double jt0 = -st * a1 + ct * a2, jt1 = -ct * a1 - st * a2;
+    double gLz[3] = {-Zd * dpose[0], -Zd * dpose[1], y1 * jt0 + y2 * jt1 - Zd * dpose[2]};
+    // pose columns and Schur complement (pose of stage 0 is fixed: columns unused but harmless)
+    const double ydv = -Zd, c1 = y1 + ydv * G.off;
+    const double hc[3][2] = {{ydv, 0.0}, {0.0, ydv}, {-c1 * st - y2 * ct, c1 * ct - y2 * st}};
+    double bc[3][5], etc[3][5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cn_inv(b, ci0, ci1, hc[c], bc[c]);
+      bc[c][2] = dpose[c];
+      bc[c][3] = (c == 2) ? jt0 : 0.0;
+      bc[c][4] = (c == 2) ? jt1 : 0.0;
+      Lf.solve(bc[c], etc[c]);
+#pragma unroll
+      for (int a = 0; a < 5; ++a) sm.bl(sm.ETA, 10 + 5 * c + a, tid) = etc[c][a];
+    }
+    const double h22 = y1 * (-ct * a1 - st * a2) + y2 * (st * a1 - ct * a2) + ydv * G.off * (-ct * a1 - st * a2);
+    int e = 0;
+#pragma unroll
+    for (int cp = 0; cp < 3; ++cp) {
+#pragma unroll
+      for (int c = 0; c <= cp; ++c) {
+        double Gm = hc[cp][0] * bc[c][0] + hc[cp][1] * bc[c][1];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) Gm -= bc[cp][a] * etc[c][a];
+        sm.bl(sm.EX, e++, tid) = Gm;        // order (0,0) (1,0) (1,1) (2,0) (2,1) (2,2) = packed symmetric
+      }
+    }
+#pragma unroll
+    for (int cp = 0; cp < 3; ++cp) {
+      double Ga = -(bc[cp][0] * h0a[0] + bc[cp][1] * h0a[1]), Gb = -(bc[cp][0] * h0b[0] + bc[cp][1] * h0b[1]);
+#pragma unroll
+      for (int a = 0; a < 5; ++a) { Ga -= bc[cp][a] * eta0a[a]; Gb -= bc[cp][a] * eta0b[a]; }
+      sm.bl(sm.EX, 6 + cp, tid) = Ga; sm.bl(sm.EX, 9 + cp, tid) = Gb; sm.bl(sm.EX, 12 + cp, tid) = gLz[cp];
+    }
+    sm.bl(sm.EX, 15, tid) = h22;
+    part[PS_F] = 0.0; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg; part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
+    part[PS_GT] = 0.0; part[PM_E1] = e1; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
+    part[PM_CT] = 0.0; part[PM_BAD] = ok ? 0.0 : 1.0; part[PN_SZMIN] = acc.szmin;
+  }
+
+  // fold the block contributions into the stage QP (lane k), finish the step-form right-hand side and the
+  // stage's share of the optimality error
+  OB_HD void assemble_combine(int k, double* part) const {
+    double Gs[EX_N];
+#pragma unroll
+    for (int e = 0; e < EX_N; ++e) Gs[e] = 0.0;
+    for (int i = 0; i < no; ++i) {
+      const int t = i * S1 + k;
+#pragma unroll
+      for (int e = 0; e < EX_N; ++e) Gs[e] += sm.bl(sm.EX, e, t);
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) sm.st(sm.H, e, k) -= Gs[e];     // packed (cp,c), cp,c < 3, is the head of H
+    sm.st(sm.H, 5, k) += Gs[15];                                // H(2,2)
+    double gL[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) gL[a] = sm.st(sm.GL, a, k);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      sm.st(sm.RA, a, k) += Gs[6 + a];
+      sm.st(sm.RB, a, k) += Gs[9 + a];
+      gL[a] += Gs[12 + a];
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) sm.st(sm.RB, a, k) -= gL[a];
+    // stage share of the dual infeasibility; the (v_prev, w_prev) rows of stage k+1 belong to u_k
+    // (rows 3, 4 of GL are final after assemble_stage, so the neighbour's can be read here)
+    double e1 = 0;
+    if (k >= 1) e1 = fmax(fabs(gL[0]), fmax(fabs(gL[1]), fabs(gL[2])));
+    if (k < N) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double gun = (k + 1 < N) ? sm.st(sm.GL, 3 + j, k + 1) : 0.0;
+        e1 = fmax(e1, fabs(gL[6 + j] + gun));
+      }
+    }
+    part[PM_E1] = e1;
+    part[PS_GT] = gL[5];
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // Riccati sweep, cooperative: the 32 lanes of the stage warp share the entries of the 8x8 stage system.
+  // Variables (x, y, th, v_prev, w_prev, T | v, w).  Sub-step A forms F = H + At^T P At and f = r + At^T pc;
+  // sub-step B eliminates (v, w) and writes the cost-to-go of stage s.  Pivots double as the inertia test.
+  // ------------------------------------------------------------------------------------------------
+  // column j of At = [A B] as <= 4 (row, value) pairs; columns 3, 4 (v_prev, w_prev) are empty
+  OB_HD int at_col(int s, int j, int rows[4], double vals[4]) const {
+    const double fth0 = sm.st(sm.DYN, 0, s), fth1 = sm.st(sm.DYN, 1, s), bv0 = sm.st(sm.DYN, 2, s), bv1 = sm.st(sm.DYN, 3, s);
+    const double bw = sm.st(sm.DYN, 4, s), fT0 = sm.st(sm.DYN, 5, s), fT1 = sm.st(sm.DYN, 6, s), fT2 = sm.st(sm.DYN, 7, s);
+    switch (j) {
+      case 0: rows[0] = 0; vals[0] = 1.0; return 1;
+      case 1: rows[0] = 1; vals[0] = 1.0; return 1;
+      case 2: rows[0] = 0; vals[0] = fth0; rows[1] = 1; vals[1] = fth1; rows[2] = 2; vals[2] = 1.0; return 3;
+      case 5: rows[0] = 0; vals[0] = fT0; rows[1] = 1; vals[1] = fT1; rows[2] = 2; vals[2] = fT2; rows[3] = 5; vals[3] = 1.0; return 4;
+      case 6: rows[0] = 0; vals[0] = bv0; rows[1] = 1; vals[1] = bv1; rows[2] = 3; vals[2] = 1.0; return 3;
+      case 7: rows[0] = 2; vals[0] = bw; rows[1] = 4; vals[1] = 1.0; return 2;
+      default: return 0;
+    }
+  }
+  OB_HD void ric_terminal(int lane, double mu, double dw, double dc) const {
+    // stage N: cost-to-go = its own 6x6 block (terminal equality folded in Levenberg-Marquardt style)
+    const int s = N;
+    if (lane < 21) {
+      int a = 0;
+      while ((a + 1) * (a + 2) / 2 <= lane) ++a;
+      const int b = lane - a * (a + 1) / 2;
+      double v = sm.st(sm.H, lane, s);
+      if (a == b && a < 3) { v += dw; if (free_) v += 1.0 / dc; }
+      sm.st(sm.PM, lane, s) = v;
+    } else if (lane < 27) {
+      const int a = lane - 21;
+      double r = mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
+      if (a < 3 && free_) r -= (sm.st(sm.Z, a, s) - xref(N)[a]) / dc;
+      sm.st(sm.PV, a, s) = r;
+    }
+  }
+  OB_HD void ric_a(int lane, int s, double mu, double dw) const {
+    double* F = sm.RIC;        // 36 packed
+    double* f = sm.RIC + 36;   // 8
+    double* Pn = sm.PM + 0;    // element e of stage s+1 at Pn[e*S1 + s+1]
+#define PN(a, b) Pn[symi(a, b) * S1 + s + 1]
+    for (int e = lane; e < 36 + 8; e += 32) {
+      if (e < 36) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int b = e - a * (a + 1) / 2;
+        double v = sm.st(sm.H, e, s);
+        int ra_[4], rb_[4];
+        double va[4], vb[4];
+        const int na = at_col(s, a, ra_, va), nbb = at_col(s, b, rb_, vb);
+        for (int p = 0; p < na; ++p)
+          for (int q = 0; q < nbb; ++q) v += va[p] * vb[q] * PN(ra_[p], rb_[q]);
+        if (a == b) {
+          if ((a < 3 && s >= 1) || a >= 6 || (a == 5 && s == 0 && free_)) v += dw;
+        }
+        F[e] = v;
+      } else {
+        const int a = e - 36;
+        double v = mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
+        int ra_[4];
+        double va[4];
+        const int na = at_col(s, a, ra_, va);
+        const double c0 = sm.st(sm.CD, 0, s), c1 = sm.st(sm.CD, 1, s), c2 = sm.st(sm.CD, 2, s);
+        for (int p = 0; p < na; ++p) {
+          const int r = ra_[p];
+          const double pc = sm.st(sm.PV, r, s + 1) - (PN(r, 0) * c0 + PN(r, 1) * c1 + PN(r, 2) * c2);
+          v += va[p] * pc;
+        }
+        f[a] = v;
+      }
+    }
+#undef PN
+  }
+  OB_HD void ric_b(int lane, int s) const {
+    Glob& G = *sm.G;
+    const double* F = sm.RIC;
+    const double* f = sm.RIC + 36;
+#define FF(a, b) F[symi(a, b)]
+    const double q00 = FF(6, 6), q01 = FF(7, 6), q11 = FF(7, 7);
+    const double det = q00 * q11 - q01 * q01;
+    if (lane == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
+    const double i00 = q11 / det, i01 = -q01 / det, i11 = q00 / det;
+    for (int e = lane; e < 21 + 6 + 14; e += 32) {
+      if (e < 21) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= e) ++a;
+        const int b = e - a * (a + 1) / 2;
+        const double fa6 = FF(a, 6), fa7 = FF(a, 7), fb6 = FF(b, 6), fb7 = FF(b, 7);
+        sm.st(sm.PM, e, s) = FF(a, b) - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
+      } else if (e < 27) {
+        const int a = e - 21;
+        const double kap0 = i00 * f[6] + i01 * f[7], kap1 = i01 * f[6] + i11 * f[7];
+        sm.st(sm.PV, a, s) = f[a] - FF(a, 6) * kap0 - FF(a, 7) * kap1;
+      } else if (e < 39) {
+        const int q = e - 27, row = q / 6, b = q % 6;
+        const double v = (row == 0) ? -(i00 * FF(6, b) + i01 * FF(7, b)) : -(i01 * FF(6, b) + i11 * FF(7, b));
+        sm.st(sm.K, q, s) = v;
+      } else {
+        const int row = e - 39;
+        sm.st(sm.KAP, row, s) = (row == 0) ? i00 * f[6] + i01 * f[7] : i01 * f[6] + i11 * f[7];
+      }
+    }
+#undef FF
+  }
+  OB_HD void ric_finish(int lane) const {
+    Glob& G = *sm.G;
+    if (lane == 0 && free_ && !(sm.st(sm.PM, 20, 0) > 0)) G.bad = 1;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // roll-out.  fwd_prep (lane k): closed-loop map  xi_{k+1} = ACL_k xi_k + CCL_k  (ACL|CCL overwrite H|RA);
+  // fwd_step (lanes 0..5, sequential in s); fwd_post (lane k): du_k, dz_k, dynamics-multiplier steps
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void fwd_prep(int k) const {
+    Glob& G = *sm.G;
+    if (k == 0) {
+      double dT = 0.0;
+      if (free_) dT = sm.st(sm.PV, 5, 0) / sm.st(sm.PM, 20, 0);
+      G.dT = dT;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) sm.st(sm.XI, a, 0) = (a == 5) ? dT : 0.0;
+    }
+    if (k >= N) return;
+    double Kr[2][6], kap[2];
+#pragma unroll
+    for (int b = 0; b < 6; ++b) { Kr[0][b] = sm.st(sm.K, b, k); Kr[1][b] = sm.st(sm.K, 6 + b, k); }
+    kap[0] = sm.st(sm.KAP, 0, k); kap[1] = sm.st(sm.KAP, 1, k);
+    const double fth0 = sm.st(sm.DYN, 0, k), fth1 = sm.st(sm.DYN, 1, k), bv0 = sm.st(sm.DYN, 2, k), bv1 = sm.st(sm.DYN, 3, k);
+    const double bw = sm.st(sm.DYN, 4, k), fT0 = sm.st(sm.DYN, 5, k), fT1 = sm.st(sm.DYN, 6, k), fT2 = sm.st(sm.DYN, 7, k);
+    const double cd0 = sm.st(sm.CD, 0, k), cd1 = sm.st(sm.CD, 1, k), cd2 = sm.st(sm.CD, 2, k);
+    double* ACL = sm.H;            // [36][S1]
+    double* CCL = sm.H + 36 * S1;  // [6][S1]  (the RA region)
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+      const double A0 = (b == 0 ? 1.0 : 0.0) + (b == 2 ? fth0 : 0.0) + (b == 5 ? fT0 : 0.0);
+      const double A1 = (b == 1 ? 1.0 : 0.0) + (b == 2 ? fth1 : 0.0) + (b == 5 ? fT1 : 0.0);
+      const double A2 = (b == 2 ? 1.0 : 0.0) + (b == 5 ? fT2 : 0.0);
+      ACL[(0 * 6 + b) * S1 + k] = A0 + bv0 * Kr[0][b];
+      ACL[(1 * 6 + b) * S1 + k] = A1 + bv1 * Kr[0][b];
+      ACL[(2 * 6 + b) * S1 + k] = A2 + bw * Kr[1][b];
+      ACL[(3 * 6 + b) * S1 + k] = Kr[0][b];
+      ACL[(4 * 6 + b) * S1 + k] = Kr[1][b];
+      ACL[(5 * 6 + b) * S1 + k] = (b == 5) ? 1.0 : 0.0;
+    }
+    CCL[0 * S1 + k] = bv0 * kap[0] + cd0;
+    CCL[1 * S1 + k] = bv1 * kap[0] + cd1;
+    CCL[2 * S1 + k] = bw * kap[1] + cd2;
+    CCL[3 * S1 + k] = kap[0];
+    CCL[4 * S1 + k] = kap[1];
+    CCL[5 * S1 + k] = 0.0;
+  }
+  OB_HD void fwd_step(int lane, int s) const {
+    if (lane < 6) {
+      const double* ACL = sm.H;
+      const double* CCL = sm.H + 36 * S1;
+      double v = CCL[lane * S1 + s];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) v += ACL[(lane * 6 + b) * S1 + s] * sm.st(sm.XI, b, s);
+      sm.st(sm.XI, lane, s + 1) = v;
+    }
+  }
+  OB_HD void fwd_post(int k, double dc) const {
+    Glob& G = *sm.G;
+    double xi[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) xi[a] = sm.st(sm.XI, a, k);
+    if (k < N) {
+      // du_k = xi_{k+1}[3:5]
+      sm.st(sm.DU, 0, k) = sm.st(sm.XI, 3, k + 1);
+      sm.st(sm.DU, 1, k) = sm.st(sm.XI, 4, k + 1);
+    } else {
+      sm.st(sm.DU, 0, k) = 0.0; sm.st(sm.DU, 1, k) = 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sm.st(sm.DZ, a, k) = (k >= 1) ? xi[a] : 0.0;
+    if (k >= 1) {
+      // dy_{k-1} = (P_k d xi_k - p_k)[0:3]
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double sacc = -sm.st(sm.PV, a, k);
+#pragma unroll
+        for (int b = 0; b < 6; ++b) sacc += sm.st(sm.PM, symi(a, b), k) * xi[b];
+        sm.st(sm.DYD, a, k - 1) = sacc;
+      }
+    }
+    if (k == N) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        sm.st(sm.DYD, a, N) = 0.0;
+        if (free_) G.dyt[a] = (xi[a] + (sm.st(sm.Z, a, N) - xref(N)[a])) / dc;
+      }
+    }
+  }
+
+  OB_HD static void ftb(double S, double Z, double dS, double mu, double tau, double& amax, double& az, double& sls) {
+    double dZ = mu / S - Z - (Z / S) * dS;
+    if (dS < 0) amax = fmin(amax, -tau * S / dS);
+    if (dZ < 0) az = fmin(az, -tau * Z / dZ);
+    sls += dS / S;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // steps of the slacks, fraction to the boundary, directional derivative - stage part (lane k)
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void backsub_stage(int k, double mu, double tau, double* part) const {
+    Glob& G = *sm.G;
+    double z[3], u[2], up[2], zn[3], dz[3], du[2], dup[2];
+    stage_point(k, 0.0, z, u, up, zn);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dz[j] = sm.st(sm.DZ, j, k);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { du[j] = sm.st(sm.DU, j, k); dup[j] = (k >= 1) ? sm.st(sm.DU, j, k - 1) : 0.0; }
+    const double T = free_ ? G.T : 1.0, h = T * G.Ts, dT = G.dT;
+    StageVals sv;
+    stage_vals(k, z, u, up, zn, T, sv);
+    double amax = 1.0, az = 1.0, sls = 0.0, dphi = 0.0;
+    {
+      double gf[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) gf[i] = sm.st(sm.GF, i, k);
+      if (k >= 1) dphi += gf[0] * dz[0] + gf[1] * dz[1] + gf[2] * dz[2];
+      if (k >= 1 && k < N) dphi += gf[3] * dup[0] + gf[4] * dup[1];
+      if (free_) dphi += gf[5] * dT;
+      if (k < N) dphi += gf[6] * du[0] + gf[7] * du[1];
+    }
+    if (k >= 1) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double S0 = sm.st(sm.SXY, j, k), S1_ = sm.st(sm.SXY, 2 + j, k);
+        double d0 = dz[j] + (sv.dxy[j] - S0), d1 = -dz[j] + (sv.dxy[2 + j] - S1_);
+        sm.st(sm.DSXY, j, k) = d0; sm.st(sm.DSXY, 2 + j, k) = d1;
+        ftb(S0, sm.st(sm.ZXY, j, k), d0, mu, tau, amax, az, sls);
+        ftb(S1_, sm.st(sm.ZXY, 2 + j, k), d1, mu, tau, amax, az, sls);
+      }
+    }
+    if (k < N) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double ga = (up[j] - u[j]) / h;
+        double dga = (dup[j] - du[j]) / h - (free_ ? ga / T * dT : 0.0);
+        double dS[4] = {du[j] + (sv.dub[j] - sm.st(sm.SUB, j, k)), -du[j] + (sv.dub[2 + j] - sm.st(sm.SUB, 2 + j, k)),
+                        dga + (sv.dub[4 + j] - sm.st(sm.SUB, 4 + j, k)), -dga + (sv.dub[6 + j] - sm.st(sm.SUB, 6 + j, k))};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          sm.st(sm.DSUB, 2 * q + j, k) = dS[q];
+          ftb(sm.st(sm.SUB, 2 * q + j, k), sm.st(sm.ZUB, 2 * q + j, k), dS[q], mu, tau, amax, az, sls);
+        }
+      }
+    }
+    if (k == 0 && free_) {
+      G.dSTb[0] = dT + ((T - P.T_min) - G.STb[0]);
+      G.dSTb[1] = -dT + ((G.Tmax - T) - G.STb[1]);
+      ftb(G.STb[0], G.ZTb[0], G.dSTb[0], mu, tau, amax, az, sls);
+      ftb(G.STb[1], G.ZTb[1], G.dSTb[1], mu, tau, amax, az, sls);
+    }
+    if (k == N && has_term) {
+      G.dStm[0] = dz[0] + ((z[0] - G.term[0]) - G.Stm[0]);
+      G.dStm[1] = dz[1] + ((z[1] - G.term[1]) - G.Stm[1]);
+      G.dStm[2] = -dz[1] + ((G.term[2] - z[1]) - G.Stm[2]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ftb(G.Stm[j], G.Ztm[j], G.dStm[j], mu, tau, amax, az, sls);
+    }
+    part[QS_DPHI] = dphi - mu * sls; part[QN_AMAX] = amax; part[QN_AZ] = az;
+  }
+
+  // block part: back-substitution of the dual block
+  OB_HD void backsub_block(int tid, const BlockRegs<EMAX>& br, double mu, double tau, double* part) const {
+    const Glob& G = *sm.G;
+    const int i = tid / S1, k = tid % S1;
+    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
+    BlkGeo b;
+    ob_sincos(z2, &b.st, &b.ct);
+    const double st = b.st, ct = b.ct;
+    b.tx = z0 + G.off * ct; b.ty = z1 + G.off * st;
+    const double dp[3] = {(k >= 1) ? sm.st(sm.DZ, 0, k) : 0.0, (k >= 1) ? sm.st(sm.DZ, 1, k) : 0.0, (k >= 1) ? sm.st(sm.DZ, 2, k) : 0.0};
+    double a1 = 0, a2 = 0, bl = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX; ++j) {
+      if (j < E) {
+        const int r = r0 + j;
+        a1 += sm.A[2 * r] * br.lam[j]; a2 += sm.A[2 * r + 1] * br.lam[j]; bl += bk(k, r) * br.lam[j];
+      }
+    }
+    b.a1 = a1; b.a2 = a2;
+    const double m0 = br.mu[0], m1 = br.mu[1], m2 = br.mu[2], m3 = br.mu[3];
+    const double dn = 1.0 - a1 * a1 - a2 * a2;
+    const double dd = -(G.g[0] * m0 + G.g[1] * m1 + G.g[2] * m2 + G.g[3] * m3) + b.tx * a1 + b.ty * a2 - bl - P.dmin;
+    const double y1 = br.ye[0], y2 = br.ye[1];
+    const double Sn = br.Sn, Zn = br.Zn, Sd = br.Sd, Zd = br.Zd;
+    const double sn = Zn / Sn, sd = Zd / Sd;
+    const double tn = (mu - Sn * Zn) / Sn - sn * (dn - Sn);
+    const double ydv = -Zd, c1 = y1 + ydv * G.off;
+    const double hc[3][2] = {{ydv, 0.0}, {0.0, ydv}, {-c1 * st - y2 * ct, c1 * ct - y2 * st}};
+    const double offt = G.off * (-st * a1 + ct * a2);
+    const double dpose[3] = {a1, a2, offt};
+    double et[5], ht[2] = {-2 * tn * a1, -2 * tn * a2};
+#pragma unroll
+    for (int a = 0; a < 5; ++a) et[a] = mu * sm.bl(sm.ETA, a, tid) + sm.bl(sm.ETA, 5 + a, tid);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+      for (int a = 0; a < 5; ++a) et[a] += sm.bl(sm.ETA, 10 + 5 * c + a, tid) * dp[c];
+      ht[0] -= hc[c][0] * dp[c]; ht[1] -= hc[c][1] * dp[c];
+    }
+    double amax = 1.0, az = 1.0, sls = 0.0;
+    double da1 = 0, da2 = 0, qdw = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX + 4; ++j) {
+      if (j < E || j >= EMAX) {
+        const int jj = (j < EMAX) ? j : E + (j - EMAX);
+        double wv, S, Z, yv[5];
+        if (j < EMAX) { wv = br.lam[j]; S = br.Sl[j]; Z = br.Zl[j]; }
+        else { wv = br.mu[j - EMAX]; S = br.Sm_[j - EMAX]; Z = br.Zm[j - EMAX]; }
+        row_y(b, k, r0, E, jj, yv);
+        const double sig = Z / S;
+        const double gl = y1 * yv[3] + y2 * yv[4] - Z + 2 * Zn * (a1 * yv[0] + a2 * yv[1]) - Zd * yv[2];
+        double s = (mu - S * Z) / S - sig * (wv - S) - gl;
+#pragma unroll
+        for (int a = 0; a < 5; ++a) s -= yv[a] * et[a];
+        const double dwv = s / fmax(sig, SIG_MIN);
+        if (j < EMAX) { sm.st(sm.DLAM, r0 + j, k) = dwv; da1 += yv[0] * dwv; da2 += yv[1] * dwv; }
+        else sm.bl(sm.DMU, j - EMAX, tid) = dwv;
+        qdw += yv[2] * dwv;
+        ftb(S, Z, dwv + (wv - S), mu, tau, amax, az, sls);
+      }
+    }
+    sm.bl(sm.DYE, 0, tid) = et[3]; sm.bl(sm.DYE, 1, tid) = et[4];
+    double ada = a1 * da1 + a2 * da2;
+    if (sn >= 1.0) ada = (a1 * (et[0] + ht[0]) + a2 * (et[1] + ht[1])) / (2 * Zn + 4 * sn * (a1 * a1 + a2 * a2));
+    const double dSn = -2 * ada + (dn - Sn);
+    double dSd;
+    if (sd >= 1.0) dSd = (mu - Sd * Zd + Sd * et[2]) / Zd;
+    else dSd = qdw + (dd - Sd) + dpose[0] * dp[0] + dpose[1] * dp[1] + dpose[2] * dp[2];
+    sm.bl(sm.DSN, 0, tid) = dSn; sm.bl(sm.DSD, 0, tid) = dSd;
+    ftb(Sn, Zn, dSn, mu, tau, amax, az, sls);
+    ftb(Sd, Zd, dSd, mu, tau, amax, az, sls);
+    part[QS_DPHI] = -mu * sls; part[QN_AMAX] = amax; part[QN_AZ] = az;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // trial point X + a dX, S + a dS: partial objective, constraint violation theta, sum log S
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void trial_stage(int k, double a, double* part) const {
+    const Glob& G = *sm.G;
+    double z[3], u[2], up[2], zn[3];
+    stage_point(k, a, z, u, up, zn);
+    if (a == 0.0) { /* stage_point skips the direction at a == 0 */ }
+    const double T = free_ ? G.T + a * G.dT : 1.0;
+    StageVals sv;
+    stage_vals(k, z, u, up, zn, T, sv);
+    double th = 0, lg = 0;
+    if (k < N) {
+      th += fabs(sv.cd[0]) + fabs(sv.cd[1]) + fabs(sv.cd[2]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { double S = sm.st(sm.SUB, j, k) + a * sm.st(sm.DSUB, j, k); th += fabs(sv.dub[j] - S); lg += log(S); }
+    }
+    if (k >= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { double S = sm.st(sm.SXY, j, k) + a * sm.st(sm.DSXY, j, k); th += fabs(sv.dxy[j] - S); lg += log(S); }
+    }
+    if (k == 0 && free_) {
+      double S = G.STb[0] + a * G.dSTb[0]; th += fabs(T - P.T_min - S); lg += log(S);
+      S = G.STb[1] + a * G.dSTb[1]; th += fabs(G.Tmax - T - S); lg += log(S);
+    }
+    if (k == N && free_) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) th += fabs(z[j] - xref(N)[j]);
+    }
+    if (k == N && has_term) {
+      double S = G.Stm[0] + a * G.dStm[0]; th += fabs(z[0] - G.term[0] - S); lg += log(S);
+      S = G.Stm[1] + a * G.dStm[1]; th += fabs(z[1] - G.term[1] - S); lg += log(S);
+      S = G.Stm[2] + a * G.dStm[2]; th += fabs(G.term[2] - z[1] - S); lg += log(S);
+    }
+    part[0] = sv.f; part[1] = th; part[2] = lg;
+  }
+  OB_HD void trial_block(int tid, const BlockRegs<EMAX>& br, double a, double* part) const {
+    const Glob& G = *sm.G;
+    const int i = tid / S1, k = tid % S1;
+    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const double ak = (k >= 1) ? a : 0.0;
+    const double z0 = sm.st(sm.Z, 0, k) + ak * sm.st(sm.DZ, 0, k), z1 = sm.st(sm.Z, 1, k) + ak * sm.st(sm.DZ, 1, k);
+    const double z2 = sm.st(sm.Z, 2, k) + ak * sm.st(sm.DZ, 2, k);
+    double st, ct;
+    ob_sincos(z2, &st, &ct);
+    const double tx = z0 + G.off * ct, ty = z1 + G.off * st;
+    double th = 0, lg = 0, a1 = 0, a2 = 0, bl = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX; ++j) {
+      if (j < E) {
+        const int r = r0 + j;
+        const double l0 = br.lam[j], dl = sm.st(sm.DLAM, r, k), S0 = br.Sl[j];
+        const double l = l0 + a * dl, S = S0 + a * (dl + (l0 - S0));
+        a1 += sm.A[2 * r] * l; a2 += sm.A[2 * r + 1] * l; bl += bk(k, r) * l;
+        th += fabs(l - S); lg += log(S);
+      }
+    }
+    double m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double m0 = br.mu[q], dm = sm.bl(sm.DMU, q, tid), S0 = br.Sm_[q];
+      m[q] = m0 + a * dm;
+      const double S = S0 + a * (dm + (m0 - S0));
+      th += fabs(m[q] - S); lg += log(S);
+    }
+    th += fabs(m[0] - m[2] + ct * a1 + st * a2) + fabs(m[1] - m[3] - st * a1 + ct * a2);
+    {
+      const double S = br.Sn + a * sm.bl(sm.DSN, 0, tid);
+      th += fabs(1.0 - a1 * a1 - a2 * a2 - S); lg += log(S);
+    }
+    {
+      const double S = br.Sd + a * sm.bl(sm.DSD, 0, tid);
+      const double d = -(G.g[0] * m[0] + G.g[1] * m[1] + G.g[2] * m[2] + G.g[3] * m[3]) + tx * a1 + ty * a2 - bl - P.dmin;
+      th += fabs(d - S); lg += log(S);
+    }
+    part[0] = 0.0; part[1] = th; part[2] = lg;
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // accept the step: primal / slacks / equality multipliers with a, inequality multipliers with a_z (then
+  // clipped into [mu/(ks S), ks mu/S] as IPOPT does)
+  // ------------------------------------------------------------------------------------------------
+  OB_HD static void upd(double& S, double& Z, double dS, double a, double az, double mu) {
+    const double ks = 1e10;
+    double dZ = mu / S - Z - (Z / S) * dS;
+    double Sn = S + a * dS, Zn = Z + az * dZ;
+    Zn = fmin(fmax(Zn, mu / (ks * Sn)), ks * mu / Sn);
+    S = Sn; Z = Zn;
+  }
+  // NOTE: reads neighbours' DZ/DU only through its own column, so no barrier is needed inside
+  OB_HD void update(int tid, BlockRegs<EMAX>& br, double a, double az, double mu) const {
+    Glob& G = *sm.G;
+    if (is_stage(tid)) {
+      const int k = stage_lane(tid);
+      if (k >= 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sm.st(sm.Z, j, k) += a * sm.st(sm.DZ, j, k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) upd(sm.st(sm.SXY, j, k), sm.st(sm.ZXY, j, k), sm.st(sm.DSXY, j, k), a, az, mu);
+      }
+      if (k < N) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) sm.st(sm.U, j, k) += a * sm.st(sm.DU, j, k);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) upd(sm.st(sm.SUB, j, k), sm.st(sm.ZUB, j, k), sm.st(sm.DSUB, j, k), a, az, mu);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sm.st(sm.YD, j, k) += a * sm.st(sm.DYD, j, k);
+      }
+      if (k == 0 && free_) {
+        G.T += a * G.dT;
+        upd(G.STb[0], G.ZTb[0], G.dSTb[0], a, az, mu);
+        upd(G.STb[1], G.ZTb[1], G.dSTb[1], a, az, mu);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) G.yt[j] += a * G.dyt[j];
+      }
+      if (k == N && has_term) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) upd(G.Stm[j], G.Ztm[j], G.dStm[j], a, az, mu);
+      }
+    }
+    if (is_block(tid)) {
+      const int i = tid / S1, k = tid % S1;
+      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+#pragma unroll
+      for (int j = 0; j < EMAX; ++j) {
+        if (j < E) {
+          const double l0 = br.lam[j], dl = sm.st(sm.DLAM, r0 + j, k);
+          upd(br.Sl[j], br.Zl[j], dl + (l0 - br.Sl[j]), a, az, mu);
+          br.lam[j] = l0 + a * dl;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double m0 = br.mu[q], dm = sm.bl(sm.DMU, q, tid);
+        upd(br.Sm_[q], br.Zm[q], dm + (m0 - br.Sm_[q]), a, az, mu);
+        br.mu[q] = m0 + a * dm;
+      }
+      upd(br.Sn, br.Zn, sm.bl(sm.DSN, 0, tid), a, az, mu);
+      upd(br.Sd, br.Zd, sm.bl(sm.DSD, 0, tid), a, az, mu);
+      br.ye[0] += a * sm.bl(sm.DYE, 0, tid);
+      br.ye[1] += a * sm.bl(sm.DYE, 1, tid);
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // results -> HBM, once:  x [B,N+1,3]  u [B,N,2]  lam [B,N+1,R]  mu [B,N+1,4 no]  T  obj  status  iters
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
+    const Glob& G = *sm.G;
+    const int R = sm.R;
+    if (is_stage(tid)) {
+      const int k = stage_lane(tid);
+      double* xo = kp.x + (b * S1 + k) * 3;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) xo[j] = sm.st(sm.Z, j, k);
+      if (k < N) {
+        double* uo = kp.u + (b * N + k) * 2;
+        uo[0] = sm.st(sm.U, 0, k); uo[1] = sm.st(sm.U, 1, k);
+      }
+      if (k == 0) {
+        kp.T[b] = free_ ? G.T : 1.0;
+        kp.obj[b] = obj;
+        kp.status[b] = status;
+        kp.iters[b] = iters;
+      }
+    }
+    if (is_block(tid)) {
+      const int i = tid / S1, k = tid % S1;
+      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      double* lo = kp.lam + (b * S1 + k) * R + r0;
+#pragma unroll
+      for (int j = 0; j < EMAX; ++j)
+        if (j < E) lo[j] = br.lam[j];
+      double* mo = kp.mu + (b * S1 + k) * 4 * no + 4 * i;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mo[q] = br.mu[q];
+    }
+  }
+};
+
+// ======================================================================================================
+// The interior-point loop of one instance.  `Exec` provides:
+//   par(f)            run f(tid, BlockRegs&, part*) for every thread of the block, then a block barrier
+//   reduce<S0,NS,M0,NM,N0,NN>()  one block reduction over the threads' part[] slots: sum of slots S0..S0+NS-1,
+//                     max of M0.., min of N0.. (results in ex.red[] at the same slots)
+//   stage(f)          run f(lane) on the 32 lanes of the stage warp, then a warp barrier (no block barrier)
+//   stage_end()       block barrier closing a run of stage() calls
+//   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
+//   once(f)           run f() on one thread (block-uniform shared state), visible after the next barrier
+// ======================================================================================================
+template <int EMAX, class Exec>
+OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iters_out, double& obj_out) {
+  const obca_params& P = S.P;
+  Glob& G = *S.sm.G;
+  const double s_max = 100.0, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+  const double dw_first = 1e-4, dw_min = 1e-20, dw_max = 1e20, kw_plus_first = 100.0, kw_plus = 8.0, kw_minus = 1.0 / 3.0;
+  const double dc_min = 1e-8, lm_cap = 1e4, stall_alpha = 1e-3;
+  const int stall_iters = 10;
+  const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta_ph = 1e-8;
+  const double tol = P.tol;
+  const int N = S.N, no = S.no;
+  const bool free_ = S.free_, has_term = S.has_term;
+  const int m_eq = 3 * N + (free_ ? 3 : 0) + 2 * no * (N + 1);
+  const int q_in = 12 * N + (free_ ? 2 : 0) + (has_term ? 3 : 0) + (S.sm.R + 6 * no) * (N + 1);
+  typedef BlockRegs<EMAX> BR;
+
+  ex.par([&](int tid, BR& br, double* part) { (void)br; S.start_a(tid, part); });
+  ex.template reduce<0, 1, 0, 0, 0, 0>();
+  const double T0 = S.start_T(ex.red[0]);
+  ex.par([&](int tid, BR& br, double* part) { (void)part; S.start_b(tid, br, T0); });
+  ex.par([&](int tid, BR& br, double* part) { (void)part; S.init_slacks(tid, br); });
+
+  double mu = P.mu_init;
+  int f_n = 0, f_wr = 0;
+  bool f_active = false;
+  double thmax = 0, thmin = 0;
+  int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
+  double dw_last = 0.0, E0 = 0.0, fcur = 0.0, best_E0 = 1e300, best_f = 0.0;
+
+  ex.tick(0);
+  for (;;) {
+    // ---- assemble
+    ex.par([&](int tid, BR& br, double* part) {
+      if (S.is_block(tid)) S.assemble_block(tid, br, part);
+      else if (S.is_stage(tid)) S.assemble_stage(S.stage_lane(tid), part);
+      else for (int q = 0; q < NPART; ++q) part[q] = (q == PN_SZMIN) ? 1e300 : 0.0;
+    });
+    ex.par([&](int tid, BR& br, double* part) { (void)br; if (S.is_stage(tid)) S.assemble_combine(S.stage_lane(tid), part); });
+    ex.template reduce<PS_F, 6, PM_E1, 5, PN_SZMIN, 1>();
+    ex.tick(1);
+    const double Ef = ex.red[PS_F], Eth = ex.red[PS_TH], ElgS = ex.red[PS_LG], Esumy = ex.red[PS_SUMY], Esumz = ex.red[PS_SUMZ];
+    double Ee1 = ex.red[PM_E1];
+    if (free_) Ee1 = fmax(Ee1, fabs(ex.red[PS_GT]));
+    const double Ee2 = ex.red[PM_E2], Eszmax = ex.red[PM_SZMAX], Ectmax = ex.red[PM_CT], Eszmin = ex.red[PN_SZMIN];
+    const bool Eok = !(ex.red[PM_BAD] > 0.0);
+    fcur = Ef;
+    if (!Eok) { status = OBCA_ST_REGFAIL; break; }
+    const double sd = fmax(s_max, (Esumy + Esumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, Esumz / q_in) / s_max;
+    E0 = fmax(fmax(Ee1 / sd, Ee2), Eszmax / sc);
+    if (E0 <= tol) { status = OBCA_ST_OK; break; }
+    if (E0 <= P.acceptable_tol) {
+      // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails
+      // later on.  The store goes straight to the result arrays: no on-chip copy is kept.
+      if (E0 < best_E0) {
+        best_E0 = E0; best_f = Ef;
+        ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
+      }
+      if (++acc_count >= P.acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
+    } else
+      acc_count = 0;
+    if (iter >= P.max_iter) { status = OBCA_ST_MAXITER; break; }
+    // ---- barrier update (monotone Fiacco-McCormick)
+    bool changed = false;
+    for (;;) {
+      const double e3 = fmax(Eszmax - mu, mu - Eszmin) / sc;
+      const double Emu = fmax(fmax(Ee1 / sd, Ee2), e3);
+      if (Emu <= kappa_eps * mu && mu > tol / 10) {
+        mu = fmax(tol / 10, fmin(kappa_mu * mu, pow(mu, theta_mu)));
+        changed = true;
+      } else
+        break;
+    }
+    if (changed && f_active) { f_n = 0; f_wr = 0; }
+    const double th = Eth, ph0 = Ef - mu * ElgS;
+    const double tau = fmax(tau_min, 1 - mu);
+    const double dc = free_ ? fmax(dc_min, Ectmax / lm_cap) : 0.0;
+    // ---- Riccati with inertia correction: the pivots are the inertia test
+    double dw = 0.0;
+    bool regfail = false;
+    for (;;) {
+      ex.once([&]() { G.bad = 0; });
+      ex.stage_end();
+      ex.stage([&](int lane) { S.ric_terminal(lane, mu, dw, dc); });
+      for (int s = N - 1; s >= 0; --s) {
+        ex.stage([&](int lane) { S.ric_a(lane, s, mu, dw); });
+        ex.stage([&](int lane) { S.ric_b(lane, s); });
+      }
+      ex.stage([&](int lane) { S.ric_finish(lane); });
+      ex.stage_end();
+      if (!G.bad) break;
+      if (dw == 0.0) dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
+      else dw = dw * ((dw_last == 0.0) ? kw_plus_first : kw_plus);
+      if (dw > dw_max) { regfail = true; break; }
+      ex.stage_end();   // everyone has read G.bad before it is cleared again
+    }
+    if (regfail) { status = OBCA_ST_REGFAIL; break; }
+    if (dw > 0) dw_last = dw;
+    ex.tick(2);
+    // ---- roll-out
+    ex.stage([&](int lane) { if (lane <= N) S.fwd_prep(lane); });
+    for (int s = 0; s < N; ++s) ex.stage([&](int lane) { S.fwd_step(lane, s); });
+    ex.stage([&](int lane) { if (lane <= N) S.fwd_post(lane, dc); });
+    ex.stage_end();
+    ex.tick(3);
+    // ---- steps of the duals / slacks, fraction to the boundary
+    ex.par([&](int tid, BR& br, double* part) {
+      if (S.is_block(tid)) S.backsub_block(tid, br, mu, tau, part);
+      else if (S.is_stage(tid)) S.backsub_stage(S.stage_lane(tid), mu, tau, part);
+      else { part[QS_DPHI] = 0.0; part[QN_AMAX] = 1.0; part[QN_AZ] = 1.0; }
+    });
+    ex.template reduce<QS_DPHI, 1, 0, 0, QN_AMAX, 2>();
+    ex.tick(4);
+    const double Dphi = ex.red[QS_DPHI], a_max = ex.red[QN_AMAX], a_z = ex.red[QN_AZ];
+    if (!f_active) {
+      thmax = 1e4 * fmax(1.0, th); thmin = 1e-4 * fmax(1.0, th);
+      f_active = true; f_n = 0; f_wr = 0;
+    }
+    double a_min;
+    if (Dphi < 0 && th <= thmin) a_min = fmin(g_th, fmin(g_ph * th / (-Dphi), (th > 0) ? pow(th, s_th) / pow(-Dphi, s_ph) : g_th));
+    else if (Dphi < 0) a_min = fmin(g_th, g_ph * th / (-Dphi));
+    else a_min = g_th;
+    a_min *= 0.05;
+    // ---- filter line search
+    double a = a_max;
+    int accepted = 0;
+    while (a >= a_min * (1 - 1e-12)) {
+      ex.par([&](int tid, BR& br, double* part) {
+        if (S.is_block(tid)) S.trial_block(tid, br, a, part);
+        else if (S.is_stage(tid)) S.trial_stage(S.stage_lane(tid), a, part);
+        else { part[0] = part[1] = part[2] = 0.0; }
+      });
+      ex.template reduce<0, 3, 0, 0, 0, 0>();
+      const double tht = ex.red[1], pht = ex.red[0] - mu * ex.red[2];
+      accepted = 0;
+      if (isfinite(pht) && tht < thmax) {
+        bool dom = false;
+        for (int q = 0; q < f_n; ++q) dom = dom || (tht >= G.fth[q] && pht >= G.fph[q]);
+        if (!dom) {
+          const bool sw = (Dphi < 0) && (a * pow(-Dphi, s_ph) > pow(th, s_th));
+          if (th <= thmin && sw) {
+            if (pht <= ph0 + eta_ph * a * Dphi + 10 * 2.220446049250313e-16 * fabs(ph0)) accepted = 2;
+          } else if (tht <= (1 - g_th) * th || pht <= ph0 - g_ph * th)
+            accepted = 1;
+        }
+      }
+      if (accepted) break;
+      a *= 0.5;
+    }
+    // IPOPT ends with Solved_To_Acceptable_Level when it cannot progress from an acceptable point; the second
+    // clause is the rounding-noise floor of a degenerate vertex of the OBCA dual polytope
+    const bool at_floor = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
+    ex.tick(5);
+    ex.trace(iter, Ef, th, E0, mu, dw, accepted ? a : -1.0);
+    if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
+    nstall = (a < stall_alpha) ? nstall + 1 : 0;
+    if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (accepted == 1) {
+      const int slot = (f_n < FILT_MAX) ? f_n++ : (f_wr % FILT_MAX);
+      ex.once([&]() { G.fth[slot] = (1 - g_th) * th; G.fph[slot] = ph0 - g_ph * th; });
+      f_wr++;
+    }
+    ex.par([&](int tid, BR& br, double* part) { (void)part; S.update(tid, br, a, a_z, mu); });
+    ex.tick(6);
+    iter++;
+  }
+  ex.tick(7);
+  iters_out = iter;
+  if (status < 0 && best_E0 < 1e300) {
+    // x, u, lam, mu, T of the stored acceptable point are already in the result arrays
+    ex.once([&]() { S.kp.status[inst] = OBCA_ST_ACCEPTABLE; S.kp.iters[inst] = iter; });
+    obj_out = best_f;
+    return OBCA_ST_STORED;
+  }
+  obj_out = fcur;
+  return status;
+}
+
+}  // namespace obca

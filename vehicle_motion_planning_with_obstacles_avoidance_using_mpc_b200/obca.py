@@ -82,7 +82,7 @@ class BatchSolver:
                     status=torch.empty((B,), dtype=torch.int32, device=device),
                     iters=torch.empty((B,), dtype=torch.int32, device=device))
 
-    def solve(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, stream=None):
+    def solve(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, stream=None, Ts=None):
         import torch
 
         def dp(t, dtype=torch.float64):
@@ -97,7 +97,7 @@ class BatchSolver:
         shared = int(A.dim() == 2)
         if stream is None:
             stream = torch.cuda.current_stream(x0.device).cuda_stream
-        rc = self._L.obca_b200_solve(self._ctx, B, dp(x0), dp(u0), dp(xref), dp(uref), dp(T_max), dp(term),
+        rc = self._L.obca_b200_solve(self._ctx, B, dp(x0), dp(u0), dp(xref), dp(uref), dp(T_max), dp(term), dp(Ts),
                                      _abi.ptr(self.edge_ptr, C.c_int32), dp(A), dp(b0), dp(db), shared,
                                      dp(out["x"]), dp(out["u"]), dp(out["lam"]), dp(out["mu"]), dp(out["T"]),
                                      dp(out["obj"]), dp(out["status"], torch.int32), dp(out["iters"], torch.int32),
@@ -106,19 +106,36 @@ class BatchSolver:
         return out
 
     # ---- host path ---------------------------------------------------------------------------------
-    def solve_host(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None):
+    def alloc_host_outputs(self, B, pinned=False):
+        """Host result arrays; ``pinned=True`` backs them with page-locked memory (torch) so the D2H copies of
+        ``solve_host`` are true DMA transfers."""
         p = self.params
         N, R, no = p.N, p.rows, p.n_obs
-        x0, u0, xref, uref, T_max, term, A, b0, db = map(_f64, (x0, u0, xref, uref, T_max, term, A, b0, db))
+        shapes = dict(x=(B, N + 1, 3), u=(B, N, 2), lam=(B, N + 1, R), mu=(B, N + 1, 4 * no), T=(B,), obj=(B,))
+        if pinned:
+            import torch
+            out = {k: torch.empty(s, dtype=torch.float64).pin_memory().numpy() for k, s in shapes.items()}
+            out["status"] = torch.empty((B,), dtype=torch.int32).pin_memory().numpy()
+            out["iters"] = torch.empty((B,), dtype=torch.int32).pin_memory().numpy()
+            return out
+        out = {k: np.empty(s) for k, s in shapes.items()}
+        out["status"] = np.empty(B, np.int32); out["iters"] = np.empty(B, np.int32)
+        return out
+
+    def solve_host(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, Ts=None):
+        p = self.params
+        N, R, no = p.N, p.rows, p.n_obs
+        x0, u0, xref, uref, T_max, term, A, b0, db, Ts = map(_f64, (x0, u0, xref, uref, T_max, term, A, b0, db, Ts))
         B = x0.shape[0]
         if xref.shape != (B, N + 1, 3) or u0.shape != (B, 2) or x0.shape != (B, 3):
             raise ValueError("x0 (B,3), u0 (B,2), xref (B,N+1,3) expected")
         shared = int(A.ndim == 2)
-        out = dict(x=np.empty((B, N + 1, 3)), u=np.empty((B, N, 2)), lam=np.empty((B, N + 1, R)),
-                   mu=np.empty((B, N + 1, 4 * no)), T=np.empty(B), obj=np.empty(B),
-                   status=np.empty(B, np.int32), iters=np.empty(B, np.int32))
+        if out is None:
+            out = self.alloc_host_outputs(B)
+        elif out["x"].shape != (B, N + 1, 3) or out["lam"].shape != (B, N + 1, R) or out["mu"].shape != (B, N + 1, 4 * no):
+            raise ValueError("preallocated outputs do not match the batch")
         P = _abi.ptr
-        rc = self._L.obca_b200_solve_host(self._ctx, B, P(x0), P(u0), P(xref), P(uref), P(T_max), P(term),
+        rc = self._L.obca_b200_solve_host(self._ctx, B, P(x0), P(u0), P(xref), P(uref), P(T_max), P(term), P(Ts),
                                           P(self.edge_ptr, C.c_int32), P(A), P(b0), P(db), shared,
                                           P(out["x"]), P(out["u"]), P(out["lam"]), P(out["mu"]), P(out["T"]),
                                           P(out["obj"]), P(out["status"], C.c_int32), P(out["iters"], C.c_int32))
@@ -170,15 +187,27 @@ class obca:
     """Same name, same methods, same returns as the reference's solver object (no constructor arguments,
     closed_loop.py:22)."""
 
-    init = INIT_WARM     # INIT_ZERO reproduces the reference's IPOPT start point (obca.py:856, SURVEY Q3)
+    # start point: None = automatic (A* warm start when xref is a path window; the reference's own IPOPT start -
+    # every variable 0, Topt = 1, obca.py:856 - when xref is the degenerate start/goal-only reference of
+    # closed_loop.py:535-544, whose poses are useless as an initial trajectory), or force INIT_ZERO / INIT_XREF / INIT_WARM
+    init = None
     device = -1
+
+    @staticmethod
+    def _auto_init(xref, x0, N):
+        P = np.concatenate([np.asarray(x0, float).reshape(3, 1)[:2], np.asarray(xref, float).reshape(3, N + 1)[:2, 1:]], axis=1)
+        seg = np.sqrt((np.diff(P, axis=1) ** 2).sum(0))
+        tot = seg.sum()
+        if N > 2 and tot > 0 and seg.max() > 0.5 * tot:
+            return INIT_ZERO
+        return INIT_WARM
 
     def _one(self, mode, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs, bObs, dmin, ego, u0,
              terminal_set=None, uref=None):
         r = solve_batch(mode, Ts, P, Q, R, int(N), np.asarray(x0, float).reshape(1, 3), xL, xU, uL, uU,
                         np.asarray(xref, float).reshape(1, 3, int(N) + 1), int(nObs), vObs, AObs, bObs, dmin, ego,
-                        np.asarray(u0, float).reshape(1, 2), terminal_set=terminal_set, uref=uref, init=self.init,
-                        device=self.device)
+                        np.asarray(u0, float).reshape(1, 2), terminal_set=terminal_set, uref=uref,
+                        init=self._auto_init(xref, x0, int(N)) if self.init is None else self.init, device=self.device)
         self.lam, self.mu = r["lam"][0], r["mu"][0]
         self.obj, self.status, self.iters, self.T = float(r["obj"][0]), int(r["status"][0]), int(r["iters"][0]), float(r["T"][0])
         return r["x"][0], r["u"][0], bool(r["feas"][0]), float(r["Ts_opt"][0])

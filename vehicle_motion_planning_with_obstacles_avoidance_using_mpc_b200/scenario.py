@@ -116,9 +116,11 @@ def update_reference_trajectory(N, ref, x0):
     return ref[:, idx].copy()
 
 
-def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0)):
+def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_seed=None):
     """cfg 2: N=10, 2 quads, FREE.  cfg 3: N=20, 4 quads, FREE (headline).  cfg 5: cfg 3 + 2 dynamic boxes,
-    FIXED_SET with Ts = 2.0 and terminal set [x0.x+5, 99] x [1, 9] (closed_loop.py:371)."""
+    FIXED_SET with Ts = 2.0 and terminal set [x0.x+5, 99] x [1, 9] (closed_loop.py:371).
+    ``pose_seed`` draws the start poses from their own stream (same scene, different instances: one shard per
+    rank in the multi-GPU runs)."""
     from . import obca as _o
     rng = np.random.default_rng((20221209 + cfg) if seed is None else seed)
     if cfg == 2:
@@ -148,6 +150,8 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0)):
             vObs.append(5)
     AObs, bObs = mo.stacked_H_rep(polys, vObs, info, N, Ts)
 
+    if pose_seed is not None:
+        rng = np.random.default_rng(pose_seed)
     # free start cells with clearance; A* once per distinct cell
     cells = [(cx, cy) for cx in range(1, 36) for cy in range(1, 10)
              if grid[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3].sum() == 0]
