@@ -23,6 +23,7 @@ struct HostExec {
     memset(brs.data(), 0, sizeof(BlockRegs<EMAX>) * T_);
   }
   template <class F> void par(F&& f) { for (int t = 0; t < T; ++t) f(t, brs[t], parts[t].data()); }
+  template <class F> void all(F&& f) { for (int t = 0; t < T; ++t) f(t); }
   template <class F> void stage(F&& f) { for (int l = 0; l < 32; ++l) f(l); }
   void stage_end() {}
   template <class F> void once(F&& f) { f(); }
@@ -30,7 +31,10 @@ struct HostExec {
   void trace(int it, double f, double th, double E0, double mu, double dw, double a) {
     if (getenv("OBCA_EMU_TRACE")) printf("  it %3d f %.6e th %.3e E0 %.3e mu %.1e dw %.1e a %.3e\n", it, f, th, E0, mu, dw, a);
   }
-  template <int S0, int NS, int M0, int NM, int N0, int NN> void reduce() {
+  template <int S0, int NS, int M0, int NM, int N0, int NN> void reduce(double* scratch) {
+    // the device version stages the partials in `scratch`, which aliases step / Hessian storage: clobber it here so
+    // that a wrong liveness assumption shows up in the emulation as well
+    for (int i = 0; i < (NS + NM + NN) * red_stride(T); ++i) scratch[i] = 0.0 / 0.0;
     for (int q = 0; q < NS; ++q) { double a = 0; for (int t = 0; t < T; ++t) a += parts[t][S0 + q]; red[S0 + q] = a; }
     for (int q = 0; q < NM; ++q) { double a = parts[0][M0 + q]; for (int t = 1; t < T; ++t) a = fmax(a, parts[t][M0 + q]); red[M0 + q] = a; }
     for (int q = 0; q < NN; ++q) { double a = parts[0][N0 + q]; for (int t = 1; t < T; ++t) a = fmin(a, parts[t][N0 + q]); red[N0 + q] = a; }

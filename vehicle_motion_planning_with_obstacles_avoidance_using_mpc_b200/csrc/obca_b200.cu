@@ -18,19 +18,50 @@ namespace obca {
 __device__ unsigned long long g_prof[16];
 #endif
 
+// Block reduction, two stages through shared memory.  `buf` holds nt rows (one per slot) of one value per thread
+// (row stride red_stride(T): a pad word every 16 values spreads stage A over the banks).  Stage A: 8 threads per
+// slot each fold T/8 consecutive values; stage B: one thread per slot folds the 8 partials into RED[slot].
+// Slots [0, ns) are sums, [ns, ns+nm) maxima, the rest minima.  One copy of this code serves every reduction of the
+// kernel (it is deliberately not inlined: instruction fetch is what limits this kernel).
+__device__ __noinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt) {
+  const int rs = red_stride(T), L = T >> 3;
+  double* P2 = RED + NPART;
+  for (int j = tid; j < nt * 8; j += T) {
+    const int q = j >> 3, seg = j & 7;
+    const double* row = buf + q * rs + seg * L + ((seg * L) >> 4);
+    double a = row[0];
+    for (int i = 1; i < L; ++i) {
+      const double b = row[i + (((seg * L + i) >> 4) - ((seg * L) >> 4))];
+      a = (q < ns) ? a + b : (q < ns + nm) ? fmax(a, b) : fmin(a, b);
+    }
+    P2[j] = a;
+  }
+  __syncthreads();
+  if (tid < nt) {
+    double a = P2[tid * 8];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const double b = P2[tid * 8 + i];
+      a = (tid < ns) ? a + b : (tid < ns + nm) ? fmax(a, b) : fmin(a, b);
+    }
+    RED[tid] = a;
+  }
+  __syncthreads();
+}
+
 // Execution model of solve_instance() on the device: one CTA, registers for the per-thread state
 template <int EMAX>
 struct DevExec {
   BlockRegs<EMAX> br;
   double part[NPART];
-  double red[NPART];
-  double* RED;
+  double* red;   // block-reduced values (shared memory), valid after reduce()
   int tid, lane, warp, nwarps;
   bool stage_warp;
 #ifdef OBCA_PROFILE
   long long prof[8], prof_t;
 #endif
   template <class F> __device__ __forceinline__ void par(F&& f) { f(tid, br, part); __syncthreads(); }
+  template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
   }
@@ -44,54 +75,20 @@ struct DevExec {
     (void)i;
 #endif
   }
-  // one block reduction: sums of part[S0..], maxima of part[M0..], minima of part[N0..] -> red[] (same slots)
-  template <int S0, int NS, int M0, int NM, int N0, int NN> __device__ __forceinline__ void reduce() {
-    double v[NS + NM + NN + 1];
+  // one block reduction: sums of part[S0..], maxima of part[M0..], minima of part[N0..] -> red[] (same slots).
+  // Slot ranges must be laid out S | M | N consecutively in part[] (they are: see the PS_/PM_/PN_ enums).
+  template <int S0, int NS, int M0, int NM, int N0, int NN> __device__ __forceinline__ void reduce(double* scratch) {
+    const int T = 32 * nwarps, rs = red_stride(T), pos = tid + (tid >> 4);
 #pragma unroll
-    for (int q = 0; q < NS; ++q) {
-      double a = part[S0 + q];
+    for (int q = 0; q < NS; ++q) scratch[q * rs + pos] = part[S0 + q];
 #pragma unroll
-      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      v[q] = a;
-    }
+    for (int q = 0; q < NM; ++q) scratch[(NS + q) * rs + pos] = part[M0 + q];
 #pragma unroll
-    for (int q = 0; q < NM; ++q) {
-      double a = part[M0 + q];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
-      v[NS + q] = a;
-    }
-#pragma unroll
-    for (int q = 0; q < NN; ++q) {
-      double a = part[N0 + q];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
-      v[NS + NM + q] = a;
-    }
-    if (lane == 0) {
-#pragma unroll
-      for (int q = 0; q < NS + NM + NN; ++q) RED[warp * NPART + q] = v[q];
-    }
+    for (int q = 0; q < NN; ++q) scratch[(NS + NM + q) * rs + pos] = part[N0 + q];
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < NS; ++q) {
-      double a = RED[q];
-      for (int w = 1; w < nwarps; ++w) a += RED[w * NPART + q];
-      red[S0 + q] = a;
-    }
-#pragma unroll
-    for (int q = 0; q < NM; ++q) {
-      double a = RED[NS + q];
-      for (int w = 1; w < nwarps; ++w) a = fmax(a, RED[w * NPART + NS + q]);
-      red[M0 + q] = a;
-    }
-#pragma unroll
-    for (int q = 0; q < NN; ++q) {
-      double a = RED[NS + NM + q];
-      for (int w = 1; w < nwarps; ++w) a = fmin(a, RED[w * NPART + NS + NM + q]);
-      red[N0 + q] = a;
-    }
-    __syncthreads();
+    // results land at red[slot] = RED[slot]: shift the base so that RED[0] is slot S0 (or M0 / N0 when NS == 0)
+    constexpr int first = (NS > 0) ? S0 : ((NM > 0) ? M0 : N0);
+    cta_reduce(scratch, red + first, T, tid, NS, NM, NS + NM + NN);
   }
 };
 
@@ -104,7 +101,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
   sm_carve(sm, obca_smem, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps, has_uref);
   const Solver<EMAX> S(kp, sm);
   DevExec<EMAX> ex;
-  ex.RED = sm.RED;
+  ex.red = sm.RED;
   ex.tid = threadIdx.x; ex.lane = threadIdx.x & 31; ex.warp = threadIdx.x >> 5; ex.nwarps = nwarps;
   ex.stage_warp = (ex.warp == nwarps - 1);
   bool first = true;

@@ -21,6 +21,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/obca_b200.h"
 
@@ -66,14 +67,27 @@ struct Sm {
   double *K, *KAP, *PM, *PV, *XI;
   double *ETA, *DLAM, *DMU, *DYE, *DSN, *DSD, *EX;
   double *A, *B0, *DB, *XREF, *UREF;
-  double *RIC, *RED;
+  double *RIC, *RED, *SCR_D, *SCR_H;
+  uint32_t* TAB;
   Glob* G;
   OB_HD double& st(double* p, int e, int k) const { return p[e * S1 + k]; }
   OB_HD double& bl(double* p, int e, int t) const { return p[e * nb + t]; }
 };
 
+// row stride of the block-reduction scratch: one value per thread, one pad word per 16 (bank spread of stage A)
+OB_HD int red_stride(int T) { return T + (T >> 4); }
+
 constexpr int EX_N = 16;   // per block: G(6) Ga(3) Gb(3) gLz(3) h22(1)
-constexpr int RIC_N = 64;
+constexpr int RIC_N = 96;   // F8(36) f(8) W(36) pc(6) of the Riccati step in flight
+// task tables of the cooperative Riccati sweep (uint32 words, filled per instance by fill_tables).  One task = one
+// output entry = a dot product of <= 4 terms; a term word holds two shared-memory offsets (in doubles, already
+// multiplied by the stage stride): coefficient offset | operand offset << 16
+constexpr int TW = 0;              // 42 x 4  W = P At (36 entries) and pc = p - P c (6 entries)
+constexpr int TF = TW + 42 * 4;    // 29 x 4  F = H + At^T W (21 entries), f = r + At^T pc (8 entries)
+constexpr int TFH = TF + 29 * 4;   // 21      packed index of the F entry | dw class << 8
+constexpr int TFC = TFH + 21;      // 15      entries of F that are plain copies of H (rows/cols v_prev, w_prev)
+constexpr int TB = TFC + 15;       // 27 x 2  elimination of (v, w): packed F indices
+constexpr int TAB_N = TB + 54;
 
 OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int has_uref) {
   const int S1 = N + 1, nb = no * S1;
@@ -82,14 +96,25 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   auto take = [&](size_t n) { double* p = base ? base + o : nullptr; o += n; return p; };
   s.Z = take(3 * S1); s.U = take(2 * S1); s.YD = take(3 * S1);
   s.SXY = take(4 * S1); s.ZXY = take(4 * S1); s.SUB = take(8 * S1); s.ZUB = take(8 * S1);
+  // step arrays first: together with the padding they double as the scratch of the 12-slot block reduction that
+  // follows assemble (nothing of the previous step is alive then); same for H|RA and the 3-slot reductions
+  const size_t d0 = o;
   s.DZ = take(3 * S1); s.DU = take(2 * S1); s.DYD = take(3 * S1); s.DSXY = take(4 * S1); s.DSUB = take(8 * S1);
+  s.DLAM = take((size_t)R * S1); s.DMU = take(4 * (size_t)nb); s.DYE = take(2 * (size_t)nb);
+  s.DSN = take(nb); s.DSD = take(nb); s.XI = take(6 * S1);
+  if (o - d0 < (size_t)NPART * red_stride(s.T)) take((size_t)NPART * red_stride(s.T) - (o - d0));
+  s.SCR_D = base ? base + d0 : nullptr;
+  const size_t h0 = o;
   s.H = take(36 * S1); s.RA = take(8 * S1);   // H|RA (44 S1) is re-used by the roll-out as ACL(36)|CCL(6)
-  s.RB = take(8 * S1); s.CD = take(3 * S1); s.GF = take(8 * S1); s.GL = take(8 * S1); s.DYN = take(8 * S1);
-  s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1); s.XI = take(6 * S1);
-  s.ETA = take(25 * (size_t)nb); s.DLAM = take((size_t)R * S1); s.DMU = take(4 * (size_t)nb); s.DYE = take(2 * (size_t)nb);
-  s.DSN = take(nb); s.DSD = take(nb); s.EX = take(EX_N * (size_t)nb);
+  if (o - h0 < (size_t)3 * red_stride(s.T)) take((size_t)3 * red_stride(s.T) - (o - h0));
+  s.SCR_H = base ? base + h0 : nullptr;
+  s.RB = take(8 * S1); s.GF = take(8 * S1); s.GL = take(8 * S1);
+  s.DYN = take(13 * S1); s.CD = s.DYN ? s.DYN + 10 * S1 : nullptr;   // CD = elements 10..12 of DYN (one coefficient base)
+  s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1);
+  s.ETA = take(25 * (size_t)nb); s.EX = take(EX_N * (size_t)nb);
   s.A = take(2 * R); s.B0 = take(R); s.DB = take(R); s.XREF = take(3 * S1); s.UREF = take(has_uref ? 2 * N : 0);
-  s.RIC = take(RIC_N); s.RED = take((size_t)NPART * nwarps);
+  s.RIC = take(RIC_N); s.RED = take(NPART + 8 * NPART);
+  s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
   s.G = (Glob*)(base ? base + o : nullptr); o += (sizeof(Glob) + 7) / 8;
   return o;  // doubles
 }
@@ -110,9 +135,64 @@ OB_HD void ob_sincos(double x, double* s, double* c) {
 #endif
 }
 
+// Branch-free reciprocal / reciprocal square root: hardware seed (MUFU.RCP64H / RSQ64H, ~2^-23) + two Newton steps
+// in FMA arithmetic (~1 ulp).  No slow-path call, no divergence region: the IEEE division/sqrt sequences are what
+// bloats the instruction stream of this kernel (see profiles/).  Arguments are positive normal numbers here.
+OB_HD double ob_rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+OB_HD double ob_rsqrt(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-h * r, r, 0.5);
+  return fma(r, e, r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+// sum of logarithms as the logarithm of a product: mantissas are multiplied, exponents added (one log per thread
+// and phase instead of one per inequality).  Non-positive arguments poison the mantissa with NaN.
+struct LogAcc {
+  double m = 1.0;
+  int e = 0;
+  OB_HD void add(double S) {
+    long long b;
+#if defined(__CUDA_ARCH__)
+    b = __double_as_longlong(S);
+#else
+    memcpy(&b, &S, 8);
+#endif
+    e += (int)((b >> 52) & 0x7ff) - 1023;
+    long long mb = (b & 0x800fffffffffffffLL) | 0x3ff0000000000000LL;
+    double mm;
+#if defined(__CUDA_ARCH__)
+    mm = __longlong_as_double(mb);
+#else
+    memcpy(&mm, &mb, 8);
+#endif
+    m *= (S > 0.0) ? mm : (0.0 / 0.0);
+    if (m > 1e200) { m *= 0x1p-512; e += 512; }
+  }
+  OB_HD double value() const { return log(m) + e * 0.6931471805599453; }
+};
+
 // 5x5 square-root factor R^T (lower triangular, packed) with Givens row insertion
 struct Tri5 {
   double l[15];
+  double id[5];   // 1 / diagonal (set by finish)
   OB_HD void zero() {
 #pragma unroll
     for (int i = 0; i < 15; ++i) l[i] = 0.0;
@@ -123,8 +203,8 @@ struct Tri5 {
     for (int c = 0; c < 5; ++c) {
       double a = at(c, c), b = row[c];
       if (b != 0.0) {
-        double rr = sqrt(a * a + b * b), cs = a / rr, sn = b / rr;
-        at(c, c) = rr;
+        const double n2 = a * a + b * b, ir = ob_rsqrt(n2), cs = a * ir, sn = b * ir;
+        at(c, c) = n2 * ir;
 #pragma unroll
         for (int q = c + 1; q < 5; ++q) {
           double u = at(q, c), w = row[q];
@@ -143,6 +223,7 @@ struct Tri5 {
         for (int q = a; q < 5; ++q) at(q, a) = -at(q, a);
       }
       ok = ok && (at(a, a) > 0) && isfinite(at(a, a));
+      id[a] = ob_rcp(at(a, a));
     }
     return ok;
   }
@@ -153,14 +234,14 @@ struct Tri5 {
       double s = r[i];
 #pragma unroll
       for (int q = 0; q < i; ++q) s -= at(i, q) * t[q];
-      t[i] = s / at(i, i);
+      t[i] = s * id[i];
     }
 #pragma unroll
     for (int i = 4; i >= 0; --i) {
       double s = t[i];
 #pragma unroll
       for (int q = i + 1; q < 5; ++q) s -= at(q, i) * x[q];
-      x[i] = s / at(i, i);
+      x[i] = s * id[i];
     }
   }
 };
@@ -174,11 +255,12 @@ OB_HD int symi(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1)
 // statistics of one inequality (slack S, multiplier Z, value d); returns sigma and the mu-split of the
 // step-form right-hand side  t - Z = mu * ta + tb
 struct IneqAcc {
-  double th = 0, lg = 0, cmax = 0, sumz = 0, szmax = 0, szmin = 1e300;
+  double th = 0, cmax = 0, sumz = 0, szmax = 0, szmin = 1e300;
+  LogAcc lg;
   OB_HD void add(double S, double Z, double d, double& sig, double& ta, double& tb) {
     double rd = d - S;
-    sig = Z / S; ta = 1.0 / S; tb = -Z - sig * rd;
-    th += fabs(rd); cmax = fmax(cmax, fabs(rd)); lg += log(S); sumz += Z;
+    ta = ob_rcp(S); sig = Z * ta; tb = -Z - sig * rd;
+    th += fabs(rd); cmax = fmax(cmax, fabs(rd)); lg.add(S); sumz += Z;
     double sz = S * Z; szmax = fmax(szmax, sz); szmin = fmin(szmin, sz);
   }
 };
@@ -214,6 +296,19 @@ struct Solver {
   OB_HD double bk(int k, int r) const { return sm.B0[r] + (stacked ? k * sm.DB[r] : 0.0); }
   OB_HD const double* xref(int k) const { return sm.XREF + 3 * k; }
 
+  // row j of a dual block (lambda rows 0..E-1, then the four mu rows): variable, slack, multiplier.  The block state
+  // lives in registers, so the (warp-uniform) row index is resolved by selects, which keeps the row loops ROLLED:
+  // one copy of the Givens-insertion code instead of E+7 (instruction fetch, not arithmetic, limits this kernel)
+  OB_HD static void row_regs(const BlockRegs<EMAX>& br, int j, int E, double& wv, double& S, double& Z) {
+    const int q = (j < E) ? j : EMAX + (j - E);
+    wv = 0.0; S = 1.0; Z = 1.0;
+#pragma unroll
+    for (int c = 0; c < EMAX; ++c)
+      if (c == q) { wv = br.lam[c]; S = br.Sl[c]; Z = br.Zl[c]; }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (EMAX + c == q) { wv = br.mu[c]; S = br.Sm_[c]; Z = br.Zm[c]; }
+  }
   OB_HD void row_y(const BlkGeo& b, int k, int r0, int E, int j, double yv[5]) const {
     const Glob& G = *sm.G;
     if (j < E) {
@@ -522,7 +617,7 @@ struct Solver {
         gf[a] += s;
       }
     }
-    double dyn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double dyn[10] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0.0};
     if (k < N) {
       // (2) input cost
       double uu[2] = {u[0], u[1]};
@@ -667,9 +762,10 @@ struct Solver {
       sm.st(sm.RA, i, k) = ra[i]; sm.st(sm.RB, i, k) = rb[i]; sm.st(sm.GL, i, k) = gL[i] + gf[i];
       sm.st(sm.GF, i, k) = gf[i]; sm.st(sm.DYN, i, k) = dyn[i];
     }
+    sm.st(sm.DYN, 8, k) = dyn[8]; sm.st(sm.DYN, 9, k) = dyn[9];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sm.st(sm.CD, j, k) = (k < N) ? sv.cd[j] : 0.0;
-    part[PS_F] = sv.f; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg; part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
+    part[PS_F] = sv.f; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg.value(); part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
     part[PS_GT] = 0.0; part[PM_E1] = 0.0; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
     part[PM_CT] = ctmax; part[PM_BAD] = 0.0; part[PN_SZMIN] = acc.szmin;
   }
@@ -713,68 +809,84 @@ struct Solver {
     Tri5 Lf;
     Lf.zero();
     double g0a[5] = {0, 0, 0, 0, 0}, g0b[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < EMAX + 4; ++j) {
-      if (j < E || j >= EMAX) {
-        const int jj = (j < EMAX) ? j : E + (j - EMAX);   // logical row index: lambda rows then the 4 mu rows
-        double wv, S, Z, yv[5], yh[5];
-        if (j < EMAX) { wv = br.lam[j]; S = br.Sl[j]; Z = br.Zl[j]; }
-        else { wv = br.mu[j - EMAX]; S = br.Sm_[j - EMAX]; Z = br.Zm[j - EMAX]; }
-        row_y(b, k, r0, E, jj, yv);
+    const double aa = a1 * a1 + a2 * a2, lam1 = 2 * Zn + 4 * sn * aa;
+    const double ci0 = ob_rcp(2 * Zn), ci1 = 4 * sn * ob_rcp(lam1);
+    const int nrow = E + 4;
+#pragma unroll 1
+    for (int j = 0; j < nrow + 3; ++j) {
+      double yh[5];
+      if (j < nrow) {
+        double wv, S, Z, yv[5];
+        row_regs(br, j, E, wv, S, Z);
+        row_y(b, k, r0, E, j, yv);
         double sig, ta, tb;
         acc.add(S, Z, wv, sig, ta, tb);
         const double gl = y1 * yv[3] + y2 * yv[4] - Z + 2 * Zn * (a1 * yv[0] + a2 * yv[1]) - Zd * yv[2];
         e1 = fmax(e1, fabs(gl));
         tb -= gl;
-        const double di = 1.0 / fmax(sig, SIG_MIN), sq = sqrt(di);
+        const double sq = ob_rsqrt(fmax(sig, SIG_MIN)), di = sq * sq;
 #pragma unroll
         for (int a = 0; a < 5; ++a) { g0a[a] += yv[a] * ta * di; g0b[a] += yv[a] * tb * di; yh[a] = yv[a] * sq; }
-        Lf.insert(yh);
-      }
-    }
-    const double aa = a1 * a1 + a2 * a2, lam1 = 2 * Zn + 4 * sn * aa;
-    const double ci0 = 1.0 / (2 * Zn), ci1 = 4 * sn / lam1;
-    bool ok;
-    {
-      double r1[5] = {0, 0, 0, 0, 0}, r2[5] = {0, 0, 0, 0, 0}, r3[5] = {0, 0, sqrt(1.0 / sd), 0, 0};
-      if (aa > 0) {
-        double na = sqrt(aa), e1_ = a1 / na, e2_ = a2 / na, s1 = sqrt(1.0 / lam1), s2 = sqrt(ci0);
-        r1[0] = s1 * e1_; r1[1] = s1 * e2_; r2[0] = -s2 * e2_; r2[1] = s2 * e1_;
       } else {
-        r1[0] = sqrt(ci0); r2[1] = r1[0];
+        // the three rows of C = blockdiag(Cn^-1, 1/sd, 0, 0) in square-root form
+#pragma unroll
+        for (int a = 0; a < 5; ++a) yh[a] = 0.0;
+        if (j == nrow + 2) {
+          yh[2] = ob_rsqrt(sd);
+        } else if (aa > 0) {
+          const double ina = ob_rsqrt(aa), e1_ = a1 * ina, e2_ = a2 * ina;
+          if (j == nrow) { const double s1 = ob_rsqrt(lam1); yh[0] = s1 * e1_; yh[1] = s1 * e2_; }
+          else { const double s2 = ob_rsqrt(2 * Zn); yh[0] = -s2 * e2_; yh[1] = s2 * e1_; }
+        } else {
+          const double s2 = ob_rsqrt(2 * Zn);
+          if (j == nrow) yh[0] = s2; else yh[1] = s2;
+        }
       }
-      Lf.insert(r1); Lf.insert(r2); Lf.insert(r3);
-      ok = Lf.finish();
+      Lf.insert(yh);
     }
-    // column 0 (split in mu): h0 = -2 tn a,  rhs = (g0 - Cn^-1 h0, g0[2] - tds, g0[3] + e1, g0[4] + e2)
+    const bool ok = Lf.finish();
+    // right-hand sides: column 0 split in mu (h0 = -2 tn a), then the three pose columns
     double h0a[2] = {-2 * tna * a1, -2 * tna * a2}, h0b[2] = {-2 * tnb * a1, -2 * tnb * a2};
-    double cha[2], chb[2], rhs[5], eta0a[5], eta0b[5];
+    double cha[2], chb[2];
     cn_inv(b, ci0, ci1, h0a, cha);
     cn_inv(b, ci0, ci1, h0b, chb);
-    rhs[0] = g0a[0] - cha[0]; rhs[1] = g0a[1] - cha[1]; rhs[2] = g0a[2] - 1.0 / Zd; rhs[3] = g0a[3]; rhs[4] = g0a[4];
-    Lf.solve(rhs, eta0a);
-    rhs[0] = g0b[0] - chb[0]; rhs[1] = g0b[1] - chb[1]; rhs[2] = g0b[2] + dd; rhs[3] = g0b[3] + ce1; rhs[4] = g0b[4] + ce2;
-    Lf.solve(rhs, eta0b);
-#pragma unroll
-    for (int a = 0; a < 5; ++a) { sm.bl(sm.ETA, a, tid) = eta0a[a]; sm.bl(sm.ETA, 5 + a, tid) = eta0b[a]; }
-    // Lagrangian gradient wrt the pose from this block
     const double offt = G.off * (-st * a1 + ct * a2);
     const double dpose[3] = {a1, a2, offt};
     const double jt0 = -st * a1 + ct * a2, jt1 = -ct * a1 - st * a2;
     double gLz[3] = {-Zd * dpose[0], -Zd * dpose[1], y1 * jt0 + y2 * jt1 - Zd * dpose[2]};
-    // pose columns and Schur complement (pose of stage 0 is fixed: columns unused but harmless)
     const double ydv = -Zd, c1 = y1 + ydv * G.off;
     const double hc[3][2] = {{ydv, 0.0}, {0.0, ydv}, {-c1 * st - y2 * ct, c1 * ct - y2 * st}};
-    double bc[3][5], etc[3][5];
+    double bc[3][5];
+    sm.bl(sm.ETA, 0, tid) = g0a[0] - cha[0]; sm.bl(sm.ETA, 1, tid) = g0a[1] - cha[1]; sm.bl(sm.ETA, 2, tid) = g0a[2] - ob_rcp(Zd);
+    sm.bl(sm.ETA, 3, tid) = g0a[3]; sm.bl(sm.ETA, 4, tid) = g0a[4];
+    sm.bl(sm.ETA, 5, tid) = g0b[0] - chb[0]; sm.bl(sm.ETA, 6, tid) = g0b[1] - chb[1]; sm.bl(sm.ETA, 7, tid) = g0b[2] + dd;
+    sm.bl(sm.ETA, 8, tid) = g0b[3] + ce1; sm.bl(sm.ETA, 9, tid) = g0b[4] + ce2;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       cn_inv(b, ci0, ci1, hc[c], bc[c]);
       bc[c][2] = dpose[c];
       bc[c][3] = (c == 2) ? jt0 : 0.0;
       bc[c][4] = (c == 2) ? jt1 : 0.0;
-      Lf.solve(bc[c], etc[c]);
 #pragma unroll
-      for (int a = 0; a < 5; ++a) sm.bl(sm.ETA, 10 + 5 * c + a, tid) = etc[c][a];
+      for (int a = 0; a < 5; ++a) sm.bl(sm.ETA, 10 + 5 * c + a, tid) = bc[c][a];
+    }
+    // five solves with the same factor, rolled: right-hand sides are staged in (and overwritten by the solutions in)
+    // this thread's ETA column
+#pragma unroll 1
+    for (int c = 0; c < 5; ++c) {
+      double r[5], x[5];
+#pragma unroll
+      for (int a = 0; a < 5; ++a) r[a] = sm.bl(sm.ETA, 5 * c + a, tid);
+      Lf.solve(r, x);
+#pragma unroll
+      for (int a = 0; a < 5; ++a) sm.bl(sm.ETA, 5 * c + a, tid) = x[a];
+    }
+    double eta0a[5], eta0b[5], etc[3][5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      eta0a[a] = sm.bl(sm.ETA, a, tid); eta0b[a] = sm.bl(sm.ETA, 5 + a, tid);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) etc[c][a] = sm.bl(sm.ETA, 10 + 5 * c + a, tid);
     }
     const double h22 = y1 * (-ct * a1 - st * a2) + y2 * (st * a1 - ct * a2) + ydv * G.off * (-ct * a1 - st * a2);
     int e = 0;
@@ -796,7 +908,7 @@ struct Solver {
       sm.bl(sm.EX, 6 + cp, tid) = Ga; sm.bl(sm.EX, 9 + cp, tid) = Gb; sm.bl(sm.EX, 12 + cp, tid) = gLz[cp];
     }
     sm.bl(sm.EX, 15, tid) = h22;
-    part[PS_F] = 0.0; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg; part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
+    part[PS_F] = 0.0; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg.value(); part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
     part[PS_GT] = 0.0; part[PM_E1] = e1; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
     part[PM_CT] = 0.0; part[PM_BAD] = ok ? 0.0 : 1.0; part[PN_SZMIN] = acc.szmin;
   }
@@ -846,108 +958,157 @@ struct Solver {
   // Variables (x, y, th, v_prev, w_prev, T | v, w).  Sub-step A forms F = H + At^T P At and f = r + At^T pc;
   // sub-step B eliminates (v, w) and writes the cost-to-go of stage s.  Pivots double as the inertia test.
   // ------------------------------------------------------------------------------------------------
-  // column j of At = [A B] as <= 4 (row, value) pairs; columns 3, 4 (v_prev, w_prev) are empty
-  OB_HD int at_col(int s, int j, int rows[4], double vals[4]) const {
-    const double fth0 = sm.st(sm.DYN, 0, s), fth1 = sm.st(sm.DYN, 1, s), bv0 = sm.st(sm.DYN, 2, s), bv1 = sm.st(sm.DYN, 3, s);
-    const double bw = sm.st(sm.DYN, 4, s), fT0 = sm.st(sm.DYN, 5, s), fT1 = sm.st(sm.DYN, 6, s), fT2 = sm.st(sm.DYN, 7, s);
-    switch (j) {
-      case 0: rows[0] = 0; vals[0] = 1.0; return 1;
-      case 1: rows[0] = 1; vals[0] = 1.0; return 1;
-      case 2: rows[0] = 0; vals[0] = fth0; rows[1] = 1; vals[1] = fth1; rows[2] = 2; vals[2] = 1.0; return 3;
-      case 5: rows[0] = 0; vals[0] = fT0; rows[1] = 1; vals[1] = fT1; rows[2] = 2; vals[2] = fT2; rows[3] = 5; vals[3] = 1.0; return 4;
-      case 6: rows[0] = 0; vals[0] = bv0; rows[1] = 1; vals[1] = bv1; rows[2] = 3; vals[2] = 1.0; return 3;
-      case 7: rows[0] = 2; vals[0] = bw; rows[1] = 4; vals[1] = 1.0; return 2;
-      default: return 0;
+  // Column a of At = [A B] as <= 4 (row, coefficient) pairs; the coefficients are entries of the per-stage vector
+  // DYN = (fth0, fth1, bv0, bv1, bw, fT0, fT1, fT2, 1, 0); columns 3, 4 (v_prev, w_prev) are empty.
+  OB_HD static void at_col_tab(int a, int rows[4], int cfs[4]) {
+    for (int p = 0; p < 4; ++p) { rows[p] = 0; cfs[p] = 9; }
+    switch (a) {
+      case 0: rows[0] = 0; cfs[0] = 8; break;
+      case 1: rows[0] = 1; cfs[0] = 8; break;
+      case 2: rows[0] = 0; cfs[0] = 0; rows[1] = 1; cfs[1] = 1; rows[2] = 2; cfs[2] = 8; break;
+      case 5: rows[0] = 0; cfs[0] = 5; rows[1] = 1; cfs[1] = 6; rows[2] = 2; cfs[2] = 7; rows[3] = 5; cfs[3] = 8; break;
+      case 6: rows[0] = 0; cfs[0] = 2; rows[1] = 1; cfs[1] = 3; rows[2] = 3; cfs[2] = 8; break;
+      case 7: rows[0] = 2; cfs[0] = 4; rows[1] = 4; cfs[1] = 8; break;
+      default: break;
     }
   }
-  OB_HD void ric_terminal(int lane, double mu, double dw, double dc) const {
+  // thread -> task tables of the sweep (every thread fills a few words)
+  OB_HD void fill_tables(int tid) const {
+    const int I6[6] = {0, 1, 2, 5, 6, 7};
+    uint32_t* tab = sm.TAB;
+    int rows[4], cfs[4];
+    for (int t = tid; t < 42; t += sm.T) {
+      if (t < 36) {                                  // W[r][jj] = sum_p cf[c_p] P[r, row_p]
+        const int r = t / 6, jj = t % 6;
+        at_col_tab(I6[jj], rows, cfs);
+        for (int p = 0; p < 4; ++p) tab[TW + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)(symi(r, rows[p]) * S1) << 16);
+      } else {                                       // pc[r] = p[r] - sum_j cd[j] P[r, j]   (cd = DYN elements 10..12)
+        const int r = t - 36;
+        for (int p = 0; p < 4; ++p)
+          tab[TW + 4 * t + p] = (uint32_t)((p < 3 ? 10 + p : 9) * S1) | ((uint32_t)(symi(r, p < 3 ? p : 0) * S1) << 16);
+      }
+    }
+    for (int t = tid; t < 29; t += sm.T) {
+      if (t < 21) {                                  // F[a][b] = H[a][b] + sum_p cf[c_p] W[row_p][jb],  a, b in I6
+        int ia = 0;
+        while ((ia + 1) * (ia + 2) / 2 <= t) ++ia;
+        const int ib = t - ia * (ia + 1) / 2, a = I6[ia], b = I6[ib];
+        at_col_tab(a, rows, cfs);
+        for (int p = 0; p < 4; ++p) tab[TF + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)(rows[p] * 6 + ib) << 16);
+        const int cls = (a != b) ? 0 : (a < 3 ? 1 : (a >= 6 ? 2 : 3));
+        tab[TFH + t] = (uint32_t)symi(a, b) | ((uint32_t)cls << 8);
+      } else {                                       // f[a] = r[a] + sum_p cf[c_p] pc[row_p]
+        const int a = t - 21;
+        at_col_tab(a, rows, cfs);
+        for (int p = 0; p < 4; ++p) tab[TF + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)rows[p] << 16);
+      }
+    }
+    if (tid == 0) {
+      int n = 0;
+      for (int a = 0; a < 8; ++a)
+        for (int b = 0; b <= a; ++b)
+          if (a == 3 || a == 4 || b == 3 || b == 4) tab[TFC + n++] = (uint32_t)symi(a, b);
+    }
+    for (int t = tid; t < 27; t += sm.T) {          // elimination of (v, w) = variables 6, 7
+      if (t < 21) {
+        int a = 0;
+        while ((a + 1) * (a + 2) / 2 <= t) ++a;
+        const int b = t - a * (a + 1) / 2;
+        tab[TB + 2 * t] = (uint32_t)symi(a, b) | ((uint32_t)symi(6, a) << 8) | ((uint32_t)symi(7, a) << 16) | ((uint32_t)symi(6, b) << 24);
+        tab[TB + 2 * t + 1] = (uint32_t)symi(7, b);
+      } else {
+        const int a = t - 21;
+        tab[TB + 2 * t] = (uint32_t)symi(6, a) | ((uint32_t)symi(7, a) << 8);
+        tab[TB + 2 * t + 1] = 0;
+      }
+    }
+  }
+  // The sweep runs on ALL threads of the block (one task per thread, a block barrier per sub-step): a single warp
+  // would serialise two task rounds per sub-step, and the sweep is the longest dependent chain of an iteration.
+  OB_HD void ric_terminal(int t, double mu, double dw, double dc) const {
     // stage N: cost-to-go = its own 6x6 block (terminal equality folded in Levenberg-Marquardt style)
     const int s = N;
-    if (lane < 21) {
-      int a = 0;
-      while ((a + 1) * (a + 2) / 2 <= lane) ++a;
-      const int b = lane - a * (a + 1) / 2;
-      double v = sm.st(sm.H, lane, s);
-      if (a == b && a < 3) { v += dw; if (free_) v += 1.0 / dc; }
-      sm.st(sm.PM, lane, s) = v;
-    } else if (lane < 27) {
-      const int a = lane - 21;
+    if (t < 21) {
+      double v = sm.st(sm.H, t, s);
+      if (t == 0 || t == 2 || t == 5) { v += dw; if (free_) v += 1.0 / dc; }   // (0,0) (1,1) (2,2)
+      sm.st(sm.PM, t, s) = v;
+    } else if (t < 27) {
+      const int a = t - 21;
       double r = mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
       if (a < 3 && free_) r -= (sm.st(sm.Z, a, s) - xref(N)[a]) / dc;
       sm.st(sm.PV, a, s) = r;
     }
   }
-  OB_HD void ric_a(int lane, int s, double mu, double dw) const {
-    double* F = sm.RIC;        // 36 packed
-    double* f = sm.RIC + 36;   // 8
-    double* Pn = sm.PM + 0;    // element e of stage s+1 at Pn[e*S1 + s+1]
-#define PN(a, b) Pn[symi(a, b) * S1 + s + 1]
-    for (int e = lane; e < 36 + 8; e += 32) {
-      if (e < 36) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        const int b = e - a * (a + 1) / 2;
-        double v = sm.st(sm.H, e, s);
-        int ra_[4], rb_[4];
-        double va[4], vb[4];
-        const int na = at_col(s, a, ra_, va), nbb = at_col(s, b, rb_, vb);
-        for (int p = 0; p < na; ++p)
-          for (int q = 0; q < nbb; ++q) v += va[p] * vb[q] * PN(ra_[p], rb_[q]);
-        if (a == b) {
-          if ((a < 3 && s >= 1) || a >= 6 || (a == 5 && s == 0 && free_)) v += dw;
-        }
-        F[e] = v;
-      } else {
-        const int a = e - 36;
-        double v = mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
-        int ra_[4];
-        double va[4];
-        const int na = at_col(s, a, ra_, va);
-        const double c0 = sm.st(sm.CD, 0, s), c1 = sm.st(sm.CD, 1, s), c2 = sm.st(sm.CD, 2, s);
-        for (int p = 0; p < na; ++p) {
-          const int r = ra_[p];
-          const double pc = sm.st(sm.PV, r, s + 1) - (PN(r, 0) * c0 + PN(r, 1) * c1 + PN(r, 2) * c2);
-          v += va[p] * pc;
-        }
-        f[a] = v;
-      }
-    }
-#undef PN
+  // sub-step 1:  W = P_{s+1} At (6x6 over the non-empty columns),  pc = p_{s+1} - P_{s+1} c
+  OB_HD void ric_w(int t, int s) const {
+    if (t >= 42) return;
+    const uint32_t* w = sm.TAB + TW + 4 * t;
+    const double* Pn = sm.PM + (s + 1);
+    const double* cf = sm.DYN + s;
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc += cf[w[p] & 0xffff] * Pn[w[p] >> 16];
+    if (t < 36) sm.RIC[44 + t] = acc;
+    else sm.RIC[80 + (t - 36)] = sm.st(sm.PV, t - 36, s + 1) - acc;
   }
-  OB_HD void ric_b(int lane, int s) const {
+  // sub-step 2:  F = H + At^T W (+ dw on the regularised diagonal),  f = mu ra + rb + At^T pc
+  OB_HD void ric_f(int t, int s, double mu, double dw) const {
+    double* F = sm.RIC;
+    const double* cf = sm.DYN + s;
+    if (t < 29) {
+      const uint32_t* w = sm.TAB + TF + 4 * t;
+      const double* op = (t < 21) ? sm.RIC + 44 : sm.RIC + 80;   // W or pc
+      double acc = 0.0;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc += cf[w[p] & 0xffff] * op[w[p] >> 16];
+      if (t < 21) {
+        const uint32_t h = sm.TAB[TFH + t];
+        const int e = h & 255, cls = h >> 8;
+        acc += sm.st(sm.H, e, s);
+        if ((cls == 1 && s >= 1) || cls == 2 || (cls == 3 && s == 0 && free_)) acc += dw;
+        F[e] = acc;
+      } else {
+        const int a = t - 21;
+        F[36 + a] = acc + mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
+      }
+    } else if (t < 44) {
+      const int e = sm.TAB[TFC + t - 29];
+      F[e] = sm.st(sm.H, e, s);
+    }
+  }
+  // sub-step 3: eliminate (v, w); cost-to-go and feedback of stage s
+  OB_HD void ric_b(int t, int s) const {
+    if (t >= 41) return;
     Glob& G = *sm.G;
+    const uint32_t* tab = sm.TAB;
     const double* F = sm.RIC;
     const double* f = sm.RIC + 36;
-#define FF(a, b) F[symi(a, b)]
-    const double q00 = FF(6, 6), q01 = FF(7, 6), q11 = FF(7, 7);
+    const double q00 = F[27], q01 = F[34], q11 = F[35];   // (6,6) (7,6) (7,7)
     const double det = q00 * q11 - q01 * q01;
-    if (lane == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
-    const double i00 = q11 / det, i01 = -q01 / det, i11 = q00 / det;
-    for (int e = lane; e < 21 + 6 + 14; e += 32) {
-      if (e < 21) {
-        int a = 0;
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        const int b = e - a * (a + 1) / 2;
-        const double fa6 = FF(a, 6), fa7 = FF(a, 7), fb6 = FF(b, 6), fb7 = FF(b, 7);
-        sm.st(sm.PM, e, s) = FF(a, b) - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
-      } else if (e < 27) {
-        const int a = e - 21;
-        const double kap0 = i00 * f[6] + i01 * f[7], kap1 = i01 * f[6] + i11 * f[7];
-        sm.st(sm.PV, a, s) = f[a] - FF(a, 6) * kap0 - FF(a, 7) * kap1;
-      } else if (e < 39) {
-        const int q = e - 27, row = q / 6, b = q % 6;
-        const double v = (row == 0) ? -(i00 * FF(6, b) + i01 * FF(7, b)) : -(i01 * FF(6, b) + i11 * FF(7, b));
-        sm.st(sm.K, q, s) = v;
-      } else {
-        const int row = e - 39;
-        sm.st(sm.KAP, row, s) = (row == 0) ? i00 * f[6] + i01 * f[7] : i01 * f[6] + i11 * f[7];
-      }
+    if (t == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
+    const double idet = ob_rcp(det);
+    const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
+    if (t < 21) {
+      const uint32_t w0 = tab[TB + 2 * t], w1 = tab[TB + 2 * t + 1];
+      const double fa6 = F[(w0 >> 8) & 255], fa7 = F[(w0 >> 16) & 255], fb6 = F[w0 >> 24], fb7 = F[w1 & 255];
+      sm.st(sm.PM, t, s) = F[w0 & 255] - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
+    } else if (t < 27) {
+      const int a = t - 21;
+      const uint32_t w0 = tab[TB + 2 * t];
+      const double kap0 = i00 * f[6] + i01 * f[7], kap1 = i01 * f[6] + i11 * f[7];
+      sm.st(sm.PV, a, s) = f[a] - F[w0 & 255] * kap0 - F[(w0 >> 8) & 255] * kap1;
+    } else if (t < 39) {
+      const int q = t - 27, row = (q >= 6) ? 1 : 0, b = q - 6 * row;
+      const double f6 = F[21 + b], f7 = F[28 + b];       // (6,b) (7,b), b < 6
+      sm.st(sm.K, q, s) = (row == 0) ? -(i00 * f6 + i01 * f7) : -(i01 * f6 + i11 * f7);
+    } else {
+      const int row = t - 39;
+      sm.st(sm.KAP, row, s) = (row == 0) ? i00 * f[6] + i01 * f[7] : i01 * f[6] + i11 * f[7];
     }
-#undef FF
   }
-  OB_HD void ric_finish(int lane) const {
+  OB_HD void ric_finish(int t) const {
     Glob& G = *sm.G;
-    if (lane == 0 && free_ && !(sm.st(sm.PM, 20, 0) > 0)) G.bad = 1;
+    if (t == 0 && free_ && !(sm.st(sm.PM, 20, 0) > 0)) G.bad = 1;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -1036,10 +1197,12 @@ struct Solver {
   }
 
   OB_HD static void ftb(double S, double Z, double dS, double mu, double tau, double& amax, double& az, double& sls) {
-    double dZ = mu / S - Z - (Z / S) * dS;
-    if (dS < 0) amax = fmin(amax, -tau * S / dS);
-    if (dZ < 0) az = fmin(az, -tau * Z / dZ);
-    sls += dS / S;
+    const double iS = ob_rcp(S);
+    const double dZ = (mu - Z * dS) * iS - Z;
+    // tau*S/(-dS) < amax  <=>  tau*S < amax*(-dS) for dS < 0: compare by cross-multiplication, divide only when it binds
+    if (dS < 0 && tau * S < amax * -dS) amax = -tau * S / dS;
+    if (dZ < 0 && tau * Z < az * -dZ) az = -tau * Z / dZ;
+    sls += dS * iS;
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -1148,25 +1311,22 @@ struct Solver {
     }
     double amax = 1.0, az = 1.0, sls = 0.0;
     double da1 = 0, da2 = 0, qdw = 0;
+    const int nrow = E + 4;
+#pragma unroll 1
+    for (int j = 0; j < nrow; ++j) {
+      double wv, S, Z, yv[5];
+      row_regs(br, j, E, wv, S, Z);
+      row_y(b, k, r0, E, j, yv);
+      const double iS = ob_rcp(S), sig = Z * iS;
+      const double gl = y1 * yv[3] + y2 * yv[4] - Z + 2 * Zn * (a1 * yv[0] + a2 * yv[1]) - Zd * yv[2];
+      double s_ = (mu - S * Z) * iS - sig * (wv - S) - gl;
 #pragma unroll
-    for (int j = 0; j < EMAX + 4; ++j) {
-      if (j < E || j >= EMAX) {
-        const int jj = (j < EMAX) ? j : E + (j - EMAX);
-        double wv, S, Z, yv[5];
-        if (j < EMAX) { wv = br.lam[j]; S = br.Sl[j]; Z = br.Zl[j]; }
-        else { wv = br.mu[j - EMAX]; S = br.Sm_[j - EMAX]; Z = br.Zm[j - EMAX]; }
-        row_y(b, k, r0, E, jj, yv);
-        const double sig = Z / S;
-        const double gl = y1 * yv[3] + y2 * yv[4] - Z + 2 * Zn * (a1 * yv[0] + a2 * yv[1]) - Zd * yv[2];
-        double s = (mu - S * Z) / S - sig * (wv - S) - gl;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) s -= yv[a] * et[a];
-        const double dwv = s / fmax(sig, SIG_MIN);
-        if (j < EMAX) { sm.st(sm.DLAM, r0 + j, k) = dwv; da1 += yv[0] * dwv; da2 += yv[1] * dwv; }
-        else sm.bl(sm.DMU, j - EMAX, tid) = dwv;
-        qdw += yv[2] * dwv;
-        ftb(S, Z, dwv + (wv - S), mu, tau, amax, az, sls);
-      }
+      for (int a = 0; a < 5; ++a) s_ -= yv[a] * et[a];
+      const double dwv = s_ * ob_rcp(fmax(sig, SIG_MIN));
+      if (j < E) { sm.st(sm.DLAM, r0 + j, k) = dwv; da1 += yv[0] * dwv; da2 += yv[1] * dwv; }
+      else sm.bl(sm.DMU, j - E, tid) = dwv;
+      qdw += yv[2] * dwv;
+      ftb(S, Z, dwv + (wv - S), mu, tau, amax, az, sls);
     }
     sm.bl(sm.DYE, 0, tid) = et[3]; sm.bl(sm.DYE, 1, tid) = et[4];
     double ada = a1 * da1 + a2 * da2;
@@ -1192,30 +1352,31 @@ struct Solver {
     const double T = free_ ? G.T + a * G.dT : 1.0;
     StageVals sv;
     stage_vals(k, z, u, up, zn, T, sv);
-    double th = 0, lg = 0;
+    double th = 0;
+    LogAcc lg;
     if (k < N) {
       th += fabs(sv.cd[0]) + fabs(sv.cd[1]) + fabs(sv.cd[2]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { double S = sm.st(sm.SUB, j, k) + a * sm.st(sm.DSUB, j, k); th += fabs(sv.dub[j] - S); lg += log(S); }
+      for (int j = 0; j < 8; ++j) { double S = sm.st(sm.SUB, j, k) + a * sm.st(sm.DSUB, j, k); th += fabs(sv.dub[j] - S); lg.add(S); }
     }
     if (k >= 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { double S = sm.st(sm.SXY, j, k) + a * sm.st(sm.DSXY, j, k); th += fabs(sv.dxy[j] - S); lg += log(S); }
+      for (int j = 0; j < 4; ++j) { double S = sm.st(sm.SXY, j, k) + a * sm.st(sm.DSXY, j, k); th += fabs(sv.dxy[j] - S); lg.add(S); }
     }
     if (k == 0 && free_) {
-      double S = G.STb[0] + a * G.dSTb[0]; th += fabs(T - P.T_min - S); lg += log(S);
-      S = G.STb[1] + a * G.dSTb[1]; th += fabs(G.Tmax - T - S); lg += log(S);
+      double S = G.STb[0] + a * G.dSTb[0]; th += fabs(T - P.T_min - S); lg.add(S);
+      S = G.STb[1] + a * G.dSTb[1]; th += fabs(G.Tmax - T - S); lg.add(S);
     }
     if (k == N && free_) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) th += fabs(z[j] - xref(N)[j]);
     }
     if (k == N && has_term) {
-      double S = G.Stm[0] + a * G.dStm[0]; th += fabs(z[0] - G.term[0] - S); lg += log(S);
-      S = G.Stm[1] + a * G.dStm[1]; th += fabs(z[1] - G.term[1] - S); lg += log(S);
-      S = G.Stm[2] + a * G.dStm[2]; th += fabs(G.term[2] - z[1] - S); lg += log(S);
+      double S = G.Stm[0] + a * G.dStm[0]; th += fabs(z[0] - G.term[0] - S); lg.add(S);
+      S = G.Stm[1] + a * G.dStm[1]; th += fabs(z[1] - G.term[1] - S); lg.add(S);
+      S = G.Stm[2] + a * G.dStm[2]; th += fabs(G.term[2] - z[1] - S); lg.add(S);
     }
-    part[0] = sv.f; part[1] = th; part[2] = lg;
+    part[0] = sv.f; part[1] = th; part[2] = lg.value();
   }
   OB_HD void trial_block(int tid, const BlockRegs<EMAX>& br, double a, double* part) const {
     const Glob& G = *sm.G;
@@ -1227,7 +1388,8 @@ struct Solver {
     double st, ct;
     ob_sincos(z2, &st, &ct);
     const double tx = z0 + G.off * ct, ty = z1 + G.off * st;
-    double th = 0, lg = 0, a1 = 0, a2 = 0, bl = 0;
+    double th = 0, a1 = 0, a2 = 0, bl = 0;
+    LogAcc lg;
 #pragma unroll
     for (int j = 0; j < EMAX; ++j) {
       if (j < E) {
@@ -1235,7 +1397,7 @@ struct Solver {
         const double l0 = br.lam[j], dl = sm.st(sm.DLAM, r, k), S0 = br.Sl[j];
         const double l = l0 + a * dl, S = S0 + a * (dl + (l0 - S0));
         a1 += sm.A[2 * r] * l; a2 += sm.A[2 * r + 1] * l; bl += bk(k, r) * l;
-        th += fabs(l - S); lg += log(S);
+        th += fabs(l - S); lg.add(S);
       }
     }
     double m[4];
@@ -1244,19 +1406,19 @@ struct Solver {
       const double m0 = br.mu[q], dm = sm.bl(sm.DMU, q, tid), S0 = br.Sm_[q];
       m[q] = m0 + a * dm;
       const double S = S0 + a * (dm + (m0 - S0));
-      th += fabs(m[q] - S); lg += log(S);
+      th += fabs(m[q] - S); lg.add(S);
     }
     th += fabs(m[0] - m[2] + ct * a1 + st * a2) + fabs(m[1] - m[3] - st * a1 + ct * a2);
     {
       const double S = br.Sn + a * sm.bl(sm.DSN, 0, tid);
-      th += fabs(1.0 - a1 * a1 - a2 * a2 - S); lg += log(S);
+      th += fabs(1.0 - a1 * a1 - a2 * a2 - S); lg.add(S);
     }
     {
       const double S = br.Sd + a * sm.bl(sm.DSD, 0, tid);
       const double d = -(G.g[0] * m[0] + G.g[1] * m[1] + G.g[2] * m[2] + G.g[3] * m[3]) + tx * a1 + ty * a2 - bl - P.dmin;
-      th += fabs(d - S); lg += log(S);
+      th += fabs(d - S); lg.add(S);
     }
-    part[0] = 0.0; part[1] = th; part[2] = lg;
+    part[0] = 0.0; part[1] = th; part[2] = lg.value();
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -1265,9 +1427,10 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   OB_HD static void upd(double& S, double& Z, double dS, double a, double az, double mu) {
     const double ks = 1e10;
-    double dZ = mu / S - Z - (Z / S) * dS;
+    const double dZ = (mu - Z * dS) * ob_rcp(S) - Z;
     double Sn = S + a * dS, Zn = Z + az * dZ;
-    Zn = fmin(fmax(Zn, mu / (ks * Sn)), ks * mu / Sn);
+    const double mS = mu * ob_rcp(Sn);
+    Zn = fmin(fmax(Zn, mS * 1e-10), ks * mS);
     S = Sn; Z = Zn;
   }
   // NOTE: reads neighbours' DZ/DU only through its own column, so no barrier is needed inside
@@ -1364,8 +1527,9 @@ struct Solver {
 // ======================================================================================================
 // The interior-point loop of one instance.  `Exec` provides:
 //   par(f)            run f(tid, BlockRegs&, part*) for every thread of the block, then a block barrier
-//   reduce<S0,NS,M0,NM,N0,NN>()  one block reduction over the threads' part[] slots: sum of slots S0..S0+NS-1,
+//   reduce<S0,NS,M0,NM,N0,NN>(scratch)  one block reduction over the threads' part[] slots: sum of slots S0..S0+NS-1,
 //                     max of M0.., min of N0.. (results in ex.red[] at the same slots)
+//   all(f)            run f(tid) on every thread of the block, then a block barrier (no per-thread state)
 //   stage(f)          run f(lane) on the 32 lanes of the stage warp, then a warp barrier (no block barrier)
 //   stage_end()       block barrier closing a run of stage() calls
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
@@ -1382,13 +1546,14 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
   const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta_ph = 1e-8;
   const double tol = P.tol;
   const int N = S.N, no = S.no;
+  (void)theta_mu;
   const bool free_ = S.free_, has_term = S.has_term;
   const int m_eq = 3 * N + (free_ ? 3 : 0) + 2 * no * (N + 1);
   const int q_in = 12 * N + (free_ ? 2 : 0) + (has_term ? 3 : 0) + (S.sm.R + 6 * no) * (N + 1);
   typedef BlockRegs<EMAX> BR;
 
-  ex.par([&](int tid, BR& br, double* part) { (void)br; S.start_a(tid, part); });
-  ex.template reduce<0, 1, 0, 0, 0, 0>();
+  ex.par([&](int tid, BR& br, double* part) { (void)br; S.start_a(tid, part); S.fill_tables(tid); });
+  ex.template reduce<0, 1, 0, 0, 0, 0>(S.sm.SCR_H);
   const double T0 = S.start_T(ex.red[0]);
   ex.par([&](int tid, BR& br, double* part) { (void)part; S.start_b(tid, br, T0); });
   ex.par([&](int tid, BR& br, double* part) { (void)part; S.init_slacks(tid, br); });
@@ -1409,7 +1574,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
       else for (int q = 0; q < NPART; ++q) part[q] = (q == PN_SZMIN) ? 1e300 : 0.0;
     });
     ex.par([&](int tid, BR& br, double* part) { (void)br; if (S.is_stage(tid)) S.assemble_combine(S.stage_lane(tid), part); });
-    ex.template reduce<PS_F, 6, PM_E1, 5, PN_SZMIN, 1>();
+    ex.template reduce<PS_F, 6, PM_E1, 5, PN_SZMIN, 1>(S.sm.SCR_D);
     ex.tick(1);
     const double Ef = ex.red[PS_F], Eth = ex.red[PS_TH], ElgS = ex.red[PS_LG], Esumy = ex.red[PS_SUMY], Esumz = ex.red[PS_SUMZ];
     double Ee1 = ex.red[PM_E1];
@@ -1438,7 +1603,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
       const double e3 = fmax(Eszmax - mu, mu - Eszmin) / sc;
       const double Emu = fmax(fmax(Ee1 / sd, Ee2), e3);
       if (Emu <= kappa_eps * mu && mu > tol / 10) {
-        mu = fmax(tol / 10, fmin(kappa_mu * mu, pow(mu, theta_mu)));
+        mu = fmax(tol / 10, fmin(kappa_mu * mu, mu * sqrt(mu)));   // mu^theta_mu, theta_mu = 1.5
         changed = true;
       } else
         break;
@@ -1452,14 +1617,13 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
     bool regfail = false;
     for (;;) {
       ex.once([&]() { G.bad = 0; });
-      ex.stage_end();
-      ex.stage([&](int lane) { S.ric_terminal(lane, mu, dw, dc); });
+      ex.all([&](int t) { S.ric_terminal(t, mu, dw, dc); });
       for (int s = N - 1; s >= 0; --s) {
-        ex.stage([&](int lane) { S.ric_a(lane, s, mu, dw); });
-        ex.stage([&](int lane) { S.ric_b(lane, s); });
+        ex.all([&](int t) { S.ric_w(t, s); });
+        ex.all([&](int t) { S.ric_f(t, s, mu, dw); });
+        ex.all([&](int t) { S.ric_b(t, s); });
       }
-      ex.stage([&](int lane) { S.ric_finish(lane); });
-      ex.stage_end();
+      ex.all([&](int t) { S.ric_finish(t); });
       if (!G.bad) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
       else dw = dw * ((dw_last == 0.0) ? kw_plus_first : kw_plus);
@@ -1481,15 +1645,17 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
       else if (S.is_stage(tid)) S.backsub_stage(S.stage_lane(tid), mu, tau, part);
       else { part[QS_DPHI] = 0.0; part[QN_AMAX] = 1.0; part[QN_AZ] = 1.0; }
     });
-    ex.template reduce<QS_DPHI, 1, 0, 0, QN_AMAX, 2>();
+    ex.template reduce<QS_DPHI, 1, 0, 0, QN_AMAX, 2>(S.sm.SCR_H);
     ex.tick(4);
     const double Dphi = ex.red[QS_DPHI], a_max = ex.red[QN_AMAX], a_z = ex.red[QN_AZ];
     if (!f_active) {
       thmax = 1e4 * fmax(1.0, th); thmin = 1e-4 * fmax(1.0, th);
       f_active = true; f_n = 0; f_wr = 0;
     }
+    // the two powers of the switching condition are loop invariants of the line search
+    const double pw_th = (th > 0) ? pow(th, s_th) : 0.0, pw_dphi = (Dphi < 0) ? pow(-Dphi, s_ph) : 0.0;
     double a_min;
-    if (Dphi < 0 && th <= thmin) a_min = fmin(g_th, fmin(g_ph * th / (-Dphi), (th > 0) ? pow(th, s_th) / pow(-Dphi, s_ph) : g_th));
+    if (Dphi < 0 && th <= thmin) a_min = fmin(g_th, fmin(g_ph * th / (-Dphi), (th > 0) ? pw_th / pw_dphi : g_th));
     else if (Dphi < 0) a_min = fmin(g_th, g_ph * th / (-Dphi));
     else a_min = g_th;
     a_min *= 0.05;
@@ -1502,14 +1668,14 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
         else if (S.is_stage(tid)) S.trial_stage(S.stage_lane(tid), a, part);
         else { part[0] = part[1] = part[2] = 0.0; }
       });
-      ex.template reduce<0, 3, 0, 0, 0, 0>();
+      ex.template reduce<0, 3, 0, 0, 0, 0>(S.sm.SCR_H);
       const double tht = ex.red[1], pht = ex.red[0] - mu * ex.red[2];
       accepted = 0;
       if (isfinite(pht) && tht < thmax) {
         bool dom = false;
         for (int q = 0; q < f_n; ++q) dom = dom || (tht >= G.fth[q] && pht >= G.fph[q]);
         if (!dom) {
-          const bool sw = (Dphi < 0) && (a * pow(-Dphi, s_ph) > pow(th, s_th));
+          const bool sw = (Dphi < 0) && (a * pw_dphi > pw_th);
           if (th <= thmin && sw) {
             if (pht <= ph0 + eta_ph * a * Dphi + 10 * 2.220446049250313e-16 * fabs(ph0)) accepted = 2;
           } else if (tht <= (1 - g_th) * th || pht <= ph0 - g_ph * th)
