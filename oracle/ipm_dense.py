@@ -16,6 +16,11 @@ Algorithm (IPOPT-flavoured, Waechter & Biegler 2006):
   matrix has inertia (n, m, 0); dc on the terminal-equality rows only (the only rows that can lose rank),
   chosen Levenberg-Marquardt style so that the terminal multiplier step stays bounded;
   fraction-to-boundary tau = max(0.99, 1-mu) on S and Z; filter line search with second-order correction;
+  watchdog (IPOPT: watchdog_shortened_iter_trigger 10, watchdog_trial_iter_max 3): after 10 consecutive shortened
+  steps a rejected full step is taken on trust from a saved reference iterate; if 3 more full steps reach no point
+  acceptable to the reference (filter + Armijo with the reference's values), the reference is restored and ordinary
+  backtracking resumes there.  (The optional second-order correction, soc=True, is not part of the specification the
+  C oracle and the CUDA kernel implement.)
   monotone barrier update mu <- max(tol/10, min(0.2 mu, mu^1.5)) when E_mu <= 10 mu;
   stop when IPOPT's scaled optimality error E_0 <= tol (1e-8); the best iterate with E_0 <= acceptable_tol is
   stored and becomes the result ("Solved To Acceptable Level") if the run later ends in a failure.
@@ -32,7 +37,8 @@ DEFAULT_OPTS = dict(tol=1e-8, max_iter=3000, mu_init=10.0, kappa_eps=10.0, kappa
                     dw_first=1e-4, dw_min=1e-20, dw_max=1e20, kw_plus_first=100.0, kw_plus=8.0, kw_minus=1.0 / 3.0,
                     dc_min=1e-8, lm_cap=1e4, acceptable_tol=1e-6, acceptable_iter=15, filt_max=32,
                     stall_alpha=1e-3, stall_iters=10, sig_min=1e-8,
-                    init="warm", verbose=False, soc=True, dbg=False)
+                    wd_trigger=10, wd_max=3,
+                    init="warm", verbose=False, soc=False, dbg=False)
 
 # status codes (shared with oracle/obca_oracle.c and the CUDA kernel)
 ST_OK, ST_ACCEPTABLE, ST_MAXITER, ST_REGFAIL, ST_EMPTYBOX, ST_LSFAIL, ST_STALL = 0, 1, -1, -2, -3, -4, -5
@@ -98,6 +104,8 @@ def solve(p: nlp.Problem, opts=None):
     acc_count = 0
     best = None
     status = ST_MAXITER
+    in_wd = False; wd_count = 0; wd_block = False; n_short = 0
+    wd_ref = None; wd_state = None
 
     def err(gr, Jm, Jd, c, d, S, y, Z, mu_t):
         sd = max(o["s_max"], (np.abs(y).sum() + Z.sum()) / max(1, m + q)) / o["s_max"]
@@ -148,6 +156,8 @@ def solve(p: nlp.Problem, opts=None):
         if changed and filt is not None:
             filt = []
             nfilt_wr = 0
+        if changed:
+            in_wd = False
         tau = max(o["tau_min"], 1 - mu)
 
         Sig = Z / S
@@ -224,27 +234,60 @@ def solve(p: nlp.Problem, opts=None):
             a_min = g_th
         a_min *= 0.05
 
-        def acceptable(tht, pht, a):
+        def acceptable(tht, pht, a, th_r=None, ph_r=None, dphi_r=None):
+            """0 rejected, 1 sufficient decrease w.r.t. the reference (current point by default), 2 Armijo"""
+            th_r = th if th_r is None else th_r
+            ph_r = ph0 if ph_r is None else ph_r
+            dphi_r = Dphi if dphi_r is None else dphi_r
             if not np.isfinite(pht) or tht >= th_max:
                 return 0
             for (tf, pf) in filt:
                 if tht >= tf and pht >= pf:
                     return 0
-            sw = Dphi < 0 and a * (-Dphi) ** s_ph > th ** s_th
-            if th <= th_min and sw:
-                return 2 if pht <= ph0 + eta_ph * a * Dphi + 10 * np.finfo(float).eps * abs(ph0) else 0
-            if tht <= (1 - g_th) * th or pht <= ph0 - g_ph * th:
+            sw = dphi_r < 0 and a * (-dphi_r) ** s_ph > th_r ** s_th
+            if th_r <= th_min and sw:
+                return 2 if pht <= ph_r + eta_ph * a * dphi_r + 10 * np.finfo(float).eps * abs(ph_r) else 0
+            if tht <= (1 - g_th) * th_r or pht <= ph_r - g_ph * th_r:
                 return 1
             return 0
+
+        def filt_add(th_e, ph_e):
+            nonlocal nfilt_wr
+            if len(filt) < o["filt_max"]:
+                filt.append(((1 - g_th) * th_e, ph_e - g_ph * th_e))
+            else:
+                filt[nfilt_wr % o["filt_max"]] = ((1 - g_th) * th_e, ph_e - g_ph * th_e)
+            nfilt_wr += 1
         a = a_max
         accepted = 0
         nbt = 0
         dXa, dSa = dX, dS
         nsoc = 0
+        restored = False
         while a >= a_min * (1 - 1e-12):
             pht, tht, ct, dt = phi_theta(X + a * dX, S + a * dS, mu)
+            if in_wd:
+                accepted = acceptable(tht, pht, wd_ref[3], wd_ref[0], wd_ref[1], wd_ref[2])
+                if accepted:
+                    in_wd = False
+                    if accepted == 1:
+                        filt_add(wd_ref[0], wd_ref[1])
+                    accepted = 3
+                else:
+                    wd_count += 1
+                    if wd_count >= o["wd_max"]:
+                        X, S, y, Z = [v.copy() for v in wd_state]
+                        in_wd = False; wd_block = True; restored = True
+                    else:
+                        accepted = 3
+                break
             accepted = acceptable(tht, pht, a)
             if accepted:
+                break
+            if nbt == 0 and not wd_block and n_short >= o["wd_trigger"] and o["wd_max"] > 0 and np.isfinite(pht):
+                wd_state = (X.copy(), S.copy(), y.copy(), Z.copy())
+                wd_ref = (th, ph0, Dphi, a)
+                in_wd = True; wd_count = 0; accepted = 3
                 break
             if nbt == 0 and tht >= th and o["soc"]:
                 csoc = a * c + ct
@@ -270,6 +313,9 @@ def solve(p: nlp.Problem, opts=None):
                     break
             a *= 0.5
             nbt += 1
+        if restored:
+            it += 1
+            continue
         at_floor = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
         if not accepted:
             status = ST_ACCEPTABLE if at_floor else ST_LSFAIL
@@ -278,12 +324,13 @@ def solve(p: nlp.Problem, opts=None):
         if nstall >= o["stall_iters"]:
             status = ST_ACCEPTABLE if at_floor else ST_STALL
             break
+        if accepted != 3:
+            wd_block = False
+            n_short = n_short + 1 if a < a_max else 0
+        elif not in_wd:
+            n_short = 0
         if accepted == 1:
-            if len(filt) < o["filt_max"]:
-                filt.append(((1 - g_th) * th, ph0 - g_ph * th))
-            else:
-                filt[nfilt_wr % o["filt_max"]] = ((1 - g_th) * th, ph0 - g_ph * th)
-            nfilt_wr += 1
+            filt_add(th, ph0)
         if o["verbose"]:
             print("      a_max %.2e a %.2e a_z %.2e |dX| %.2e |dy| %.2e acc %d bt %d soc %d ntry %d nf %d dc %.1e" % (
                 a_max, a, a_z, np.abs(dX).max(), np.abs(dy).max(), accepted, nbt, nsoc, ntry, len(filt), lm.get("dc", 0)))

@@ -755,7 +755,7 @@ static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const
  * the interior-point loop (oracle/ipm_dense.py solve(), soc = False)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  iter_t it, tr, best; /* best: stored acceptable point */
+  iter_t it, tr, best, wd; /* best: stored acceptable point; wd: watchdog reference iterate */
   vals_t v, vt;
   stageqp_t q;
   blk_t blk[NS][OM];
@@ -765,6 +765,8 @@ typedef struct {
 
 typedef void (*trace_fn)(int it, double f, double th, double E0, double mu, double dw, double alpha);
 static trace_fn g_trace = 0;
+static int g_wd_trigger = 10, g_wd_max = 3;   /* watchdog: shortened steps before it starts / full steps on trust */
+void obca_oracle_set_watchdog(int trigger, int max_trust) { g_wd_trigger = trigger; g_wd_max = max_trust; }
 void obca_oracle_set_trace(trace_fn fn) { g_trace = fn; }
 
 static void apply_step(const prob_t* p, const iter_t* it, const dir_t* d, double a, iter_t* o) {
@@ -815,6 +817,12 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   memset(&F, 0, sizeof(F));
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
   double dw_last = 0.0, E0 = 0, best_E0 = 1e300;
+  /* watchdog (Chamberlain et al.; IPOPT's watchdog, triggered earlier): after WD_TRIGGER consecutive shortened steps a
+   * rejected full step is taken anyway from a saved reference iterate; if within WD_MAX further full steps no point
+   * acceptable to the reference is reached, the reference is restored and ordinary backtracking resumes there */
+  const int WD_TRIGGER = g_wd_trigger, WD_MAX = g_wd_max;
+  int in_wd = 0, wd_count = 0, wd_block = 0, n_short = 0;
+  double wd_th = 0, wd_ph = 0, wd_dphi = 0, wd_alpha = 1;
   int m_eq = 3 * N + (p->free_ ? 3 : 0) + 2 * p->nobs * (N + 1);
   int q_in = 4 * N + 8 * N + (p->free_ ? 2 : 0) + (p->has_term ? 3 : 0) + (p->R + 6 * p->nobs) * (N + 1);
 
@@ -879,6 +887,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
         break;
     }
     if (changed) {
+      in_wd = 0; /* a new barrier problem: the current point becomes an ordinary iterate */
       if (F.active) { F.n = 0; F.wr = 0; }
       if (assemble(p, it, v, mu, &w->q, w->blk)) { status = OBCA_ST_REGFAIL; break; }
       theta_phi(p, it, v, mu, &th, &ph0, &cmax);
@@ -976,28 +985,58 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       a_min = g_th;
     a_min *= 0.05;
     double a = a_max;
-    int accepted = 0;
+    int accepted = 0, restored = 0;
+    /* acceptance of a trial (tht, pht) against a reference point (th_r, ph_r, Dphi_r) reached with step a_r:
+     * 0 rejected, 1 sufficient decrease (h-type: the reference goes into the filter), 2 Armijo (f-type) */
+#define ACCEPT_TEST(res, tht, pht, th_r, ph_r, dphi_r, a_r)                                                   \
+    do { (res) = 0;                                                                                           \
+      if (isfinite(pht) && (tht) < F.thmax) {                                                                 \
+        int dominated_ = 0;                                                                                   \
+        for (int i_ = 0; i_ < F.n; ++i_)                                                                      \
+          if ((tht) >= F.th[i_] && (pht) >= F.ph[i_]) { dominated_ = 1; break; }                              \
+        if (!dominated_) {                                                                                    \
+          int sw_ = ((dphi_r) < 0) && ((a_r) * pow(-(dphi_r), s_ph) > pow((th_r), s_th));                     \
+          if ((th_r) <= F.thmin && sw_) {                                                                     \
+            if ((pht) <= (ph_r) + eta_ph * (a_r) * (dphi_r) + 10 * 2.220446049250313e-16 * fabs(ph_r)) (res) = 2; \
+          } else if ((tht) <= (1 - g_th) * (th_r) || (pht) <= (ph_r) - g_ph * (th_r))                         \
+            (res) = 1;                                                                                        \
+        }                                                                                                     \
+      } } while (0)
+    int first = 1;
     while (a >= a_min * (1 - 1e-12)) {
       apply_step(p, it, d, a, &w->tr);
       eval_values(p, &w->tr, &w->vt);
       double tht, pht;
       theta_phi(p, &w->tr, &w->vt, mu, &tht, &pht, 0);
-      accepted = 0;
-      if (isfinite(pht) && tht < F.thmax) {
-        int dominated = 0;
-        for (int i = 0; i < F.n; ++i)
-          if (tht >= F.th[i] && pht >= F.ph[i]) { dominated = 1; break; }
-        if (!dominated) {
-          int sw = (Dphi < 0) && (a * pow(-Dphi, s_ph) > pow(th, s_th));
-          if (th <= F.thmin && sw) {
-            if (pht <= ph0 + eta_ph * a * Dphi + 10 * 2.220446049250313e-16 * fabs(ph0)) accepted = 2;
-          } else if (tht <= (1 - g_th) * th || pht <= ph0 - g_ph * th)
-            accepted = 1;
-        }
+      if (in_wd) {
+        /* watchdog: only full steps, judged against the reference iterate */
+        ACCEPT_TEST(accepted, tht, pht, wd_th, wd_ph, wd_dphi, wd_alpha);
+        if (accepted) {
+          in_wd = 0;
+          if (accepted == 1) { /* the reference point enters the filter */
+            int slot = (F.n < FILT_MAX) ? F.n++ : (F.wr % FILT_MAX);
+            F.th[slot] = (1 - g_th) * wd_th; F.ph[slot] = wd_ph - g_ph * wd_th;
+            F.wr++;
+          }
+          accepted = 3;
+        } else if (++wd_count >= WD_MAX) {
+          *it = w->wd; in_wd = 0; wd_block = 1; restored = 1;   /* give up: back to the reference iterate */
+        } else
+          accepted = 3;                                         /* one more full step on trust */
+        break;
       }
+      ACCEPT_TEST(accepted, tht, pht, th, ph0, Dphi, a);
       if (accepted) break;
+      if (first && !wd_block && n_short >= WD_TRIGGER && WD_MAX > 0 && isfinite(pht)) {
+        w->wd = *it; wd_th = th; wd_ph = ph0; wd_dphi = Dphi; wd_alpha = a;
+        in_wd = 1; wd_count = 0; accepted = 3;
+        break;
+      }
+      first = 0;
       a *= 0.5;
     }
+#undef ACCEPT_TEST
+    if (restored) { iter++; continue; }
     if (g_trace) g_trace(iter, v->f, th, E0, mu, dw, accepted ? a : -1.0);
     /* IPOPT returns Solved_To_Acceptable_Level when it cannot make progress from a point that meets the
      * acceptable tolerance; near a degenerate vertex of the OBCA dual polytope the step noise floor is
@@ -1008,6 +1047,8 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
     if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (accepted != 3) { wd_block = 0; n_short = (a < a_max) ? n_short + 1 : 0; }
+    else if (!in_wd) n_short = 0;   /* watchdog succeeded */
     if (accepted == 1) {
       int slot = (F.n < FILT_MAX) ? F.n++ : (F.wr % FILT_MAX);
       F.th[slot] = (1 - g_th) * th; F.ph[slot] = ph0 - g_ph * th;

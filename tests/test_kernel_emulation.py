@@ -83,3 +83,15 @@ def test_uref_tracking_obca2():
     assert np.abs(e["x"] - c["x"]).max() <= 1e-8 and abs(e["obj"][0] - c["obj"][0]) <= 1e-8
     c0 = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], ep, A, b0, db, T_max=a["T_max"])
     assert abs(c0["obj"][0] - c["obj"][0]) > 1e-6          # the uref term is really in the cost
+
+
+def test_watchdog_instances():
+    """instances that crawl for 100-360 iterations without the watchdog: kernel code == oracle, ~30 iterations"""
+    b = sc.make_batch(3, 8192)
+    prm, a = common.batch_arrays(b)
+    idx = np.array([7330, 232, 4692, 1940])
+    sub = {k: (v[idx] if (v is not None and k in ("x0", "u0", "xref", "T_max")) else v) for k, v in a.items()}
+    c = _oracle(prm, sub); e = common.emu_solve(prm, sub)
+    assert (c["status"] == 0).all() and (e["status"] == 0).all()
+    assert np.array_equal(c["iters"], e["iters"]) and c["iters"].max() <= 40
+    assert np.abs(c["x"] - e["x"]).max() <= 1e-9 and np.abs(c["obj"] - e["obj"]).max() <= 1e-8

@@ -130,3 +130,28 @@ def test_objective_restatement():
     _, _, c = _c("demo9_N6_astar_free", _abi.INIT_WARM)
     f = nlp.objective_of(p, c["x"][0].T, c["u"][0].T, c["T"][0])
     assert abs(f - c["obj"][0]) <= 1e-9 * abs(f)
+
+
+def test_watchdog_path_matches_dense_spec():
+    """two cfg-2 instances whose solve goes through the watchdog (10 shortened steps -> full step on trust):
+    the structured C oracle follows the dense specification step for step; without the watchdog they crawl"""
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import scenario as sc
+    b = sc.make_batch(2, 400)
+    prm, a = common.batch_arrays(b)
+    L = c_oracle.lib()
+    for i in (14, 383):
+        sl = lambda v: None if v is None else v[i:i + 1]
+        args = (prm, sl(a["x0"]), sl(a["u0"]), sl(a["xref"]), a["edge_ptr"], a["A"], a["b0"], a["db"])
+        try:
+            L.obca_oracle_set_watchdog(10, 0)
+            c0 = c_oracle.solve(*args, T_max=sl(a["T_max"]))
+        finally:
+            L.obca_oracle_set_watchdog(10, 3)
+        c1 = c_oracle.solve(*args, T_max=sl(a["T_max"]))
+        assert c1["status"][0] == 0 and c1["iters"][0] < c0["iters"][0] - 15
+        p = nlp.build_problem(b.mode, b.Ts, b.P, b.Q, b.R, b.N, b.x0[i], b.xL, b.xU, b.uL, b.uU, b.xref[i], b.nObs, b.vObs,
+                              b.AObs, b.bObs, b.dmin, b.ego, b.u0[i])
+        r = ipm_dense.solve(p, dict(init="warm"))
+        assert r["status"] == 0 and r["iters"] == c1["iters"][0]
+        assert np.abs(r["x"].T - c1["x"][0]).max() <= 1e-9 and abs(r["obj"] - c1["obj"][0]) <= 1e-9 * abs(r["obj"])
+        assert abs(c0["obj"][0] - c1["obj"][0]) <= 1e-7 * abs(c1["obj"][0])      # same minimiser either way

@@ -55,7 +55,8 @@ static void run(const KParams& kp, int nwarps, int has_uref) {
     for (int t = 0; t < ex.T; ++t) S.load(t, (size_t)b, true);
     int iters = 0;
     double obj = 0;
-    int st = solve_instance(S, ex, (size_t)b, iters, obj);
+    std::vector<double> wd(Solver<EMAX>::wd_doubles(ex.T, P.N + 1), 0.0);
+    int st = solve_instance(S, ex, (size_t)b, wd.data(), iters, obj);
     if (st != OBCA_ST_STORED)
       for (int t = 0; t < ex.T; ++t) S.store(t, ex.brs[t], (size_t)b, st, iters, obj);
   }

@@ -15,7 +15,7 @@ namespace obca {
 
 // Optional in-kernel phase timing (-DOBCA_PROFILE; tools/phase_profile.py): cycles per phase summed over blocks.
 #ifdef OBCA_PROFILE
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[24];   // phase cycles | par-body cycles of warp 0 | of the stage warp
 #endif
 
 // Block reduction, two stages through shared memory.  `buf` holds nt rows (one per slot) of one value per thread
@@ -59,8 +59,17 @@ struct DevExec {
   bool stage_warp;
 #ifdef OBCA_PROFILE
   long long prof[8], prof_t;
-#endif
+  long long work[8];   // cycles this warp spent inside par() bodies of the current phase group (before the barrier)
+  int phase;
+  template <class F> __device__ __forceinline__ void par(F&& f) {
+    const long long t0 = clock64();
+    f(tid, br, part);
+    work[phase] += clock64() - t0;
+    __syncthreads();
+  }
+#else
   template <class F> __device__ __forceinline__ void par(F&& f) { f(tid, br, part); __syncthreads(); }
+#endif
   template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
@@ -71,6 +80,7 @@ struct DevExec {
   __device__ __forceinline__ void tick(int i) {
 #ifdef OBCA_PROFILE
     long long t = clock64(); prof[i] += t - prof_t; prof_t = t;
+    phase = (i + 1) & 7;
 #else
     (void)i;
 #endif
@@ -111,20 +121,22 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     const unsigned int inst = s_inst;
     if (inst >= (unsigned)kp.batch) break;
 #ifdef OBCA_PROFILE
-    for (int i = 0; i < 8; ++i) ex.prof[i] = 0;
-    ex.prof_t = clock64();
+    for (int i = 0; i < 8; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
+    ex.prof_t = clock64(); ex.phase = 0;
 #endif
     S.load(ex.tid, inst, first || !kp.shared_obs);
     first = false;
     __syncthreads();
     int iters = 0;
     double obj = 0.0;
-    const int status = solve_instance(S, ex, (size_t)inst, iters, obj);
+    const int status = solve_instance(S, ex, (size_t)inst, kp.wd_buf + (size_t)blockIdx.x * kp.wd_stride, iters, obj);
     if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
     else if (ex.tid == 0) kp.obj[inst] = obj;
 #ifdef OBCA_PROFILE
     if (ex.tid == 0)
-      for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[i], (unsigned long long)ex.prof[i]);
+      for (int i = 0; i < 8; ++i) { atomicAdd(&g_prof[i], (unsigned long long)ex.prof[i]); atomicAdd(&g_prof[8 + i], (unsigned long long)ex.work[i]); }
+    if (ex.stage_warp && ex.lane == 0)
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[16 + i], (unsigned long long)ex.work[i]);
 #endif
     __syncthreads();
   }
@@ -147,6 +159,9 @@ struct obca_ctx {
   kernel_fn fn;
   int cfg_emax, cfg_uref; // configuration the launch geometry was computed for
   unsigned int* counter;
+  double* wd_buf;         // watchdog checkpoints, one slot per resident block
+  size_t wd_bytes;
+  int64_t wd_stride;
   int64_t launches;
   cudaEvent_t ev0, ev1;
   bool timed;
@@ -193,6 +208,14 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   const char* env = getenv("OBCA_CTAS_PER_SM");
   if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
   c->grid = sm_count_of(c->device) * per_sm;
+  c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
+  const size_t need = (size_t)c->grid * c->wd_stride * sizeof(double);
+  if (need > c->wd_bytes) {
+    if (c->wd_buf) cudaFree(c->wd_buf);
+    c->wd_buf = nullptr; c->wd_bytes = 0;
+    if (cudaMalloc(&c->wd_buf, need) != cudaSuccess) { cudaGetLastError(); return OBCA_E_NOMEM; }
+    c->wd_bytes = need;
+  }
   c->cfg_emax = emax; c->cfg_uref = has_uref;
   return OBCA_OK;
 }
@@ -238,6 +261,7 @@ int obca_b200_destroy(obca_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->counter);
   if (c->stage) cudaFree(c->stage);
+  if (c->wd_buf) cudaFree(c->wd_buf);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
   free(c);
   return OBCA_OK;
@@ -246,9 +270,9 @@ int obca_b200_destroy(obca_ctx* c) {
 #ifdef OBCA_PROFILE
 // phase cycle counters: 0 start 1 assemble 2 riccati 3 roll-out 4 steps 5 line search 6 update 7 exit
 int obca_b200_prof_read(unsigned long long* out, int reset) {
-  if (cudaMemcpyFromSymbol(out, obca::g_prof, 8 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
+  if (cudaMemcpyFromSymbol(out, obca::g_prof, 24 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
   if (reset) {
-    unsigned long long z[16] = {0};
+    unsigned long long z[24] = {0};
     if (cudaMemcpyToSymbol(obca::g_prof, z, sizeof(z)) != cudaSuccess) return OBCA_E_CUDA;
   }
   return OBCA_OK;
@@ -256,8 +280,8 @@ int obca_b200_prof_read(unsigned long long* out, int reset) {
 #endif
 
 // device bytes held by the context: the solver keeps its whole working set on-chip, so this is only the work-queue
-// counter and the staging buffer of the host entry point
-int64_t obca_b200_scratch_bytes(const obca_ctx* c) { return c ? (int64_t)(sizeof(unsigned int) + c->stage_bytes) : 0; }
+// counter, the watchdog checkpoint slots (one per resident block) and the staging buffer of the host entry point
+int64_t obca_b200_scratch_bytes(const obca_ctx* c) { return c ? (int64_t)(sizeof(unsigned int) + c->stage_bytes + c->wd_bytes) : 0; }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
 
 float obca_b200_last_kernel_ms(obca_ctx* c) {
@@ -301,7 +325,7 @@ int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, 
   kp.x0 = x0; kp.u0 = u0; kp.xref = xref; kp.uref = uref; kp.Tmax = T_max; kp.term = term; kp.Ts_inst = Ts_inst;
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
-  kp.counter = c->counter;
+  kp.counter = c->counter; kp.wd_buf = c->wd_buf; kp.wd_stride = c->wd_stride;
   if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
   cudaEventRecord(c->ev0, st);

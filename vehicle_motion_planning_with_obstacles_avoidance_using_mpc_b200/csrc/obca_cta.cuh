@@ -46,6 +46,8 @@ struct KParams {
   double *x, *u, *lam, *mu, *T, *obj;
   int32_t *status, *iters;
   unsigned int* counter;  // persistent-block work queue
+  double* wd_buf;         // watchdog checkpoints in HBM: one slot of wd_stride doubles per resident block
+  int64_t wd_stride;
 };
 
 // block-uniform scalar state of one instance (shared memory)
@@ -103,15 +105,18 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   s.DLAM = take((size_t)R * S1); s.DMU = take(4 * (size_t)nb); s.DYE = take(2 * (size_t)nb);
   s.DSN = take(nb); s.DSD = take(nb); s.XI = take(6 * S1);
   if (o - d0 < (size_t)NPART * red_stride(s.T)) take((size_t)NPART * red_stride(s.T) - (o - d0));
+  if (o - d0 < (size_t)EX_N * nb) take((size_t)EX_N * nb - (o - d0));
   s.SCR_D = base ? base + d0 : nullptr;
+  s.EX = s.SCR_D;   // block -> stage exchange of assemble: consumed (combine) before the reduction scratch is written
   const size_t h0 = o;
   s.H = take(36 * S1); s.RA = take(8 * S1);   // H|RA (44 S1) is re-used by the roll-out as ACL(36)|CCL(6)
   if (o - h0 < (size_t)3 * red_stride(s.T)) take((size_t)3 * red_stride(s.T) - (o - h0));
   s.SCR_H = base ? base + h0 : nullptr;
-  s.RB = take(8 * S1); s.GF = take(8 * S1); s.GL = take(8 * S1);
+  s.RB = take(8 * S1); s.GF = take(8 * S1);
   s.DYN = take(13 * S1); s.CD = s.DYN ? s.DYN + 10 * S1 : nullptr;   // CD = elements 10..12 of DYN (one coefficient base)
   s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1);
-  s.ETA = take(25 * (size_t)nb); s.EX = take(EX_N * (size_t)nb);
+  s.GL = s.K;       // Lagrangian gradient of assemble: dead before the sweep writes the feedback gains
+  s.ETA = take(25 * (size_t)nb);
   s.A = take(2 * R); s.B0 = take(R); s.DB = take(R); s.XREF = take(3 * S1); s.UREF = take(has_uref ? 2 * N : 0);
   s.RIC = take(RIC_N); s.RED = take(NPART + 8 * NPART);
   s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
@@ -1489,6 +1494,49 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------------
+  // watchdog checkpoint of the whole iterate (primal, slacks, multipliers) in HBM: the on-chip budget has no room
+  // for a second copy, and a checkpoint is written only when a full step is taken on trust (rare), read back only
+  // when that trust was misplaced (rarer).  Layout: block registers [element][thread] | stage arrays | scalars.
+  // ------------------------------------------------------------------------------------------------
+  OB_HD static int wd_doubles(int T, int S1) { return (6 * EMAX + 6) * T + 32 * S1 + 16; }
+  OB_HD void wd_save(int tid, const BlockRegs<EMAX>& br, double* buf) const {
+    const Glob& G = *sm.G;
+    const int T = sm.T;
+    int e = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX; ++j) { buf[(e++) * T + tid] = br.lam[j]; buf[(e++) * T + tid] = br.Sl[j]; buf[(e++) * T + tid] = br.Zl[j]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { buf[(e++) * T + tid] = br.mu[q]; buf[(e++) * T + tid] = br.Sm_[q]; buf[(e++) * T + tid] = br.Zm[q]; }
+    buf[(e++) * T + tid] = br.ye[0]; buf[(e++) * T + tid] = br.ye[1];
+    buf[(e++) * T + tid] = br.Sn; buf[(e++) * T + tid] = br.Zn; buf[(e++) * T + tid] = br.Sd; buf[(e++) * T + tid] = br.Zd;
+    double* sb = buf + (6 * EMAX + 6) * T;
+    for (int i = tid; i < 32 * S1; i += T) sb[i] = sm.Z[i];     // Z U YD SXY ZXY SUB ZUB are contiguous
+    if (tid == 0) {
+      double* g = sb + 32 * S1;
+      g[0] = G.T; g[1] = G.STb[0]; g[2] = G.STb[1]; g[3] = G.ZTb[0]; g[4] = G.ZTb[1];
+      for (int j = 0; j < 3; ++j) { g[5 + j] = G.Stm[j]; g[8 + j] = G.Ztm[j]; g[11 + j] = G.yt[j]; }
+    }
+  }
+  OB_HD void wd_restore(int tid, BlockRegs<EMAX>& br, const double* buf) const {
+    Glob& G = *sm.G;
+    const int T = sm.T;
+    int e = 0;
+#pragma unroll
+    for (int j = 0; j < EMAX; ++j) { br.lam[j] = buf[(e++) * T + tid]; br.Sl[j] = buf[(e++) * T + tid]; br.Zl[j] = buf[(e++) * T + tid]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { br.mu[q] = buf[(e++) * T + tid]; br.Sm_[q] = buf[(e++) * T + tid]; br.Zm[q] = buf[(e++) * T + tid]; }
+    br.ye[0] = buf[(e++) * T + tid]; br.ye[1] = buf[(e++) * T + tid];
+    br.Sn = buf[(e++) * T + tid]; br.Zn = buf[(e++) * T + tid]; br.Sd = buf[(e++) * T + tid]; br.Zd = buf[(e++) * T + tid];
+    const double* sb = buf + (6 * EMAX + 6) * T;
+    for (int i = tid; i < 32 * S1; i += T) sm.Z[i] = sb[i];
+    if (tid == 0) {
+      const double* g = sb + 32 * S1;
+      G.T = g[0]; G.STb[0] = g[1]; G.STb[1] = g[2]; G.ZTb[0] = g[3]; G.ZTb[1] = g[4];
+      for (int j = 0; j < 3; ++j) { G.Stm[j] = g[5 + j]; G.Ztm[j] = g[8 + j]; G.yt[j] = g[11 + j]; }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
   // results -> HBM, once:  x [B,N+1,3]  u [B,N,2]  lam [B,N+1,R]  mu [B,N+1,4 no]  T  obj  status  iters
   // ------------------------------------------------------------------------------------------------
   OB_HD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
@@ -1536,7 +1584,7 @@ struct Solver {
 //   once(f)           run f() on one thread (block-uniform shared state), visible after the next barrier
 // ======================================================================================================
 template <int EMAX, class Exec>
-OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iters_out, double& obj_out) {
+OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, int& iters_out, double& obj_out) {
   const obca_params& P = S.P;
   Glob& G = *S.sm.G;
   const double s_max = 100.0, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
@@ -1564,6 +1612,13 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
   double thmax = 0, thmin = 0;
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
   double dw_last = 0.0, E0 = 0.0, fcur = 0.0, best_E0 = 1e300, best_f = 0.0;
+  // watchdog (IPOPT: watchdog_shortened_iter_trigger = 10, watchdog_trial_iter_max = 3): after 10 consecutive shortened
+  // steps a rejected full step is taken on trust from a checkpointed reference iterate; if 3 further full steps reach no
+  // point acceptable to the reference, the reference is restored and ordinary backtracking resumes there.  This is what
+  // ends the Maratos-type crawl (hundreds of 2^-9 steps) that otherwise dominates the tail of a batch.
+  const int WD_TRIGGER = 10, WD_MAX = 3;
+  int in_wd = 0, wd_count = 0, wd_block = 0, n_short = 0;
+  double wd_th = 0, wd_ph = 0, wd_dphi = 0, wd_alpha = 1, wd_pw_th = 0, wd_pw_dphi = 0;
 
   ex.tick(0);
   for (;;) {
@@ -1609,6 +1664,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
         break;
     }
     if (changed && f_active) { f_n = 0; f_wr = 0; }
+    if (changed) in_wd = 0;   // a new barrier problem: the current point becomes an ordinary iterate
     const double th = Eth, ph0 = Ef - mu * ElgS;
     const double tau = fmax(tau_min, 1 - mu);
     const double dc = free_ ? fmax(dc_min, Ectmax / lm_cap) : 0.0;
@@ -1662,6 +1718,17 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
     // ---- filter line search
     double a = a_max;
     int accepted = 0;
+    bool restored = false, first = true;
+    // acceptance of a trial against a reference (th_r, ph_r, Dphi_r; powers pre-computed) reached with step a_r:
+    // 0 rejected, 1 sufficient decrease (the reference enters the filter), 2 Armijo on the barrier function
+    auto accept_test = [&](double tht, double pht, double th_r, double ph_r, double dphi_r, double a_r, double pwt, double pwd) -> int {
+      if (!(isfinite(pht) && tht < thmax)) return 0;
+      for (int q = 0; q < f_n; ++q)
+        if (tht >= G.fth[q] && pht >= G.fph[q]) return 0;
+      const bool sw = (dphi_r < 0) && (a_r * pwd > pwt);
+      if (th_r <= thmin && sw) return (pht <= ph_r + eta_ph * a_r * dphi_r + 10 * 2.220446049250313e-16 * fabs(ph_r)) ? 2 : 0;
+      return (tht <= (1 - g_th) * th_r || pht <= ph_r - g_ph * th_r) ? 1 : 0;
+    };
     while (a >= a_min * (1 - 1e-12)) {
       ex.par([&](int tid, BR& br, double* part) {
         if (S.is_block(tid)) S.trial_block(tid, br, a, part);
@@ -1670,21 +1737,36 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
       });
       ex.template reduce<0, 3, 0, 0, 0, 0>(S.sm.SCR_H);
       const double tht = ex.red[1], pht = ex.red[0] - mu * ex.red[2];
-      accepted = 0;
-      if (isfinite(pht) && tht < thmax) {
-        bool dom = false;
-        for (int q = 0; q < f_n; ++q) dom = dom || (tht >= G.fth[q] && pht >= G.fph[q]);
-        if (!dom) {
-          const bool sw = (Dphi < 0) && (a * pw_dphi > pw_th);
-          if (th <= thmin && sw) {
-            if (pht <= ph0 + eta_ph * a * Dphi + 10 * 2.220446049250313e-16 * fabs(ph0)) accepted = 2;
-          } else if (tht <= (1 - g_th) * th || pht <= ph0 - g_ph * th)
-            accepted = 1;
-        }
+      if (in_wd) {
+        // watchdog: only full steps, judged against the reference iterate
+        accepted = accept_test(tht, pht, wd_th, wd_ph, wd_dphi, wd_alpha, wd_pw_th, wd_pw_dphi);
+        if (accepted) {
+          in_wd = 0;
+          if (accepted == 1) {   // the reference point enters the filter
+            const int slot = (f_n < FILT_MAX) ? f_n++ : (f_wr % FILT_MAX);
+            ex.once([&]() { G.fth[slot] = (1 - g_th) * wd_th; G.fph[slot] = wd_ph - g_ph * wd_th; });
+            f_wr++;
+          }
+          accepted = 3;
+        } else if (++wd_count >= WD_MAX) {
+          ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_restore(tid, br, wd_buf); });
+          in_wd = 0; wd_block = 1; restored = true;   // give up: back to the reference iterate
+        } else
+          accepted = 3;                               // one more full step on trust
+        break;
       }
+      accepted = accept_test(tht, pht, th, ph0, Dphi, a, pw_th, pw_dphi);
       if (accepted) break;
+      if (first && !wd_block && n_short >= WD_TRIGGER && isfinite(pht)) {
+        ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_save(tid, br, wd_buf); });
+        wd_th = th; wd_ph = ph0; wd_dphi = Dphi; wd_alpha = a; wd_pw_th = pw_th; wd_pw_dphi = pw_dphi;
+        in_wd = 1; wd_count = 0; accepted = 3;
+        break;
+      }
+      first = false;
       a *= 0.5;
     }
+    if (restored) { iter++; continue; }
     // IPOPT ends with Solved_To_Acceptable_Level when it cannot progress from an acceptable point; the second
     // clause is the rounding-noise floor of a degenerate vertex of the OBCA dual polytope
     const bool at_floor = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
@@ -1693,6 +1775,8 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, int& iter
     if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
     if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (accepted != 3) { wd_block = 0; n_short = (a < a_max) ? n_short + 1 : 0; }
+    else if (!in_wd) n_short = 0;   // watchdog succeeded
     if (accepted == 1) {
       const int slot = (f_n < FILT_MAX) ? f_n++ : (f_wr % FILT_MAX);
       ex.once([&]() { G.fth[slot] = (1 - g_th) * th; G.fph[slot] = ph0 - g_ph * th; });
