@@ -40,7 +40,7 @@ def is_free(mode):
 
 
 def make_params(mode, N, n_obs, rows, Ts, P, Q, R, xL, xU, uL, uU, dmin, ego, *, init=INIT_WARM, has_term=None,
-                max_iter=None, tol=1e-8, acceptable_tol=None, acceptable_iter=15, mu_init=10.0, bound_push=0.1):
+                max_iter=None, tol=1e-8, acceptable_tol=None, acceptable_iter=15, mu_init=10.0, bound_push=0.1, T_min=1e-4):
     """Solver options default to what the reference passes to IPOPT: mpc4 -> IPOPT defaults (max_iter 3000,
     acceptable_tol 1e-6; obca.py:1044); mpc6/mpc8/obca2-fixed -> max_iter 1000, acceptable_tol 1e-8
     (obca.py:1538-1539, 1734-1735, 596-598)."""
@@ -66,7 +66,7 @@ def make_params(mode, N, n_obs, rows, Ts, P, Q, R, xL, xU, uL, uU, dmin, ego, *,
     p.uU[:] = np.asarray(uU, float).reshape(2).tolist()
     p.acc_max[:] = [0.6, float(np.pi / 6)]          # obca.py:932-933
     p.time_cost[:] = [10.0, 1.0]                     # obca.py:888
-    p.T_min = 1e-4                                   # obca.py:963
+    p.T_min = T_min                                  # 1e-4: obca.py:963
     p.tol = tol
     p.acceptable_tol = (1e-6 if free else 1e-8) if acceptable_tol is None else acceptable_tol
     p.mu_init, p.bound_push = mu_init, bound_push

@@ -144,7 +144,7 @@ class BatchSolver:
 
 
 def solve_batch(mode, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs, bObs, dmin, ego, u0,
-                terminal_set=None, uref=None, init=INIT_WARM, device=-1, **opts):
+                terminal_set=None, uref=None, init=INIT_WARM, device=-1, T_max=None, **opts):
     """Batched form of the reference call: x0 (B,3), u0 (B,2), xref (B,3,N+1) [the reference's layout],
     terminal_set (B,2,2) or None; one scene (AObs, bObs) shared by the batch.  Host arrays in, host arrays
     out (x (B,3,N+1), u (B,2,N), feas (B,), Ts_opt (B,), plus lam/mu/obj/status/iters)."""
@@ -160,8 +160,10 @@ def solve_batch(mode, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs
         raise ValueError("obca_mpc6 needs a terminal_set")
     prm = _abi.make_params(mode, N, nObs, int(edge_ptr[-1]), Ts, P, Q, R, xL, xU, uL, uU, dmin, ego, init=init,
                            has_term=has_term and mode in (MODE_FIXED_SET, MODE_FIXED_OBCA2), **opts)
-    T_max = term = None
-    if _abi.is_free(mode):
+    term = None
+    if T_max is not None:
+        T_max = np.broadcast_to(np.asarray(T_max, float).reshape(-1), (B,)).copy()
+    elif _abi.is_free(mode):
         uU0 = float(np.asarray(uU, float).reshape(-1)[0])
         T_max = ((xref[:, 0, N] - x0[:, 0]) + (xref[:, 1, N] - x0[:, 1])) / (N * uU0 * Ts) + 1.0   # obca.py:961-962
     if prm.has_term:
@@ -203,11 +205,12 @@ class obca:
         return INIT_WARM
 
     def _one(self, mode, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs, bObs, dmin, ego, u0,
-             terminal_set=None, uref=None):
+             terminal_set=None, uref=None, **opts):
         r = solve_batch(mode, Ts, P, Q, R, int(N), np.asarray(x0, float).reshape(1, 3), xL, xU, uL, uU,
                         np.asarray(xref, float).reshape(1, 3, int(N) + 1), int(nObs), vObs, AObs, bObs, dmin, ego,
                         np.asarray(u0, float).reshape(1, 2), terminal_set=terminal_set, uref=uref,
-                        init=self._auto_init(xref, x0, int(N)) if self.init is None else self.init, device=self.device)
+                        init=self._auto_init(xref, x0, int(N)) if self.init is None else self.init, device=self.device,
+                        **opts)
         self.lam, self.mu = r["lam"][0], r["mu"][0]
         self.obj, self.status, self.iters, self.T = float(r["obj"][0]), int(r["status"][0]), int(r["iters"][0]), float(r["T"][0])
         return r["x"][0], r["u"][0], bool(r["feas"][0]), float(r["Ts_opt"][0])
@@ -233,6 +236,24 @@ class obca:
         ts = terminal_set if (terminal_set is not None and np.size(terminal_set) > 0) else None
         return self._one(MODE_FIXED_OBCA2, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs, bObs, dmin,
                          ego, u0, terminal_set=ts, uref=uref)
+
+    def obca(self, Ts, P, Q, R, N, x0, u0, xL, xU, uL, uU, xref, uref, nObs, vObs, AObs, bObs, dmin, ego, fixtime,
+             timeScale_size):
+        """The earliest variant (obca.py:12-336; no caller anywhere in the reference).  Free time only: obca2's NLP with the
+        time-scale box of obca.py:234-240 - 'big': [1e-4, sqrt(dx^2 + dy)/(N uU Ts) + 1] (the missing square on dy is the
+        reference's), 'small': [0.8, 1.2].  Its fixed-time form (terminal xy equality with a +-pi/4 heading
+        band, obca.py:223-225) has no counterpart in the live code paths and is not implemented."""
+        if fixtime != 0:
+            raise NotImplementedError("obca.obca(fixtime=1) is dead code in the reference; use obca_mpc6 / obca_mpc8 / obca2")
+        x0a = np.asarray(x0, float).reshape(3); xr = np.asarray(xref, float).reshape(3, int(N) + 1)
+        if timeScale_size == 'small':
+            opts = dict(T_min=0.8, T_max=1.2)
+        else:
+            uU0 = float(np.asarray(uU, float).reshape(-1)[0])
+            dis = np.sqrt((xr[0, N] - x0a[0]) ** 2 + (xr[1, N] - x0a[1]))
+            opts = dict(T_min=1e-4, T_max=dis / (N * uU0 * Ts) + 1)
+        return self._one(MODE_FREE_STACKED, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AObs, bObs, dmin, ego,
+                         u0, uref=uref, **opts)
 
 
 OBCA = obca
