@@ -152,3 +152,84 @@ def test_device_path_matches_host_path():
         assert np.array_equal(o[k].cpu().numpy(), h[k]), k      # same kernel, same inputs: bit-identical
     assert np.array_equal(o["status"].cpu().numpy(), h["status"])
     s.close()
+
+
+def test_per_instance_Ts_and_obstacle_rows():
+    """ABI v2: per-instance sampling time + per-instance obstacle rows (what the lock-step closed loop feeds)"""
+    from oracle import c_oracle
+    prm, a, d = common.fixture_arrays("demo9_N5_fixed")
+    B = 3
+    rep = lambda v: None if v is None else np.repeat(v, B, axis=0)
+    Ts = np.array([2.0, 1.5, 2.5])
+    A = np.repeat(a["A"][None], B, 0); b0 = np.repeat(a["b0"][None], B, 0)
+    db = np.repeat(a["db"][None], B, 0) * (Ts / 2.0)[:, None]
+    c = c_oracle.solve(prm, rep(a["x0"]), rep(a["u0"]), rep(a["xref"]), a["edge_ptr"], A, b0, db, term=rep(a["term"]), Ts=Ts)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], B)
+    g = s.solve_host(rep(a["x0"]), rep(a["u0"]), rep(a["xref"]), A, b0, db, term=rep(a["term"]), Ts=Ts)
+    s.close()
+    ok = c["status"] >= 0
+    assert np.array_equal(ok, g["status"] >= 0) and ok[0] and ok[2]
+    assert common.rel(g["x"][ok], c["x"][ok]) <= PRIMAL_RTOL and common.rel(g["u"][ok], c["u"][ok]) <= PRIMAL_RTOL
+    assert (np.abs(g["obj"][ok] - c["obj"][ok]) <= OBJ_RTOL * np.maximum(1, np.abs(c["obj"][ok]))).all()
+
+
+def test_obca2_uref_and_obca_free():
+    """obca2 (free, time-stacked rows, uref in the cost: obca.py:421-424) and obca(...,'big') through the drop-in"""
+    from oracle import c_oracle
+    mode, d = common.load_fixture("demo1_N6_astar_free")
+    N = int(d["N"])
+    s = obca_mod.obca()
+    uref = np.tile(np.array([[0.5], [0.0]]), (1, N))
+    x, u, feas, Ts_opt = s.obca2(float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], N, d["x0"], d["u0"], d["xL"], d["xU"],
+                                 d["uL"], d["uU"], d["xref"], uref, int(d["nObs"]), d["vObs"], d["AObs"], d["bObs"],
+                                 float(d["dmin"]), d["ego"], 0, '', [])
+    assert feas and x.shape == (3, N + 1)
+    ep, A, b0, db = _abi.pack_obstacles(_abi.MODE_FREE_STACKED, N, int(d["nObs"]), d["vObs"], d["AObs"], d["bObs"])
+    prm = _abi.make_params(_abi.MODE_FREE_STACKED, N, int(d["nObs"]), int(ep[-1]), float(d["Ts"]), d["P"], d["Q"],
+                           [d["R1"], d["R2"]], d["xL"], d["xU"], d["uL"], d["uU"], float(d["dmin"]), d["ego"])
+    Tm = np.array([_abi.tmax_of(d["xref"][:, N], d["x0"], N, d["uU"][0], float(d["Ts"]))])
+    c = c_oracle.solve(prm, d["x0"].reshape(1, 3), d["u0"].reshape(1, 2), np.ascontiguousarray(d["xref"].T)[None], ep, A, b0, db,
+                       T_max=Tm, uref=np.ascontiguousarray(uref.T)[None])
+    assert abs(s.obj - c["obj"][0]) <= OBJ_RTOL * abs(c["obj"][0]) and np.abs(x.T - c["x"][0]).max() <= 1e-4
+    x2, u2, feas2, T2 = s.obca(float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], N, d["x0"], d["u0"], d["xL"], d["xU"], d["uL"],
+                               d["uU"], d["xref"], [], int(d["nObs"]), d["vObs"], d["AObs"], d["bObs"], float(d["dmin"]), d["ego"], 0, 'big')
+    assert feas2 and abs(s.obj - 4334.19729465) < 1e-3
+
+
+def test_sharded_single_rank_path():
+    import torch
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import sharding
+    b = sc.make_batch(2, 96)
+    prm, a = common.batch_arrays(b)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], 96)
+    out, packed = sharding.solve_sharded(s, a, 96, 0, 1, torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    h = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"])
+    for k in ("x", "u", "lam", "mu", "T", "obj", "status", "iters"):
+        assert np.array_equal(out[k].cpu().numpy(), h[k]), k
+    assert packed.nbytes == packed.buf.numel() * 8
+    s.close()
+
+
+def test_closed_loop_lockstep_batch_matches_oracle_driver():
+    """cfg 4: demo9 map, Monte-Carlo moving box, lock-step closed loops on the GPU vs the same driver on the oracle"""
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import closed_loop as cl, demo_setting as ds
+    B, steps = 48, 8
+    dyn = cl.demo9_monte_carlo(B)
+    dyn[:, 1] = np.linspace(12, 30, B)            # close enough to meet the car within a few steps
+    dyn[:, 6] = 0
+    mk = lambda: (lambda s: (setattr(s, "senseDis", 8), s)[1])(ds.problemSetting("demo9"))
+    g = cl.ClosedLoopBatch(mk(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps)
+    og = g.run(); g.close()
+    c = cl.ClosedLoopBatch(mk(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps,
+                           solver_factory=lambda prm, ep, cap: common.OracleSolver(prm, ep, cap, nthreads=8))
+    oc = c.run()
+    assert og["launches"] >= steps and og["solves"] >= B * 2
+    # first step is identical for everybody (same start, no obstacle in range yet): tight agreement
+    assert np.nanmax(np.abs(og["traj"][:, 1] - oc["traj"][:, 1])) <= 1e-4
+    same = (og["steps"] == oc["steps"]) & (og["failed"] == oc["failed"])
+    assert same.mean() >= 0.9
+    n = np.minimum(og["steps"], oc["steps"])
+    close = [np.abs(og["traj"][i, :n[i] + 1] - oc["traj"][i, :n[i] + 1]).max() <= 1e-3 for i in range(B) if same[i]]
+    assert np.mean(close) >= 0.9
+    assert (og["mode"] == _abi.MODE_FIXED_SET).any() or (og["mode"] == _abi.MODE_FIXED_NOTERM).any()
