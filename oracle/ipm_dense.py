@@ -133,7 +133,7 @@ def solve(p: nlp.Problem, opts=None):
             status = 0
             break
         if E0 <= o["acceptable_tol"]:
-            if best is None or E0 < best[0]:       # IPOPT stores the best acceptable point ...
+            if best is None or E0 < 0.1 * best[0]:  # IPOPT stores the acceptable point (here: a new copy per decade) ...
                 best = (E0, X.copy(), S.copy(), y.copy(), Z.copy())
             acc_count += 1
             if acc_count >= o["acceptable_iter"]:

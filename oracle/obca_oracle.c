@@ -870,7 +870,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     if (E0 <= P->acceptable_tol) {
       /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
        * ("Solved To Acceptable Level") */
-      if (E0 < best_E0) { best_E0 = E0; w->best = *it; }
+      if (E0 < 0.1 * best_E0) { best_E0 = E0; w->best = *it; }   /* a new copy per decade of improvement */
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
       acc_count = 0;

@@ -43,20 +43,20 @@ def main():
     t = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
     dv = {k: t(a[k]) for k in ("x0", "u0", "xref", "A", "b0", "db", "T_max", "term")}
     out = s.alloc_outputs(B, "cuda")
-    buf = (C.c_ulonglong * 24)()
+    buf = (C.c_ulonglong * 48)()
     for i in range(2):
         L.obca_b200_prof_read(buf, 1)
         s.solve(dv["x0"], dv["u0"], dv["xref"], dv["A"], dv["b0"], dv["db"], T_max=dv["T_max"], term=dv["term"], out=out)
         torch.cuda.synchronize()
     L.obca_b200_prof_read(buf, 0)
-    names = ["start", "assemble", "riccati", "rollout", "steps", "linesearch", "update", "exit"]
-    tot = float(sum(buf[:8]))
+    names = ["start", "assemble", "combine", "asm-reduce", "control", "riccati", "rollout", "steps", "steps-reduce",
+             "ls-setup", "trial", "trial-reduce", "update", "exit"]
+    tot = float(sum(buf[:14]))
     it = out["iters"].cpu().numpy()
     print("cfg %d B %d kernel %.2f ms -> %.0f solves/s, iters mean %.1f max %d" % (cfg, B, s.last_kernel_ms(), B / s.last_kernel_ms() * 1e3, it.mean(), it.max()))
     print("  %-10s %8s %12s %14s %14s" % ("phase", "share", "cycles/iter", "block-warp work", "stage-warp work"))
-    for i, (n, v) in enumerate(zip(names, buf[:8])):
-        print("  %-10s %6.2f %%  %10.0f   %12.0f   %12.0f" % (n, 100.0 * v / tot, v / max(1, it.sum()), buf[8 + i] / max(1, it.sum()),
-                                                          buf[16 + i] / max(1, it.sum())))
+    for i, (n, v) in enumerate(zip(names, buf[:14])):
+        print("  %-12s %6.2f %%  %10.0f" % (n, 100.0 * v / tot, v / max(1, it.sum())))
 
 
 if __name__ == "__main__":

@@ -15,23 +15,27 @@ namespace obca {
 
 // Optional in-kernel phase timing (-DOBCA_PROFILE; tools/phase_profile.py): cycles per phase summed over blocks.
 #ifdef OBCA_PROFILE
-__device__ unsigned long long g_prof[24];   // phase cycles | par-body cycles of warp 0 | of the stage warp
+__device__ unsigned long long g_prof[48];   // phase cycles (16) | par-body cycles of warp 0 (16) | of the stage warp (16)
 #endif
 
 // Block reduction, two stages through shared memory.  `buf` holds nt rows (one per slot) of one value per thread
-// (row stride red_stride(T): a pad word every 16 values spreads stage A over the banks).  Stage A: 8 threads per
+// (row stride T).  Stage A: 8 threads per
 // slot each fold T/8 consecutive values; stage B: one thread per slot folds the 8 partials into RED[slot].
-// Slots [0, ns) are sums, [ns, ns+nm) maxima, the rest minima.  One copy of this code serves every reduction of the
-// kernel (it is deliberately not inlined: instruction fetch is what limits this kernel).
-__device__ __noinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt) {
-  const int rs = red_stride(T), L = T >> 3;
+// Slots [0, ns) are sums, [ns, ns+nm) maxima, the rest minima.  (Inlined: as a real call it cost ~5 k cycles per
+// reduction in caller-saved register traffic - the block threads carry their iterate in registers.)
+__device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt) {
+  const int L = T >> 3;
   double* P2 = RED + NPART;
   for (int j = tid; j < nt * 8; j += T) {
     const int q = j >> 3, seg = j & 7;
-    const double* row = buf + q * rs + seg * L + ((seg * L) >> 4);
-    double a = row[0];
+    const double* row = buf + q * T + seg * L;
+    // the 8 segments of a slot start a multiple of 32 words apart: start each at a different offset (rotation) so
+    // that the lanes of a warp hit different banks
+    double a = row[seg];              // seg < 8 <= L
     for (int i = 1; i < L; ++i) {
-      const double b = row[i + (((seg * L + i) >> 4) - ((seg * L) >> 4))];
+      int idx = seg + i;
+      if (idx >= L) idx -= L;
+      const double b = row[idx];
       a = (q < ns) ? a + b : (q < ns + nm) ? fmax(a, b) : fmin(a, b);
     }
     P2[j] = a;
@@ -58,8 +62,8 @@ struct DevExec {
   int tid, lane, warp, nwarps;
   bool stage_warp;
 #ifdef OBCA_PROFILE
-  long long prof[8], prof_t;
-  long long work[8];   // cycles this warp spent inside par() bodies of the current phase group (before the barrier)
+  long long prof[16], prof_t;
+  long long work[16];   // cycles this warp spent inside par() bodies of the current phase group (before the barrier)
   int phase;
   template <class F> __device__ __forceinline__ void par(F&& f) {
     const long long t0 = clock64();
@@ -71,6 +75,12 @@ struct DevExec {
   template <class F> __device__ __forceinline__ void par(F&& f) { f(tid, br, part); __syncthreads(); }
 #endif
   template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
+  // sweep sub-step: <= 64 tasks, run by warps 0-1 only and closed by a 64-thread named barrier; the other warps
+  // skip the whole sweep and rejoin at the block barrier of sweep_end()
+  template <class F> __device__ __forceinline__ void sweep(F&& f) {
+    if (warp < 2) { f(tid); asm volatile("bar.sync 1, 64;" ::: "memory"); }
+  }
+  __device__ __forceinline__ void sweep_end() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
   }
@@ -80,7 +90,7 @@ struct DevExec {
   __device__ __forceinline__ void tick(int i) {
 #ifdef OBCA_PROFILE
     long long t = clock64(); prof[i] += t - prof_t; prof_t = t;
-    phase = (i + 1) & 7;
+    phase = (i + 1) & 15;
 #else
     (void)i;
 #endif
@@ -88,7 +98,7 @@ struct DevExec {
   // one block reduction: sums of part[S0..], maxima of part[M0..], minima of part[N0..] -> red[] (same slots).
   // Slot ranges must be laid out S | M | N consecutively in part[] (they are: see the PS_/PM_/PN_ enums).
   template <int S0, int NS, int M0, int NM, int N0, int NN> __device__ __forceinline__ void reduce(double* scratch) {
-    const int T = 32 * nwarps, rs = red_stride(T), pos = tid + (tid >> 4);
+    const int T = 32 * nwarps, rs = T, pos = tid;
 #pragma unroll
     for (int q = 0; q < NS; ++q) scratch[q * rs + pos] = part[S0 + q];
 #pragma unroll
@@ -104,11 +114,16 @@ struct DevExec {
 
 extern __shared__ double obca_smem[];
 
-template <int EMAX, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps, int has_uref) {
+// NT/NOT/RT > 0: kernel specialised for horizon NT, NOT obstacles, RT half-space rows (sizes are literals);
+// 0: generic kernel, sizes read from the parameter block
+template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0>
+__global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
   __shared__ unsigned int s_inst;
   Sm sm;
-  sm_carve(sm, obca_smem, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps, has_uref);
+  constexpr bool fixed = NT > 0;
+  const int nwarps = fixed ? (NOT * (NT + 1) + 31) / 32 + 1 : nwarps_rt;
+  if (fixed) sm_carve(sm, obca_smem, NT, NOT, RT, (NOT * (NT + 1) + 31) / 32 + 1, has_uref);
+  else sm_carve(sm, obca_smem, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps_rt, has_uref);
   const Solver<EMAX> S(kp, sm);
   DevExec<EMAX> ex;
   ex.red = sm.RED;
@@ -121,7 +136,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     const unsigned int inst = s_inst;
     if (inst >= (unsigned)kp.batch) break;
 #ifdef OBCA_PROFILE
-    for (int i = 0; i < 8; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
+    for (int i = 0; i < 16; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
     ex.prof_t = clock64(); ex.phase = 0;
 #endif
     S.load(ex.tid, inst, first || !kp.shared_obs);
@@ -134,9 +149,9 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     else if (ex.tid == 0) kp.obj[inst] = obj;
 #ifdef OBCA_PROFILE
     if (ex.tid == 0)
-      for (int i = 0; i < 8; ++i) { atomicAdd(&g_prof[i], (unsigned long long)ex.prof[i]); atomicAdd(&g_prof[8 + i], (unsigned long long)ex.work[i]); }
+      for (int i = 0; i < 16; ++i) { atomicAdd(&g_prof[i], (unsigned long long)ex.prof[i]); atomicAdd(&g_prof[16 + i], (unsigned long long)ex.work[i]); }
     if (ex.stage_warp && ex.lane == 0)
-      for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[16 + i], (unsigned long long)ex.work[i]);
+      for (int i = 0; i < 16; ++i) atomicAdd(&g_prof[32 + i], (unsigned long long)ex.work[i]);
 #endif
     __syncthreads();
   }
@@ -175,8 +190,10 @@ static int sm_count_of(int device) {
   return n;
 }
 
-// kernel variant for (max edges per obstacle, threads per block)
-static kernel_fn pick_kernel(int emax, int threads) {
+// kernel variant for (max edges per obstacle, threads per block); the BASELINE configurations have kernels with
+// compile-time sizes
+static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
+  if (emax <= 4 && N == 20 && no == 4 && R == 16) return obca::obca_solve_kernel<4, 128, 3, 20, 4, 16>;   // cfg 3 (headline)
   if (emax <= 4) {
     if (threads <= 128) return obca::obca_solve_kernel<4, 128, 3>;
     if (threads <= 192) return obca::obca_solve_kernel<4, 192, 2>;
@@ -194,7 +211,7 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   c->threads = 32 * c->nwarps;
   obca::Sm sm;
   c->smem_bytes = obca::sm_carve(sm, nullptr, P.N, P.n_obs, P.rows, c->nwarps, has_uref) * sizeof(double);
-  c->fn = pick_kernel(emax, c->threads);
+  c->fn = pick_kernel(emax, c->threads, P.N, P.n_obs, P.rows);
   if (c->smem_bytes > 227 * 1024) return OBCA_E_SIZE;
   if (cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess) {
     cudaGetLastError();
@@ -268,11 +285,12 @@ int obca_b200_destroy(obca_ctx* c) {
 }
 
 #ifdef OBCA_PROFILE
-// phase cycle counters: 0 start 1 assemble 2 riccati 3 roll-out 4 steps 5 line search 6 update 7 exit
+// phase cycle counters (tick i closes phase i): 0 start 1 assemble 2 combine 3 reduce 4 control 5 riccati 6 roll-out
+// 7 steps 8 reduce 9 line-search setup 10 trial 11 reduce+test 12 update 13 exit
 int obca_b200_prof_read(unsigned long long* out, int reset) {
-  if (cudaMemcpyFromSymbol(out, obca::g_prof, 24 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
+  if (cudaMemcpyFromSymbol(out, obca::g_prof, 48 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
   if (reset) {
-    unsigned long long z[24] = {0};
+    unsigned long long z[48] = {0};
     if (cudaMemcpyToSymbol(obca::g_prof, z, sizeof(z)) != cudaSuccess) return OBCA_E_CUDA;
   }
   return OBCA_OK;

@@ -65,7 +65,7 @@ struct Sm {
   int N, S1, no, R, nb, T, nwarps, has_uref;
   double *Z, *U, *YD, *SXY, *ZXY, *SUB, *ZUB;
   double *DZ, *DU, *DYD, *DSXY, *DSUB;
-  double *H, *RA, *RB, *CD, *GF, *GL, *DYN;
+  double *H, *RA, *RB, *CD, *GL, *DYN;
   double *K, *KAP, *PM, *PV, *XI;
   double *ETA, *DLAM, *DMU, *DYE, *DSN, *DSD, *EX;
   double *A, *B0, *DB, *XREF, *UREF;
@@ -77,19 +77,21 @@ struct Sm {
 };
 
 // row stride of the block-reduction scratch: one value per thread, one pad word per 16 (bank spread of stage A)
-OB_HD int red_stride(int T) { return T + (T >> 4); }
+OB_HD int red_stride(int T) { return T; }
 
 constexpr int EX_N = 16;   // per block: G(6) Ga(3) Gb(3) gLz(3) h22(1)
 constexpr int RIC_N = 96;   // F8(36) f(8) W(36) pc(6) of the Riccati step in flight
 // task tables of the cooperative Riccati sweep (uint32 words, filled per instance by fill_tables).  One task = one
-// output entry = a dot product of <= 4 terms; a term word holds two shared-memory offsets (in doubles, already
-// multiplied by the stage stride): coefficient offset | operand offset << 16
-constexpr int TW = 0;              // 42 x 4  W = P At (36 entries) and pc = p - P c (6 entries)
-constexpr int TF = TW + 42 * 4;    // 29 x 4  F = H + At^T W (21 entries), f = r + At^T pc (8 entries)
-constexpr int TFH = TF + 29 * 4;   // 21      packed index of the F entry | dw class << 8
-constexpr int TFC = TFH + 21;      // 15      entries of F that are plain copies of H (rows/cols v_prev, w_prev)
-constexpr int TB = TFC + 15;       // 27 x 2  elimination of (v, w): packed F indices
-constexpr int TAB_N = TB + 54;
+// output entry = a dot product of <= 4 terms.  Operands are addressed by 16-bit references into the block's shared
+// memory: bits 0..14 = offset in doubles from the first array, bit 15 = "add the stage index s" (arrays laid out
+// [element][stage]).  A term word = coefficient reference | operand reference << 16.  Every sub-step has <= 32 tasks,
+// so the sweep runs on ONE warp with warp barriers only.
+constexpr int TW = 0;              // 30 x 4  W = P At (24 entries: columns th, T, v, w) and pc = p - P c (6 entries)
+constexpr int TF = TW + 30 * 4;    // 29 x 4  F = H + At^T W (21 entries), f = r + At^T pc (8 entries)
+constexpr int TFH = TF + 29 * 4;   // 29      F entry index | dw class << 8 | (feedback slot + 1) << 12
+constexpr int TB = TFH + 29;       // 27 x 3  elimination of (v, w): operand references (2 per word)
+constexpr int TAB_N = TB + 27 * 3;
+constexpr uint32_t REF_S = 0x8000u;   // reference flag: add the stage index
 
 OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int has_uref) {
   const int S1 = N + 1, nb = no * S1;
@@ -106,19 +108,21 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   s.DSN = take(nb); s.DSD = take(nb); s.XI = take(6 * S1);
   if (o - d0 < (size_t)NPART * red_stride(s.T)) take((size_t)NPART * red_stride(s.T) - (o - d0));
   if (o - d0 < (size_t)EX_N * nb) take((size_t)EX_N * nb - (o - d0));
+  if (o - d0 < (size_t)RIC_N) take((size_t)RIC_N - (o - d0));
   s.SCR_D = base ? base + d0 : nullptr;
   s.EX = s.SCR_D;   // block -> stage exchange of assemble: consumed (combine) before the reduction scratch is written
   const size_t h0 = o;
   s.H = take(36 * S1); s.RA = take(8 * S1);   // H|RA (44 S1) is re-used by the roll-out as ACL(36)|CCL(6)
   if (o - h0 < (size_t)3 * red_stride(s.T)) take((size_t)3 * red_stride(s.T) - (o - h0));
   s.SCR_H = base ? base + h0 : nullptr;
-  s.RB = take(8 * S1); s.GF = take(8 * S1);
+  s.RB = take(8 * S1);
   s.DYN = take(13 * S1); s.CD = s.DYN ? s.DYN + 10 * S1 : nullptr;   // CD = elements 10..12 of DYN (one coefficient base)
   s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1);
   s.GL = s.K;       // Lagrangian gradient of assemble: dead before the sweep writes the feedback gains
   s.ETA = take(25 * (size_t)nb);
   s.A = take(2 * R); s.B0 = take(R); s.DB = take(R); s.XREF = take(3 * S1); s.UREF = take(has_uref ? 2 * N : 0);
-  s.RIC = take(RIC_N); s.RED = take(NPART + 8 * NPART);
+  s.RIC = s.SCR_D;   // scratch of the sweep: the step arrays are dead while the sweep runs
+  s.RED = take(NPART + 8 * NPART);
   s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
   s.G = (Glob*)(base ? base + o : nullptr); o += (sizeof(Glob) + 7) / 8;
   return o;  // doubles
@@ -130,6 +134,8 @@ struct BlockRegs {
   double lam[EMAX], Sl[EMAX], Zl[EMAX];
   double mu[4], Sm_[4], Zm[4];
   double ye[2], Sn, Zn, Sd, Zd;
+  int i, k, r0, E;   // obstacle, stage, first row and edge count of this thread's block (set once per instance)
+  double gf[8];      // stage lanes only: objective gradient of the stage, assemble -> directional derivative
 };
 
 OB_HD void ob_sincos(double x, double* s, double* c) {
@@ -289,8 +295,11 @@ struct Solver {
   int N, S1, no, nb;
   bool free_, has_term, stacked;
 
+  // The dimensions come from the shared-memory map, not from the parameter block: a kernel instantiated for a fixed
+  // (N, n_obs, rows, warps) carves with literals, so every array offset and loop bound below folds to a constant
+  // (on the generic kernel a quarter of the executed instructions were shared-memory address arithmetic).
   OB_HD Solver(const KParams& kp_, const Sm& sm_)
-      : kp(kp_), P(kp_.P), sm(sm_), N(kp_.P.N), S1(kp_.P.N + 1), no(kp_.P.n_obs), nb(kp_.P.n_obs * (kp_.P.N + 1)),
+      : kp(kp_), P(kp_.P), sm(sm_), N(sm_.N), S1(sm_.S1), no(sm_.no), nb(sm_.nb),
         free_(kp_.free_ != 0), has_term(kp_.has_term != 0), stacked(kp_.stacked != 0) {}
 
   // ---- thread roles
@@ -426,8 +435,7 @@ struct Solver {
       if (k == 0) { G.T = T0; G.yt[0] = G.yt[1] = G.yt[2] = 0.0; }
     }
     if (is_block(tid)) {
-      const int i = tid / S1, k = tid % S1;
-      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
 #pragma unroll
       for (int j = 0; j < EMAX; ++j) br.lam[j] = 0.0;
 #pragma unroll
@@ -556,8 +564,7 @@ struct Solver {
       }
     }
     if (is_block(tid)) {
-      const int i = tid / S1, k = tid % S1;
-      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
       const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
       double st, ct;
       ob_sincos(z2, &st, &ct);
@@ -585,7 +592,7 @@ struct Solver {
   // sides are split as  mu * (a part) + (b part)  so that mu can be chosen from this pass's own error.
   // Leaves H, RA, RB (without the Lagrangian gradient), GL, GF, CD, DYN in shared memory.
   // ------------------------------------------------------------------------------------------------
-  OB_HD void assemble_stage(int k, double* part) const {
+  OB_HD void assemble_stage(int k, BlockRegs<EMAX>& br, double* part) const {
     const Glob& G = *sm.G;
     double z[3], u[2], up[2], zn[3], yd[3], ydm[3];
     stage_point(k, 0.0, z, u, up, zn);
@@ -765,7 +772,7 @@ struct Solver {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       sm.st(sm.RA, i, k) = ra[i]; sm.st(sm.RB, i, k) = rb[i]; sm.st(sm.GL, i, k) = gL[i] + gf[i];
-      sm.st(sm.GF, i, k) = gf[i]; sm.st(sm.DYN, i, k) = dyn[i];
+      br.gf[i] = gf[i]; sm.st(sm.DYN, i, k) = dyn[i];
     }
     sm.st(sm.DYN, 8, k) = dyn[8]; sm.st(sm.DYN, 9, k) = dyn[9];
 #pragma unroll
@@ -781,8 +788,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   OB_HD void assemble_block(int tid, const BlockRegs<EMAX>& br, double* part) const {
     const Glob& G = *sm.G;
-    const int i = tid / S1, k = tid % S1;
-    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
     const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
     BlkGeo b;
     ob_sincos(z2, &b.st, &b.ct);
@@ -977,59 +983,83 @@ struct Solver {
       default: break;
     }
   }
-  // thread -> task tables of the sweep (every thread fills a few words)
+  // shared-memory reference of element e of a stage array (bit 15: + stage index) / of a scratch word
+  OB_HD uint32_t ref_st(const double* arr, int e, int dstage = 0) const { return (uint32_t)((arr - sm.Z) + e * S1 + dstage) | REF_S; }
+  OB_HD uint32_t ref_abs(const double* p) const { return (uint32_t)(p - sm.Z); }
+  OB_HD double ld(uint32_t ref, int s) const { return sm.Z[(ref & 0x7fffu) + ((ref & REF_S) ? s : 0)]; }
+  // feedback-gain inputs kept per stage for fwd_prep (in the K|KAP region): F(6,b), F(7,b) for b in {0,1,2,5},
+  // the 2x2 pivot block, f6, f7
+  OB_HD static int kraw_slot(int e) {   // e = packed index of the 8x8 system, or 36 + a for f[a]
+    switch (e) {
+      case 21: return 0; case 22: return 1; case 23: return 2; case 26: return 3;
+      case 28: return 4; case 29: return 5; case 30: return 6; case 33: return 7;
+      case 27: return 8; case 34: return 9; case 35: return 10; case 42: return 11; case 43: return 12;
+      default: return -1;
+    }
+  }
+  // lane -> task tables of the sweep (every thread fills a few words; depends on the sizes only)
   OB_HD void fill_tables(int tid) const {
     const int I6[6] = {0, 1, 2, 5, 6, 7};
     uint32_t* tab = sm.TAB;
     int rows[4], cfs[4];
-    for (int t = tid; t < 42; t += sm.T) {
-      if (t < 36) {                                  // W[r][jj] = sum_p cf[c_p] P[r, row_p]
-        const int r = t / 6, jj = t % 6;
+    const double* Wb = sm.RIC + 44;   // W[r][jj-2], jj = 2..5
+    const double* pcb = sm.RIC + 80;
+    for (int t = tid; t < 30; t += sm.T) {
+      if (t < 24) {                                  // W[r][jj] = sum_p cf[c_p] P_{s+1}[r, row_p],  jj = 2..5
+        const int r = t / 4, jj = 2 + t % 4;
         at_col_tab(I6[jj], rows, cfs);
-        for (int p = 0; p < 4; ++p) tab[TW + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)(symi(r, rows[p]) * S1) << 16);
-      } else {                                       // pc[r] = p[r] - sum_j cd[j] P[r, j]   (cd = DYN elements 10..12)
-        const int r = t - 36;
+        for (int p = 0; p < 4; ++p) tab[TW + 4 * t + p] = ref_st(sm.DYN, cfs[p]) | (ref_st(sm.PM, symi(r, rows[p]), 1) << 16);
+      } else {                                       // pc[r] = p_{s+1}[r] - sum_j cd[j] P_{s+1}[r, j]   (cd = DYN 10..12)
+        const int r = t - 24;
         for (int p = 0; p < 4; ++p)
-          tab[TW + 4 * t + p] = (uint32_t)((p < 3 ? 10 + p : 9) * S1) | ((uint32_t)(symi(r, p < 3 ? p : 0) * S1) << 16);
+          tab[TW + 4 * t + p] = ref_st(sm.DYN, p < 3 ? 10 + p : 9) | (ref_st(sm.PM, symi(r, p < 3 ? p : 0), 1) << 16);
       }
     }
     for (int t = tid; t < 29; t += sm.T) {
-      if (t < 21) {                                  // F[a][b] = H[a][b] + sum_p cf[c_p] W[row_p][jb],  a, b in I6
+      if (t < 21) {                                  // F[a][b] = H[a][b] + sum_p cf[c_p] (P At)[row_p][b],  a, b in I6
         int ia = 0;
         while ((ia + 1) * (ia + 2) / 2 <= t) ++ia;
         const int ib = t - ia * (ia + 1) / 2, a = I6[ia], b = I6[ib];
         at_col_tab(a, rows, cfs);
-        for (int p = 0; p < 4; ++p) tab[TF + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)(rows[p] * 6 + ib) << 16);
+        for (int p = 0; p < 4; ++p) {
+          // columns x, y of At are unit vectors: (P At)[r][x|y] is P itself
+          const uint32_t op = (ib >= 2) ? ref_abs(Wb + rows[p] * 4 + (ib - 2)) : ref_st(sm.PM, symi(rows[p], ib), 1);
+          tab[TF + 4 * t + p] = ref_st(sm.DYN, cfs[p]) | (op << 16);
+        }
         const int cls = (a != b) ? 0 : (a < 3 ? 1 : (a >= 6 ? 2 : 3));
-        tab[TFH + t] = (uint32_t)symi(a, b) | ((uint32_t)cls << 8);
+        const int e = symi(a, b);
+        tab[TFH + t] = (uint32_t)e | ((uint32_t)cls << 8) | ((uint32_t)(kraw_slot(e) + 1) << 12);
       } else {                                       // f[a] = r[a] + sum_p cf[c_p] pc[row_p]
         const int a = t - 21;
         at_col_tab(a, rows, cfs);
-        for (int p = 0; p < 4; ++p) tab[TF + 4 * t + p] = (uint32_t)(cfs[p] * S1) | ((uint32_t)rows[p] << 16);
+        for (int p = 0; p < 4; ++p) tab[TF + 4 * t + p] = ref_st(sm.DYN, cfs[p]) | (ref_abs(pcb + rows[p]) << 16);
+        tab[TFH + t] = (uint32_t)(36 + a) | ((uint32_t)(kraw_slot(36 + a) + 1) << 12);
       }
     }
-    if (tid == 0) {
-      int n = 0;
-      for (int a = 0; a < 8; ++a)
-        for (int b = 0; b <= a; ++b)
-          if (a == 3 || a == 4 || b == 3 || b == 4) tab[TFC + n++] = (uint32_t)symi(a, b);
-    }
     for (int t = tid; t < 27; t += sm.T) {          // elimination of (v, w) = variables 6, 7
+      // entry (x, y) of the 8x8 system: computed entries sit in the scratch, rows/columns v_prev, w_prev are H itself
+      auto fref = [&](int x, int y) -> uint32_t {
+        const int e = symi(x, y);
+        const bool inH = (x == 3 || x == 4 || y == 3 || y == 4);
+        return inH ? ref_st(sm.H, e) : ref_abs(sm.RIC + e);
+      };
       if (t < 21) {
         int a = 0;
         while ((a + 1) * (a + 2) / 2 <= t) ++a;
         const int b = t - a * (a + 1) / 2;
-        tab[TB + 2 * t] = (uint32_t)symi(a, b) | ((uint32_t)symi(6, a) << 8) | ((uint32_t)symi(7, a) << 16) | ((uint32_t)symi(6, b) << 24);
-        tab[TB + 2 * t + 1] = (uint32_t)symi(7, b);
+        tab[TB + 3 * t] = fref(a, b) | (fref(6, a) << 16);
+        tab[TB + 3 * t + 1] = fref(7, a) | (fref(6, b) << 16);
+        tab[TB + 3 * t + 2] = fref(7, b);
       } else {
         const int a = t - 21;
-        tab[TB + 2 * t] = (uint32_t)symi(6, a) | ((uint32_t)symi(7, a) << 8);
-        tab[TB + 2 * t + 1] = 0;
+        tab[TB + 3 * t] = fref(6, a) | (fref(7, a) << 16);
+        tab[TB + 3 * t + 1] = ref_abs(sm.RIC + 36 + a);
+        tab[TB + 3 * t + 2] = 0;
       }
     }
   }
-  // The sweep runs on ALL threads of the block (one task per thread, a block barrier per sub-step): a single warp
-  // would serialise two task rounds per sub-step, and the sweep is the longest dependent chain of an iteration.
+  // The sweep is the longest dependent chain of an iteration (3 sub-steps x N stages).  Each sub-step has <= 32 tasks
+  // and runs on the stage warp alone, separated by warp barriers; the other warps wait at one block barrier.
   OB_HD void ric_terminal(int t, double mu, double dw, double dc) const {
     // stage N: cost-to-go = its own 6x6 block (terminal equality folded in Levenberg-Marquardt style)
     const int s = N;
@@ -1044,71 +1074,55 @@ struct Solver {
       sm.st(sm.PV, a, s) = r;
     }
   }
-  // sub-step 1:  W = P_{s+1} At (6x6 over the non-empty columns),  pc = p_{s+1} - P_{s+1} c
+  // sub-step 1:  W = P_{s+1} At (columns th, T, v, w),  pc = p_{s+1} - P_{s+1} c
   OB_HD void ric_w(int t, int s) const {
-    if (t >= 42) return;
+    if (t >= 30) return;
     const uint32_t* w = sm.TAB + TW + 4 * t;
-    const double* Pn = sm.PM + (s + 1);
-    const double* cf = sm.DYN + s;
     double acc = 0.0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc += cf[w[p] & 0xffff] * Pn[w[p] >> 16];
-    if (t < 36) sm.RIC[44 + t] = acc;
-    else sm.RIC[80 + (t - 36)] = sm.st(sm.PV, t - 36, s + 1) - acc;
+    for (int p = 0; p < 4; ++p) acc += ld(w[p] & 0xffffu, s) * ld(w[p] >> 16, s);
+    if (t < 24) sm.RIC[44 + t] = acc;
+    else sm.RIC[80 + (t - 24)] = sm.st(sm.PV, t - 24, s + 1) - acc;
   }
   // sub-step 2:  F = H + At^T W (+ dw on the regularised diagonal),  f = mu ra + rb + At^T pc
   OB_HD void ric_f(int t, int s, double mu, double dw) const {
-    double* F = sm.RIC;
-    const double* cf = sm.DYN + s;
-    if (t < 29) {
-      const uint32_t* w = sm.TAB + TF + 4 * t;
-      const double* op = (t < 21) ? sm.RIC + 44 : sm.RIC + 80;   // W or pc
-      double acc = 0.0;
+    if (t >= 29) return;
+    const uint32_t* w = sm.TAB + TF + 4 * t;
+    double acc = 0.0;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) acc += cf[w[p] & 0xffff] * op[w[p] >> 16];
-      if (t < 21) {
-        const uint32_t h = sm.TAB[TFH + t];
-        const int e = h & 255, cls = h >> 8;
-        acc += sm.st(sm.H, e, s);
-        if ((cls == 1 && s >= 1) || cls == 2 || (cls == 3 && s == 0 && free_)) acc += dw;
-        F[e] = acc;
-      } else {
-        const int a = t - 21;
-        F[36 + a] = acc + mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
-      }
-    } else if (t < 44) {
-      const int e = sm.TAB[TFC + t - 29];
-      F[e] = sm.st(sm.H, e, s);
+    for (int p = 0; p < 4; ++p) acc += ld(w[p] & 0xffffu, s) * ld(w[p] >> 16, s);
+    const uint32_t h = sm.TAB[TFH + t];
+    const int e = h & 255, cls = (h >> 8) & 15, slot = (int)(h >> 12) - 1;
+    if (t < 21) {
+      acc += sm.st(sm.H, e, s);
+      if ((cls == 1 && s >= 1) || cls == 2 || (cls == 3 && s == 0 && free_)) acc += dw;
+    } else {
+      const int a = e - 36;
+      acc += mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
     }
+    sm.RIC[e] = acc;
+    if (slot >= 0) sm.st(sm.K, slot, s) = acc;
   }
-  // sub-step 3: eliminate (v, w); cost-to-go and feedback of stage s
+  // sub-step 3: eliminate (v, w); cost-to-go of stage s (the feedback gains follow in fwd_prep, lane-parallel)
   OB_HD void ric_b(int t, int s) const {
-    if (t >= 41) return;
+    if (t >= 27) return;
     Glob& G = *sm.G;
-    const uint32_t* tab = sm.TAB;
+    const uint32_t* w = sm.TAB + TB + 3 * t;
     const double* F = sm.RIC;
-    const double* f = sm.RIC + 36;
     const double q00 = F[27], q01 = F[34], q11 = F[35];   // (6,6) (7,6) (7,7)
     const double det = q00 * q11 - q01 * q01;
     if (t == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
     const double idet = ob_rcp(det);
     const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
     if (t < 21) {
-      const uint32_t w0 = tab[TB + 2 * t], w1 = tab[TB + 2 * t + 1];
-      const double fa6 = F[(w0 >> 8) & 255], fa7 = F[(w0 >> 16) & 255], fb6 = F[w0 >> 24], fb7 = F[w1 & 255];
-      sm.st(sm.PM, t, s) = F[w0 & 255] - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
-    } else if (t < 27) {
-      const int a = t - 21;
-      const uint32_t w0 = tab[TB + 2 * t];
-      const double kap0 = i00 * f[6] + i01 * f[7], kap1 = i01 * f[6] + i11 * f[7];
-      sm.st(sm.PV, a, s) = f[a] - F[w0 & 255] * kap0 - F[(w0 >> 8) & 255] * kap1;
-    } else if (t < 39) {
-      const int q = t - 27, row = (q >= 6) ? 1 : 0, b = q - 6 * row;
-      const double f6 = F[21 + b], f7 = F[28 + b];       // (6,b) (7,b), b < 6
-      sm.st(sm.K, q, s) = (row == 0) ? -(i00 * f6 + i01 * f7) : -(i01 * f6 + i11 * f7);
+      const double fab = ld(w[0] & 0xffffu, s), fa6 = ld(w[0] >> 16, s), fa7 = ld(w[1] & 0xffffu, s);
+      const double fb6 = ld(w[1] >> 16, s), fb7 = ld(w[2] & 0xffffu, s);
+      sm.st(sm.PM, t, s) = fab - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
     } else {
-      const int row = t - 39;
-      sm.st(sm.KAP, row, s) = (row == 0) ? i00 * f[6] + i01 * f[7] : i01 * f[6] + i11 * f[7];
+      const int a = t - 21;
+      const double f6 = F[42], f7 = F[43];
+      const double kap0 = i00 * f6 + i01 * f7, kap1 = i01 * f6 + i11 * f7;
+      sm.st(sm.PV, a, s) = ld(w[1] & 0xffffu, s) - ld(w[0] & 0xffffu, s) * kap0 - ld(w[0] >> 16, s) * kap1;
     }
   }
   OB_HD void ric_finish(int t) const {
@@ -1130,10 +1144,22 @@ struct Solver {
       for (int a = 0; a < 6; ++a) sm.st(sm.XI, a, 0) = (a == 5) ? dT : 0.0;
     }
     if (k >= N) return;
+    // feedback gains K = -Q^-1 F_ux, kap = Q^-1 f_u from what the sweep left in the K|KAP region (kraw_slot) and the
+    // untouched (v_prev, w_prev) columns of H - read before ACL|CCL overwrite H|RA below
     double Kr[2][6], kap[2];
+    {
+      const double q00 = sm.st(sm.K, 8, k), q01 = sm.st(sm.K, 9, k), q11 = sm.st(sm.K, 10, k);
+      const double idet = ob_rcp(q00 * q11 - q01 * q01);
+      const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
+      const double F6[6] = {sm.st(sm.K, 0, k), sm.st(sm.K, 1, k), sm.st(sm.K, 2, k), sm.st(sm.H, symi(6, 3), k),
+                            sm.st(sm.H, symi(6, 4), k), sm.st(sm.K, 3, k)};
+      const double F7[6] = {sm.st(sm.K, 4, k), sm.st(sm.K, 5, k), sm.st(sm.K, 6, k), sm.st(sm.H, symi(7, 3), k),
+                            sm.st(sm.H, symi(7, 4), k), sm.st(sm.K, 7, k)};
+      const double f6 = sm.st(sm.K, 11, k), f7 = sm.st(sm.K, 12, k);
 #pragma unroll
-    for (int b = 0; b < 6; ++b) { Kr[0][b] = sm.st(sm.K, b, k); Kr[1][b] = sm.st(sm.K, 6 + b, k); }
-    kap[0] = sm.st(sm.KAP, 0, k); kap[1] = sm.st(sm.KAP, 1, k);
+      for (int b = 0; b < 6; ++b) { Kr[0][b] = -(i00 * F6[b] + i01 * F7[b]); Kr[1][b] = -(i01 * F6[b] + i11 * F7[b]); }
+      kap[0] = i00 * f6 + i01 * f7; kap[1] = i01 * f6 + i11 * f7;
+    }
     const double fth0 = sm.st(sm.DYN, 0, k), fth1 = sm.st(sm.DYN, 1, k), bv0 = sm.st(sm.DYN, 2, k), bv1 = sm.st(sm.DYN, 3, k);
     const double bw = sm.st(sm.DYN, 4, k), fT0 = sm.st(sm.DYN, 5, k), fT1 = sm.st(sm.DYN, 6, k), fT2 = sm.st(sm.DYN, 7, k);
     const double cd0 = sm.st(sm.CD, 0, k), cd1 = sm.st(sm.CD, 1, k), cd2 = sm.st(sm.CD, 2, k);
@@ -1213,7 +1239,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // steps of the slacks, fraction to the boundary, directional derivative - stage part (lane k)
   // ------------------------------------------------------------------------------------------------
-  OB_HD void backsub_stage(int k, double mu, double tau, double* part) const {
+  OB_HD void backsub_stage(int k, const BlockRegs<EMAX>& br, double mu, double tau, double* part) const {
     Glob& G = *sm.G;
     double z[3], u[2], up[2], zn[3], dz[3], du[2], dup[2];
     stage_point(k, 0.0, z, u, up, zn);
@@ -1226,9 +1252,7 @@ struct Solver {
     stage_vals(k, z, u, up, zn, T, sv);
     double amax = 1.0, az = 1.0, sls = 0.0, dphi = 0.0;
     {
-      double gf[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) gf[i] = sm.st(sm.GF, i, k);
+      const double* gf = br.gf;
       if (k >= 1) dphi += gf[0] * dz[0] + gf[1] * dz[1] + gf[2] * dz[2];
       if (k >= 1 && k < N) dphi += gf[3] * dup[0] + gf[4] * dup[1];
       if (free_) dphi += gf[5] * dT;
@@ -1277,8 +1301,7 @@ struct Solver {
   // block part: back-substitution of the dual block
   OB_HD void backsub_block(int tid, const BlockRegs<EMAX>& br, double mu, double tau, double* part) const {
     const Glob& G = *sm.G;
-    const int i = tid / S1, k = tid % S1;
-    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
     const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
     BlkGeo b;
     ob_sincos(z2, &b.st, &b.ct);
@@ -1385,8 +1408,7 @@ struct Solver {
   }
   OB_HD void trial_block(int tid, const BlockRegs<EMAX>& br, double a, double* part) const {
     const Glob& G = *sm.G;
-    const int i = tid / S1, k = tid % S1;
-    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
     const double ak = (k >= 1) ? a : 0.0;
     const double z0 = sm.st(sm.Z, 0, k) + ak * sm.st(sm.DZ, 0, k), z1 = sm.st(sm.Z, 1, k) + ak * sm.st(sm.DZ, 1, k);
     const double z2 = sm.st(sm.Z, 2, k) + ak * sm.st(sm.DZ, 2, k);
@@ -1470,8 +1492,7 @@ struct Solver {
       }
     }
     if (is_block(tid)) {
-      const int i = tid / S1, k = tid % S1;
-      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
 #pragma unroll
       for (int j = 0; j < EMAX; ++j) {
         if (j < E) {
@@ -1559,8 +1580,7 @@ struct Solver {
       }
     }
     if (is_block(tid)) {
-      const int i = tid / S1, k = tid % S1;
-      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
       double* lo = kp.lam + (b * S1 + k) * R + r0;
 #pragma unroll
       for (int j = 0; j < EMAX; ++j)
@@ -1578,6 +1598,8 @@ struct Solver {
 //   reduce<S0,NS,M0,NM,N0,NN>(scratch)  one block reduction over the threads' part[] slots: sum of slots S0..S0+NS-1,
 //                     max of M0.., min of N0.. (results in ex.red[] at the same slots)
 //   all(f)            run f(tid) on every thread of the block, then a block barrier (no per-thread state)
+//   sweep(f)          run f(t) for t < 64 (first two warps) closed by a barrier among those 64 threads;
+//   sweep_end()       block barrier that opens / closes a run of sweep() calls
 //   stage(f)          run f(lane) on the 32 lanes of the stage warp, then a warp barrier (no block barrier)
 //   stage_end()       block barrier closing a run of stage() calls
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
@@ -1600,7 +1622,11 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   const int q_in = 12 * N + (free_ ? 2 : 0) + (has_term ? 3 : 0) + (S.sm.R + 6 * no) * (N + 1);
   typedef BlockRegs<EMAX> BR;
 
-  ex.par([&](int tid, BR& br, double* part) { (void)br; S.start_a(tid, part); S.fill_tables(tid); });
+  ex.par([&](int tid, BR& br, double* part) {
+    br.i = (tid < S.nb) ? tid / S.S1 : 0; br.k = (tid < S.nb) ? tid % S.S1 : 0;
+    br.r0 = S.kp.eptr[br.i]; br.E = S.kp.eptr[br.i + 1] - br.r0;
+    S.start_a(tid, part); S.fill_tables(tid);
+  });
   ex.template reduce<0, 1, 0, 0, 0, 0>(S.sm.SCR_H);
   const double T0 = S.start_T(ex.red[0]);
   ex.par([&](int tid, BR& br, double* part) { (void)part; S.start_b(tid, br, T0); });
@@ -1625,12 +1651,14 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     // ---- assemble
     ex.par([&](int tid, BR& br, double* part) {
       if (S.is_block(tid)) S.assemble_block(tid, br, part);
-      else if (S.is_stage(tid)) S.assemble_stage(S.stage_lane(tid), part);
+      else if (S.is_stage(tid)) S.assemble_stage(S.stage_lane(tid), br, part);
       else for (int q = 0; q < NPART; ++q) part[q] = (q == PN_SZMIN) ? 1e300 : 0.0;
     });
-    ex.par([&](int tid, BR& br, double* part) { (void)br; if (S.is_stage(tid)) S.assemble_combine(S.stage_lane(tid), part); });
-    ex.template reduce<PS_F, 6, PM_E1, 5, PN_SZMIN, 1>(S.sm.SCR_D);
     ex.tick(1);
+    ex.par([&](int tid, BR& br, double* part) { (void)br; if (S.is_stage(tid)) S.assemble_combine(S.stage_lane(tid), part); });
+    ex.tick(2);
+    ex.template reduce<PS_F, 6, PM_E1, 5, PN_SZMIN, 1>(S.sm.SCR_D);
+    ex.tick(3);
     const double Ef = ex.red[PS_F], Eth = ex.red[PS_TH], ElgS = ex.red[PS_LG], Esumy = ex.red[PS_SUMY], Esumz = ex.red[PS_SUMZ];
     double Ee1 = ex.red[PM_E1];
     if (free_) Ee1 = fmax(Ee1, fabs(ex.red[PS_GT]));
@@ -1644,7 +1672,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     if (E0 <= P.acceptable_tol) {
       // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails
       // later on.  The store goes straight to the result arrays: no on-chip copy is kept.
-      if (E0 < best_E0) {
+      if (E0 < 0.1 * best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
         best_E0 = E0; best_f = Ef;
         ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
       }
@@ -1668,18 +1696,21 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     const double th = Eth, ph0 = Ef - mu * ElgS;
     const double tau = fmax(tau_min, 1 - mu);
     const double dc = free_ ? fmax(dc_min, Ectmax / lm_cap) : 0.0;
+    ex.tick(4);
     // ---- Riccati with inertia correction: the pivots are the inertia test
     double dw = 0.0;
     bool regfail = false;
     for (;;) {
       ex.once([&]() { G.bad = 0; });
-      ex.all([&](int t) { S.ric_terminal(t, mu, dw, dc); });
+      ex.stage_end();
+      ex.stage([&](int t) { S.ric_terminal(t, mu, dw, dc); });
       for (int s = N - 1; s >= 0; --s) {
-        ex.all([&](int t) { S.ric_w(t, s); });
-        ex.all([&](int t) { S.ric_f(t, s, mu, dw); });
-        ex.all([&](int t) { S.ric_b(t, s); });
+        ex.stage([&](int t) { S.ric_w(t, s); });
+        ex.stage([&](int t) { S.ric_f(t, s, mu, dw); });
+        ex.stage([&](int t) { S.ric_b(t, s); });
       }
-      ex.all([&](int t) { S.ric_finish(t); });
+      ex.stage([&](int t) { S.ric_finish(t); });
+      ex.stage_end();
       if (!G.bad) break;
       if (dw == 0.0) dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
       else dw = dw * ((dw_last == 0.0) ? kw_plus_first : kw_plus);
@@ -1688,21 +1719,22 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     }
     if (regfail) { status = OBCA_ST_REGFAIL; break; }
     if (dw > 0) dw_last = dw;
-    ex.tick(2);
+    ex.tick(5);
     // ---- roll-out
     ex.stage([&](int lane) { if (lane <= N) S.fwd_prep(lane); });
     for (int s = 0; s < N; ++s) ex.stage([&](int lane) { S.fwd_step(lane, s); });
     ex.stage([&](int lane) { if (lane <= N) S.fwd_post(lane, dc); });
     ex.stage_end();
-    ex.tick(3);
+    ex.tick(6);
     // ---- steps of the duals / slacks, fraction to the boundary
     ex.par([&](int tid, BR& br, double* part) {
       if (S.is_block(tid)) S.backsub_block(tid, br, mu, tau, part);
-      else if (S.is_stage(tid)) S.backsub_stage(S.stage_lane(tid), mu, tau, part);
+      else if (S.is_stage(tid)) S.backsub_stage(S.stage_lane(tid), br, mu, tau, part);
       else { part[QS_DPHI] = 0.0; part[QN_AMAX] = 1.0; part[QN_AZ] = 1.0; }
     });
+    ex.tick(7);
     ex.template reduce<QS_DPHI, 1, 0, 0, QN_AMAX, 2>(S.sm.SCR_H);
-    ex.tick(4);
+    ex.tick(8);
     const double Dphi = ex.red[QS_DPHI], a_max = ex.red[QN_AMAX], a_z = ex.red[QN_AZ];
     if (!f_active) {
       thmax = 1e4 * fmax(1.0, th); thmin = 1e-4 * fmax(1.0, th);
@@ -1729,12 +1761,14 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       if (th_r <= thmin && sw) return (pht <= ph_r + eta_ph * a_r * dphi_r + 10 * 2.220446049250313e-16 * fabs(ph_r)) ? 2 : 0;
       return (tht <= (1 - g_th) * th_r || pht <= ph_r - g_ph * th_r) ? 1 : 0;
     };
+    ex.tick(9);
     while (a >= a_min * (1 - 1e-12)) {
       ex.par([&](int tid, BR& br, double* part) {
         if (S.is_block(tid)) S.trial_block(tid, br, a, part);
         else if (S.is_stage(tid)) S.trial_stage(S.stage_lane(tid), a, part);
         else { part[0] = part[1] = part[2] = 0.0; }
       });
+      ex.tick(10);
       ex.template reduce<0, 3, 0, 0, 0, 0>(S.sm.SCR_H);
       const double tht = ex.red[1], pht = ex.red[0] - mu * ex.red[2];
       if (in_wd) {
@@ -1770,7 +1804,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     // IPOPT ends with Solved_To_Acceptable_Level when it cannot progress from an acceptable point; the second
     // clause is the rounding-noise floor of a degenerate vertex of the OBCA dual polytope
     const bool at_floor = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
-    ex.tick(5);
+    ex.tick(11);
     ex.trace(iter, Ef, th, E0, mu, dw, accepted ? a : -1.0);
     if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
@@ -1783,10 +1817,10 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       f_wr++;
     }
     ex.par([&](int tid, BR& br, double* part) { (void)part; S.update(tid, br, a, a_z, mu); });
-    ex.tick(6);
+    ex.tick(12);
     iter++;
   }
-  ex.tick(7);
+  ex.tick(13);
   iters_out = iter;
   if (status < 0 && best_E0 < 1e300) {
     // x, u, lam, mu, T of the stored acceptable point are already in the result arrays
