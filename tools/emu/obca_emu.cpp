@@ -24,8 +24,8 @@ struct HostExec {
   }
   template <class F> void par(F&& f) { for (int t = 0; t < T; ++t) f(t, brs[t], parts[t].data()); }
   template <class F> void all(F&& f) { for (int t = 0; t < T; ++t) f(t); }
-  template <class F> void sweep(F&& f) { for (int t = 0; t < 64; ++t) f(t); }
-  void sweep_end() {}
+  SweepRegs srs[32];
+  template <class F> void sweep(F&& f) { for (int l = 0; l < 32; ++l) f(l, srs[l]); }
   template <class F> void stage(F&& f) { for (int l = 0; l < 32; ++l) f(l); }
   void stage_end() {}
   template <class F> void once(F&& f) { f(); }

@@ -55,6 +55,8 @@ def main():
     it = out["iters"].cpu().numpy()
     print("cfg %d B %d kernel %.2f ms -> %.0f solves/s, iters mean %.1f max %d" % (cfg, B, s.last_kernel_ms(), B / s.last_kernel_ms() * 1e3, it.mean(), it.max()))
     print("  %-10s %8s %12s %14s %14s" % ("phase", "share", "cycles/iter", "block-warp work", "stage-warp work"))
+    print("  sweep sub-steps: %.1f per iteration, %.0f cycles each (stage warp, clock64 around body + warp barrier)" % (
+        buf[32 + 14] / max(1, it.sum()), buf[32 + 15] / max(1, buf[32 + 14])))
     for i, (n, v) in enumerate(zip(names, buf[:14])):
         print("  %-12s %6.2f %%  %10.0f" % (n, 100.0 * v / tot, v / max(1, it.sum())))
 

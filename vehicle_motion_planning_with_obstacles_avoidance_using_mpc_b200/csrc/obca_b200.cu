@@ -75,12 +75,14 @@ struct DevExec {
   template <class F> __device__ __forceinline__ void par(F&& f) { f(tid, br, part); __syncthreads(); }
 #endif
   template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
-  // sweep sub-step: <= 64 tasks, run by warps 0-1 only and closed by a 64-thread named barrier; the other warps
-  // skip the whole sweep and rejoin at the block barrier of sweep_end()
+  SweepRegs sr;
   template <class F> __device__ __forceinline__ void sweep(F&& f) {
-    if (warp < 2) { f(tid); asm volatile("bar.sync 1, 64;" ::: "memory"); }
+#ifdef OBCA_PROFILE
+    if (stage_warp) { const long long t0 = clock64(); f(lane, sr); __syncwarp(); work[15] += clock64() - t0; work[14] += 1; }
+#else
+    if (stage_warp) { f(lane, sr); __syncwarp(); }
+#endif
   }
-  __device__ __forceinline__ void sweep_end() { __syncthreads(); }
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
   }

@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define OB_HD __host__ __device__ __forceinline__
+#define OB_COLD __host__ __device__ __noinline__   // once-per-instance / rare paths: kept out of the iteration body
 #else
 #define OB_HD inline
+#define OB_COLD inline
 #endif
 
 namespace obca {
@@ -97,7 +99,9 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   const int S1 = N + 1, nb = no * S1;
   s.N = N; s.S1 = S1; s.no = no; s.R = R; s.nb = nb; s.nwarps = nwarps; s.T = 32 * nwarps; s.has_uref = has_uref;
   size_t o = 0;
-  auto take = [&](size_t n) { double* p = base ? base + o : nullptr; o += n; return p; };
+  // (base may be null when only the size is wanted: the pointers are then meaningless but never dereferenced; no
+  //  null test here - on the device it would put a select in front of every shared-memory access)
+  auto take = [&](size_t n) { double* p = base + o; o += n; return p; };
   s.Z = take(3 * S1); s.U = take(2 * S1); s.YD = take(3 * S1);
   s.SXY = take(4 * S1); s.ZXY = take(4 * S1); s.SUB = take(8 * S1); s.ZUB = take(8 * S1);
   // step arrays first: together with the padding they double as the scratch of the 12-slot block reduction that
@@ -109,14 +113,14 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   if (o - d0 < (size_t)NPART * red_stride(s.T)) take((size_t)NPART * red_stride(s.T) - (o - d0));
   if (o - d0 < (size_t)EX_N * nb) take((size_t)EX_N * nb - (o - d0));
   if (o - d0 < (size_t)RIC_N) take((size_t)RIC_N - (o - d0));
-  s.SCR_D = base ? base + d0 : nullptr;
+  s.SCR_D = base + d0;
   s.EX = s.SCR_D;   // block -> stage exchange of assemble: consumed (combine) before the reduction scratch is written
   const size_t h0 = o;
   s.H = take(36 * S1); s.RA = take(8 * S1);   // H|RA (44 S1) is re-used by the roll-out as ACL(36)|CCL(6)
   if (o - h0 < (size_t)3 * red_stride(s.T)) take((size_t)3 * red_stride(s.T) - (o - h0));
-  s.SCR_H = base ? base + h0 : nullptr;
+  s.SCR_H = base + h0;
   s.RB = take(8 * S1);
-  s.DYN = take(13 * S1); s.CD = s.DYN ? s.DYN + 10 * S1 : nullptr;   // CD = elements 10..12 of DYN (one coefficient base)
+  s.DYN = take(13 * S1); s.CD = s.DYN + 10 * S1;   // CD = elements 10..12 of DYN (one coefficient base)
   s.K = take(12 * S1); s.KAP = take(2 * S1); s.PM = take(21 * S1); s.PV = take(6 * S1);
   s.GL = s.K;       // Lagrangian gradient of assemble: dead before the sweep writes the feedback gains
   s.ETA = take(25 * (size_t)nb);
@@ -124,7 +128,7 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   s.RIC = s.SCR_D;   // scratch of the sweep: the step arrays are dead while the sweep runs
   s.RED = take(NPART + 8 * NPART);
   s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
-  s.G = (Glob*)(base ? base + o : nullptr); o += (sizeof(Glob) + 7) / 8;
+  s.G = (Glob*)(base + o); o += (sizeof(Glob) + 7) / 8;
   return o;  // doubles
 }
 
@@ -136,6 +140,15 @@ struct BlockRegs {
   double ye[2], Sn, Zn, Sd, Zd;
   int i, k, r0, E;   // obstacle, stage, first row and edge count of this thread's block (set once per instance)
   double gf[8];      // stage lanes only: objective gradient of the stage, assemble -> directional derivative
+};
+
+// registers of a stage-warp lane during the Riccati sweep: the operand addresses of its three tasks, decoded once per
+// sweep from the task tables (offsets in doubles from the first shared array; "+s" = add the stage index)
+struct SweepRegs {
+  uint32_t wc[4], wo[4];         // sub-step 1: coefficient / operand offsets, all +s
+  uint32_t fc[4], fo[4], fs;     // sub-step 2: coefficient offsets (+s), operand offsets, fs = 1 if the operands are +s
+  uint32_t fmeta;                //             F entry | dw class << 8 | (feedback slot + 1) << 12
+  uint32_t bo[5], bs;            // sub-step 3: operand offsets, bit p of bs = operand p is +s
 };
 
 OB_HD void ob_sincos(double x, double* s, double* c) {
@@ -349,7 +362,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // instance load (all threads): inputs HBM -> shared, once
   // ------------------------------------------------------------------------------------------------
-  OB_HD void load(int tid, size_t b, bool load_obs) const {
+  OB_COLD void load(int tid, size_t b, bool load_obs) const {
     Glob& G = *sm.G;
     const int T = sm.T, R = sm.R;
     for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = kp.xref[b * 3 * S1 + i];
@@ -416,7 +429,7 @@ struct Solver {
     return fmin(fmax(T0, 1.0), fmax(G.Tmax, P.T_min));
   }
   // Pass 2: inputs (stage lanes) and duals (block threads)
-  OB_HD void start_b(int tid, BlockRegs<EMAX>& br, double T0) const {
+  OB_COLD void start_b(int tid, BlockRegs<EMAX>& br, double T0) const {
     Glob& G = *sm.G;
     if (is_stage(tid)) {
       const int k = stage_lane(tid);
@@ -540,7 +553,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // slack / multiplier initialisation: S = max(d(x0), bound_push), Z = 1
   // ------------------------------------------------------------------------------------------------
-  OB_HD void init_slacks(int tid, BlockRegs<EMAX>& br) const {
+  OB_COLD void init_slacks(int tid, BlockRegs<EMAX>& br) const {
     Glob& G = *sm.G;
     const double bp = P.bound_push;
     const double T = free_ ? G.T : 1.0;
@@ -998,7 +1011,7 @@ struct Solver {
     }
   }
   // lane -> task tables of the sweep (every thread fills a few words; depends on the sizes only)
-  OB_HD void fill_tables(int tid) const {
+  OB_COLD void fill_tables(int tid) const {
     const int I6[6] = {0, 1, 2, 5, 6, 7};
     uint32_t* tab = sm.TAB;
     int rows[4], cfs[4];
@@ -1074,25 +1087,42 @@ struct Solver {
       sm.st(sm.PV, a, s) = r;
     }
   }
+  // decode this lane's three tasks (once per sweep)
+  OB_HD void sweep_load(int t, SweepRegs& r) const {
+    const uint32_t* tab = sm.TAB;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t w = (t < 30) ? tab[TW + 4 * t + p] : 0u, f = (t < 29) ? tab[TF + 4 * t + p] : 0u;
+      r.wc[p] = w & 0x7fffu; r.wo[p] = (w >> 16) & 0x7fffu;
+      r.fc[p] = f & 0x7fffu; r.fo[p] = (f >> 16) & 0x7fffu;
+      if (p == 0) r.fs = (f >> 31) & 1u;     // all four operands of a task live in the same array
+    }
+    r.fmeta = (t < 29) ? tab[TFH + t] : 0u;
+    const uint32_t b0 = (t < 27) ? tab[TB + 3 * t] : 0u, b1 = (t < 27) ? tab[TB + 3 * t + 1] : 0u, b2 = (t < 27) ? tab[TB + 3 * t + 2] : 0u;
+    const uint32_t refs[5] = {b0 & 0xffffu, b0 >> 16, b1 & 0xffffu, b1 >> 16, b2 & 0xffffu};
+    r.bs = 0;
+#pragma unroll
+    for (int p = 0; p < 5; ++p) { r.bo[p] = refs[p] & 0x7fffu; r.bs |= ((refs[p] >> 15) & 1u) << p; }
+  }
   // sub-step 1:  W = P_{s+1} At (columns th, T, v, w),  pc = p_{s+1} - P_{s+1} c
-  OB_HD void ric_w(int t, int s) const {
+  OB_HD void ric_w(int t, int s, const SweepRegs& r) const {
     if (t >= 30) return;
-    const uint32_t* w = sm.TAB + TW + 4 * t;
+    const double* B = sm.Z + s;
     double acc = 0.0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc += ld(w[p] & 0xffffu, s) * ld(w[p] >> 16, s);
+    for (int p = 0; p < 4; ++p) acc += B[r.wc[p]] * B[r.wo[p]];
     if (t < 24) sm.RIC[44 + t] = acc;
     else sm.RIC[80 + (t - 24)] = sm.st(sm.PV, t - 24, s + 1) - acc;
   }
   // sub-step 2:  F = H + At^T W (+ dw on the regularised diagonal),  f = mu ra + rb + At^T pc
-  OB_HD void ric_f(int t, int s, double mu, double dw) const {
+  OB_HD void ric_f(int t, int s, double mu, double dw, const SweepRegs& r) const {
     if (t >= 29) return;
-    const uint32_t* w = sm.TAB + TF + 4 * t;
+    const double* B = sm.Z + s;
+    const double* O = sm.Z + (r.fs ? s : 0);
     double acc = 0.0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) acc += ld(w[p] & 0xffffu, s) * ld(w[p] >> 16, s);
-    const uint32_t h = sm.TAB[TFH + t];
-    const int e = h & 255, cls = (h >> 8) & 15, slot = (int)(h >> 12) - 1;
+    for (int p = 0; p < 4; ++p) acc += B[r.fc[p]] * O[r.fo[p]];
+    const int e = r.fmeta & 255, cls = (r.fmeta >> 8) & 15, slot = (int)(r.fmeta >> 12) - 1;
     if (t < 21) {
       acc += sm.st(sm.H, e, s);
       if ((cls == 1 && s >= 1) || cls == 2 || (cls == 3 && s == 0 && free_)) acc += dw;
@@ -1104,25 +1134,25 @@ struct Solver {
     if (slot >= 0) sm.st(sm.K, slot, s) = acc;
   }
   // sub-step 3: eliminate (v, w); cost-to-go of stage s (the feedback gains follow in fwd_prep, lane-parallel)
-  OB_HD void ric_b(int t, int s) const {
+  OB_HD void ric_b(int t, int s, const SweepRegs& r) const {
     if (t >= 27) return;
     Glob& G = *sm.G;
-    const uint32_t* w = sm.TAB + TB + 3 * t;
     const double* F = sm.RIC;
     const double q00 = F[27], q01 = F[34], q11 = F[35];   // (6,6) (7,6) (7,7)
     const double det = q00 * q11 - q01 * q01;
     if (t == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
     const double idet = ob_rcp(det);
     const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
+    double v[5];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) v[p] = sm.Z[r.bo[p] + (((r.bs >> p) & 1u) ? s : 0)];
     if (t < 21) {
-      const double fab = ld(w[0] & 0xffffu, s), fa6 = ld(w[0] >> 16, s), fa7 = ld(w[1] & 0xffffu, s);
-      const double fb6 = ld(w[1] >> 16, s), fb7 = ld(w[2] & 0xffffu, s);
-      sm.st(sm.PM, t, s) = fab - (fa6 * (i00 * fb6 + i01 * fb7) + fa7 * (i01 * fb6 + i11 * fb7));
+      sm.st(sm.PM, t, s) = v[0] - (v[1] * (i00 * v[3] + i01 * v[4]) + v[2] * (i01 * v[3] + i11 * v[4]));
     } else {
       const int a = t - 21;
       const double f6 = F[42], f7 = F[43];
       const double kap0 = i00 * f6 + i01 * f7, kap1 = i01 * f6 + i11 * f7;
-      sm.st(sm.PV, a, s) = ld(w[1] & 0xffffu, s) - ld(w[0] & 0xffffu, s) * kap0 - ld(w[0] >> 16, s) * kap1;
+      sm.st(sm.PV, a, s) = v[2] - v[0] * kap0 - v[1] * kap1;
     }
   }
   OB_HD void ric_finish(int t) const {
@@ -1520,7 +1550,7 @@ struct Solver {
   // when that trust was misplaced (rarer).  Layout: block registers [element][thread] | stage arrays | scalars.
   // ------------------------------------------------------------------------------------------------
   OB_HD static int wd_doubles(int T, int S1) { return (6 * EMAX + 6) * T + 32 * S1 + 16; }
-  OB_HD void wd_save(int tid, const BlockRegs<EMAX>& br, double* buf) const {
+  OB_COLD void wd_save(int tid, const BlockRegs<EMAX>& br, double* buf) const {
     const Glob& G = *sm.G;
     const int T = sm.T;
     int e = 0;
@@ -1538,7 +1568,7 @@ struct Solver {
       for (int j = 0; j < 3; ++j) { g[5 + j] = G.Stm[j]; g[8 + j] = G.Ztm[j]; g[11 + j] = G.yt[j]; }
     }
   }
-  OB_HD void wd_restore(int tid, BlockRegs<EMAX>& br, const double* buf) const {
+  OB_COLD void wd_restore(int tid, BlockRegs<EMAX>& br, const double* buf) const {
     Glob& G = *sm.G;
     const int T = sm.T;
     int e = 0;
@@ -1560,7 +1590,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // results -> HBM, once:  x [B,N+1,3]  u [B,N,2]  lam [B,N+1,R]  mu [B,N+1,4 no]  T  obj  status  iters
   // ------------------------------------------------------------------------------------------------
-  OB_HD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
+  OB_COLD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
     const Glob& G = *sm.G;
     const int R = sm.R;
     if (is_stage(tid)) {
@@ -1598,8 +1628,7 @@ struct Solver {
 //   reduce<S0,NS,M0,NM,N0,NN>(scratch)  one block reduction over the threads' part[] slots: sum of slots S0..S0+NS-1,
 //                     max of M0.., min of N0.. (results in ex.red[] at the same slots)
 //   all(f)            run f(tid) on every thread of the block, then a block barrier (no per-thread state)
-//   sweep(f)          run f(t) for t < 64 (first two warps) closed by a barrier among those 64 threads;
-//   sweep_end()       block barrier that opens / closes a run of sweep() calls
+//   sweep(f)          like stage(f) with the lane's SweepRegs: f(lane, SweepRegs&)
 //   stage(f)          run f(lane) on the 32 lanes of the stage warp, then a warp barrier (no block barrier)
 //   stage_end()       block barrier closing a run of stage() calls
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
@@ -1703,11 +1732,11 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     for (;;) {
       ex.once([&]() { G.bad = 0; });
       ex.stage_end();
-      ex.stage([&](int t) { S.ric_terminal(t, mu, dw, dc); });
+      ex.sweep([&](int t, SweepRegs& sr) { S.sweep_load(t, sr); S.ric_terminal(t, mu, dw, dc); });
       for (int s = N - 1; s >= 0; --s) {
-        ex.stage([&](int t) { S.ric_w(t, s); });
-        ex.stage([&](int t) { S.ric_f(t, s, mu, dw); });
-        ex.stage([&](int t) { S.ric_b(t, s); });
+        ex.sweep([&](int t, SweepRegs& sr) { S.ric_w(t, s, sr); });
+        ex.sweep([&](int t, SweepRegs& sr) { S.ric_f(t, s, mu, dw, sr); });
+        ex.sweep([&](int t, SweepRegs& sr) { S.ric_b(t, s, sr); });
       }
       ex.stage([&](int t) { S.ric_finish(t); });
       ex.stage_end();
