@@ -13,7 +13,7 @@ from . import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(CSRC, "libobca_b200.so")
+LIB = os.environ.get("OBCA_B200_LIB") or os.path.join(CSRC, "libobca_b200.so")   # env override: developer builds
 SOURCES = ["obca_b200.cu"]
 HEADERS = ["obca_cta.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,6 +21,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def _stale():
+    if os.environ.get("OBCA_B200_LIB"):
+        return False
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)

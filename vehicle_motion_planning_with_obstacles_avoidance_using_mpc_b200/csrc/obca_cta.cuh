@@ -27,10 +27,8 @@
 
 #if defined(__CUDACC__)
 #define OB_HD __host__ __device__ __forceinline__
-#define OB_COLD __host__ __device__ __noinline__   // once-per-instance / rare paths: kept out of the iteration body
 #else
 #define OB_HD inline
-#define OB_COLD inline
 #endif
 
 namespace obca {
@@ -59,6 +57,10 @@ struct Glob {
   double Tmax, x0[3], u0[2], term[3];
   double Ts, off, g[4];
   double fth[FILT_MAX], fph[FILT_MAX];
+  // loop-carried control state that is read rarely: kept here instead of in every thread's registers (the iteration
+  // body is register-bound).  Written by one thread, read by all after a block barrier.
+  double c_best_E0, c_best_f, c_thmax, c_thmin, c_dw_last;
+  double c_wd_th, c_wd_ph, c_wd_dphi, c_wd_alpha, c_wd_pw_th, c_wd_pw_dphi;
   int bad;
 };
 
@@ -362,7 +364,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // instance load (all threads): inputs HBM -> shared, once
   // ------------------------------------------------------------------------------------------------
-  OB_COLD void load(int tid, size_t b, bool load_obs) const {
+  OB_HD void load(int tid, size_t b, bool load_obs) const {
     Glob& G = *sm.G;
     const int T = sm.T, R = sm.R;
     for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = kp.xref[b * 3 * S1 + i];
@@ -429,7 +431,7 @@ struct Solver {
     return fmin(fmax(T0, 1.0), fmax(G.Tmax, P.T_min));
   }
   // Pass 2: inputs (stage lanes) and duals (block threads)
-  OB_COLD void start_b(int tid, BlockRegs<EMAX>& br, double T0) const {
+  OB_HD void start_b(int tid, BlockRegs<EMAX>& br, double T0) const {
     Glob& G = *sm.G;
     if (is_stage(tid)) {
       const int k = stage_lane(tid);
@@ -553,7 +555,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // slack / multiplier initialisation: S = max(d(x0), bound_push), Z = 1
   // ------------------------------------------------------------------------------------------------
-  OB_COLD void init_slacks(int tid, BlockRegs<EMAX>& br) const {
+  OB_HD void init_slacks(int tid, BlockRegs<EMAX>& br) const {
     Glob& G = *sm.G;
     const double bp = P.bound_push;
     const double T = free_ ? G.T : 1.0;
@@ -1011,7 +1013,7 @@ struct Solver {
     }
   }
   // lane -> task tables of the sweep (every thread fills a few words; depends on the sizes only)
-  OB_COLD void fill_tables(int tid) const {
+  OB_HD void fill_tables(int tid) const {
     const int I6[6] = {0, 1, 2, 5, 6, 7};
     uint32_t* tab = sm.TAB;
     int rows[4], cfs[4];
@@ -1550,7 +1552,7 @@ struct Solver {
   // when that trust was misplaced (rarer).  Layout: block registers [element][thread] | stage arrays | scalars.
   // ------------------------------------------------------------------------------------------------
   OB_HD static int wd_doubles(int T, int S1) { return (6 * EMAX + 6) * T + 32 * S1 + 16; }
-  OB_COLD void wd_save(int tid, const BlockRegs<EMAX>& br, double* buf) const {
+  OB_HD void wd_save(int tid, const BlockRegs<EMAX>& br, double* buf) const {
     const Glob& G = *sm.G;
     const int T = sm.T;
     int e = 0;
@@ -1568,7 +1570,7 @@ struct Solver {
       for (int j = 0; j < 3; ++j) { g[5 + j] = G.Stm[j]; g[8 + j] = G.Ztm[j]; g[11 + j] = G.yt[j]; }
     }
   }
-  OB_COLD void wd_restore(int tid, BlockRegs<EMAX>& br, const double* buf) const {
+  OB_HD void wd_restore(int tid, BlockRegs<EMAX>& br, const double* buf) const {
     Glob& G = *sm.G;
     const int T = sm.T;
     int e = 0;
@@ -1590,7 +1592,7 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // results -> HBM, once:  x [B,N+1,3]  u [B,N,2]  lam [B,N+1,R]  mu [B,N+1,4 no]  T  obj  status  iters
   // ------------------------------------------------------------------------------------------------
-  OB_COLD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
+  OB_HD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
     const Glob& G = *sm.G;
     const int R = sm.R;
     if (is_stage(tid)) {
@@ -1664,16 +1666,15 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   double mu = P.mu_init;
   int f_n = 0, f_wr = 0;
   bool f_active = false;
-  double thmax = 0, thmin = 0;
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
-  double dw_last = 0.0, E0 = 0.0, fcur = 0.0, best_E0 = 1e300, best_f = 0.0;
+  double E0 = 0.0, fcur = 0.0;
+  ex.once([&]() { G.c_best_E0 = 1e300; G.c_best_f = 0.0; G.c_dw_last = 0.0; });   // visible after the barriers of the start phase
   // watchdog (IPOPT: watchdog_shortened_iter_trigger = 10, watchdog_trial_iter_max = 3): after 10 consecutive shortened
   // steps a rejected full step is taken on trust from a checkpointed reference iterate; if 3 further full steps reach no
   // point acceptable to the reference, the reference is restored and ordinary backtracking resumes there.  This is what
   // ends the Maratos-type crawl (hundreds of 2^-9 steps) that otherwise dominates the tail of a batch.
   const int WD_TRIGGER = 10, WD_MAX = 3;
   int in_wd = 0, wd_count = 0, wd_block = 0, n_short = 0;
-  double wd_th = 0, wd_ph = 0, wd_dphi = 0, wd_alpha = 1, wd_pw_th = 0, wd_pw_dphi = 0;
 
   ex.tick(0);
   for (;;) {
@@ -1701,9 +1702,9 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     if (E0 <= P.acceptable_tol) {
       // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails
       // later on.  The store goes straight to the result arrays: no on-chip copy is kept.
-      if (E0 < 0.1 * best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
-        best_E0 = E0; best_f = Ef;
+      if (E0 < 0.1 * G.c_best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
         ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
+        ex.once([&]() { G.c_best_E0 = E0; G.c_best_f = Ef; });   // after the barrier: everyone has evaluated the test
       }
       if (++acc_count >= P.acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
@@ -1728,6 +1729,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     ex.tick(4);
     // ---- Riccati with inertia correction: the pivots are the inertia test
     double dw = 0.0;
+    const double dw_last = G.c_dw_last;
     bool regfail = false;
     for (;;) {
       ex.once([&]() { G.bad = 0; });
@@ -1747,7 +1749,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       ex.stage_end();   // everyone has read G.bad before it is cleared again
     }
     if (regfail) { status = OBCA_ST_REGFAIL; break; }
-    if (dw > 0) dw_last = dw;
+    if (dw > 0) ex.once([&]() { G.c_dw_last = dw; });   // read again only after the barriers of the roll-out
     ex.tick(5);
     // ---- roll-out
     ex.stage([&](int lane) { if (lane <= N) S.fwd_prep(lane); });
@@ -1765,9 +1767,13 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     ex.template reduce<QS_DPHI, 1, 0, 0, QN_AMAX, 2>(S.sm.SCR_H);
     ex.tick(8);
     const double Dphi = ex.red[QS_DPHI], a_max = ex.red[QN_AMAX], a_z = ex.red[QN_AZ];
+    double thmax, thmin;
     if (!f_active) {
       thmax = 1e4 * fmax(1.0, th); thmin = 1e-4 * fmax(1.0, th);
+      ex.once([&]() { G.c_thmax = thmax; G.c_thmin = thmin; });
       f_active = true; f_n = 0; f_wr = 0;
+    } else {
+      thmax = G.c_thmax; thmin = G.c_thmin;
     }
     // the two powers of the switching condition are loop invariants of the line search
     const double pw_th = (th > 0) ? pow(th, s_th) : 0.0, pw_dphi = (Dphi < 0) ? pow(-Dphi, s_ph) : 0.0;
@@ -1802,7 +1808,8 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       const double tht = ex.red[1], pht = ex.red[0] - mu * ex.red[2];
       if (in_wd) {
         // watchdog: only full steps, judged against the reference iterate
-        accepted = accept_test(tht, pht, wd_th, wd_ph, wd_dphi, wd_alpha, wd_pw_th, wd_pw_dphi);
+        const double wd_th = G.c_wd_th, wd_ph = G.c_wd_ph;
+        accepted = accept_test(tht, pht, wd_th, wd_ph, G.c_wd_dphi, G.c_wd_alpha, G.c_wd_pw_th, G.c_wd_pw_dphi);
         if (accepted) {
           in_wd = 0;
           if (accepted == 1) {   // the reference point enters the filter
@@ -1822,7 +1829,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       if (accepted) break;
       if (first && !wd_block && n_short >= WD_TRIGGER && isfinite(pht)) {
         ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_save(tid, br, wd_buf); });
-        wd_th = th; wd_ph = ph0; wd_dphi = Dphi; wd_alpha = a; wd_pw_th = pw_th; wd_pw_dphi = pw_dphi;
+        ex.once([&]() { G.c_wd_th = th; G.c_wd_ph = ph0; G.c_wd_dphi = Dphi; G.c_wd_alpha = a; G.c_wd_pw_th = pw_th; G.c_wd_pw_dphi = pw_dphi; });
         in_wd = 1; wd_count = 0; accepted = 3;
         break;
       }
@@ -1851,10 +1858,10 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   }
   ex.tick(13);
   iters_out = iter;
-  if (status < 0 && best_E0 < 1e300) {
+  if (status < 0 && G.c_best_E0 < 1e300) {
     // x, u, lam, mu, T of the stored acceptable point are already in the result arrays
     ex.once([&]() { S.kp.status[inst] = OBCA_ST_ACCEPTABLE; S.kp.iters[inst] = iter; });
-    obj_out = best_f;
+    obj_out = G.c_best_f;
     return OBCA_ST_STORED;
   }
   obj_out = fcur;
