@@ -221,6 +221,10 @@ static int sm_count_of(int device) {
 // compile-time sizes
 static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
   if (emax <= 4 && N == 20 && no == 4 && R == 16) return obca::obca_solve_kernel<4, 128, 3, 20, 4, 16>;   // cfg 3 (headline)
+  if (emax <= 4 && N == 20 && no == 6 && R == 24) return obca::obca_solve_kernel<4, 192, 2, 20, 6, 24>;   // cfg 5
+  if (emax <= 4 && N == 10 && no == 2 && R == 8) return obca::obca_solve_kernel<4, 128, 3, 10, 2, 8>;     // cfg 2
+  if (emax <= 4 && N == 5 && no == 6 && R == 18) return obca::obca_solve_kernel<4, 128, 3, 5, 6, 18>;     // cfg 4, detected obstacle
+  if (emax <= 4 && N == 5 && no == 5 && R == 14) return obca::obca_solve_kernel<4, 128, 3, 5, 5, 14>;     // cfg 4, free phase
   if (emax <= 4) {
     if (threads <= 128) return obca::obca_solve_kernel<4, 128, 3>;
     if (threads <= 192) return obca::obca_solve_kernel<4, 192, 2>;
