@@ -22,8 +22,9 @@ Algorithm (IPOPT-flavoured, Waechter & Biegler 2006):
   backtracking resumes there.  (The optional second-order correction, soc=True, is not part of the specification the
   C oracle and the CUDA kernel implement.)
   monotone barrier update mu <- max(tol/10, min(0.2 mu, mu^1.5)) when E_mu <= 10 mu;
-  stop when IPOPT's scaled optimality error E_0 <= tol (1e-8); the best iterate with E_0 <= acceptable_tol is
-  stored and becomes the result ("Solved To Acceptable Level") if the run later ends in a failure.
+  stop when IPOPT's scaled optimality error E_0 <= tol (1e-8); the best iterate at the acceptable level (E_0 <=
+  acceptable_tol, or - at the final mu - theta <= 1e-6 and E_0 <= 1e-3) is stored and becomes the result ("Solved To
+  Acceptable Level") if the run later ends in a failure or stalls there (error not halved for 10 iterations).
 """
 from __future__ import annotations
 
@@ -37,7 +38,7 @@ DEFAULT_OPTS = dict(tol=1e-8, max_iter=3000, mu_init=10.0, kappa_eps=10.0, kappa
                     dw_first=1e-4, dw_min=1e-20, dw_max=1e20, kw_plus_first=100.0, kw_plus=8.0, kw_minus=1.0 / 3.0,
                     dc_min=1e-8, lm_cap=1e4, acceptable_tol=1e-6, acceptable_iter=15, filt_max=32,
                     stall_alpha=1e-3, stall_iters=10, sig_min=1e-8,
-                    wd_trigger=10, wd_max=3,
+                    wd_trigger=10, wd_max=3, acc_stall=10,
                     init="warm", verbose=False, soc=False, dbg=False)
 
 # status codes (shared with oracle/obca_oracle.c and the CUDA kernel)
@@ -103,6 +104,7 @@ def solve(p: nlp.Problem, opts=None):
     tol = o["tol"]
     acc_count = 0
     best = None
+    e_min, e_min_iter = 1e300, 0
     status = ST_MAXITER
     in_wd = False; wd_count = 0; wd_block = False; n_short = 0
     wd_ref = None; wd_state = None
@@ -132,15 +134,24 @@ def solve(p: nlp.Problem, opts=None):
         if E0 <= tol:
             status = 0
             break
-        if E0 <= o["acceptable_tol"]:
+        acc_lvl = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
+        if acc_lvl:
             if best is None or E0 < 0.1 * best[0]:  # IPOPT stores the acceptable point (here: a new copy per decade) ...
                 best = (E0, X.copy(), S.copy(), y.copy(), Z.copy())
+            if E0 < 0.5 * e_min:
+                e_min, e_min_iter = E0, it
+        if E0 <= o["acceptable_tol"]:
             acc_count += 1
             if acc_count >= o["acceptable_iter"]:
                 status = 1
                 break
         else:
             acc_count = 0
+        # stall at the acceptable level (final barrier parameter, error not halved for acc_stall iterations): end with
+        # the stored point, as IPOPT does when it cannot progress from an acceptable point
+        if best is not None and mu <= tol / 10 * (1 + 1e-12) and it - e_min_iter >= o["acc_stall"]:
+            status = ST_LSFAIL
+            break
         if it >= o["max_iter"]:
             status = ST_MAXITER
             break

@@ -765,6 +765,8 @@ typedef struct {
 
 typedef void (*trace_fn)(int it, double f, double th, double E0, double mu, double dw, double alpha);
 static trace_fn g_trace = 0;
+static int g_acc_stall = 10;                  /* iterations without halving the error at the acceptable level */
+void obca_oracle_set_acc_stall(int n) { g_acc_stall = n; }
 static int g_wd_trigger = 10, g_wd_max = 3;   /* watchdog: shortened steps before it starts / full steps on trust */
 void obca_oracle_set_watchdog(int trigger, int max_trust) { g_wd_trigger = trigger; g_wd_max = max_trust; }
 void obca_oracle_set_trace(trace_fn fn) { g_trace = fn; }
@@ -816,7 +818,8 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   filt_t F;
   memset(&F, 0, sizeof(F));
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
-  double dw_last = 0.0, E0 = 0, best_E0 = 1e300;
+  double dw_last = 0.0, E0 = 0, best_E0 = 1e300, e_min = 1e300;
+  int e_min_iter = 0;
   /* watchdog (Chamberlain et al.; IPOPT's watchdog, triggered earlier): after WD_TRIGGER consecutive shortened steps a
    * rejected full step is taken anyway from a saved reference iterate; if within WD_MAX further full steps no point
    * acceptable to the reference is reached, the reference is restored and ordinary backtracking resumes there */
@@ -867,13 +870,24 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     double sd = fmax(s_max, (sumy + sumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, sumz / q_in) / s_max;
     E0 = fmax(fmax(e1 / sd, e2), szmax / sc);
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
-    if (E0 <= P->acceptable_tol) {
+    /* acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
+     * complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of
+     * the OBCA dual polytope; same condition as at_floor below) */
+    const int acc_lvl = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
+    if (acc_lvl) {
       /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
        * ("Solved To Acceptable Level") */
       if (E0 < 0.1 * best_E0) { best_E0 = E0; w->best = *it; }   /* a new copy per decade of improvement */
+      if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
+    }
+    if (E0 <= P->acceptable_tol) {
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
       acc_count = 0;
+    /* stall at the acceptable level: an acceptable point is stored, the barrier parameter is final and the error has
+     * not halved for ACC_STALL iterations - the iterate is wandering on the noise floor (objective constant to 10
+     * digits).  End like IPOPT does when it cannot progress from an acceptable point: with the stored point. */
+    if (best_E0 < 1e300 && mu <= tol / 10 * (1 + 1e-12) && iter - e_min_iter >= g_acc_stall) { status = OBCA_ST_LSFAIL; break; }
     if (iter >= P->max_iter) { status = OBCA_ST_MAXITER; break; }
     /* barrier update */
     int changed = 0;

@@ -95,3 +95,18 @@ def test_watchdog_instances():
     assert (c["status"] == 0).all() and (e["status"] == 0).all()
     assert np.array_equal(c["iters"], e["iters"]) and c["iters"].max() <= 40
     assert np.abs(c["x"] - e["x"]).max() <= 1e-9 and np.abs(c["obj"] - e["obj"]).max() <= 1e-8
+
+
+def test_stall_at_acceptable_level():
+    """instances that wander on the noise floor (E0 1e-6..1e-4, objective constant) for 60-80 iterations without the
+    stall rule: they end 10 iterations after their best acceptable point, kernel code == oracle"""
+    b = sc.make_batch(3, 8192)
+    prm, a = common.batch_arrays(b)
+    idx = np.array([7483, 3525, 1237])
+    sub = {k: (v[idx] if (v is not None and k in ("x0", "u0", "xref", "T_max")) else v) for k, v in a.items()}
+    c = _oracle(prm, sub); e = common.emu_solve(prm, sub)
+    # on the noise floor the two implementations take different (chaotic) paths; both must end soon after their best
+    # acceptable point, with the same answer to well within the parity tolerances
+    assert (c["status"] == 1).all() and (e["status"] == 1).all()
+    assert c["iters"].max() <= 55 and e["iters"].max() <= 55
+    assert np.abs(c["x"] - e["x"]).max() <= 1e-6 and (np.abs(c["obj"] - e["obj"]) <= 1e-8 * np.abs(c["obj"])).all()
