@@ -48,7 +48,8 @@ def bytes_per_solve(N, n_obs, rows, free=True, n_dyn_rows=0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md): one streaming
+    `nvidia-smi -lms 100` process, lines stamped on arrival; summary over the samples inside [mark_start, mark_stop]."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -56,24 +57,34 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._halt = threading.Event()
+        self.t0 = self.t1 = None
+        self.proc = None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in o.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.strip().split(",")]))
+        except Exception:
+            pass
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._halt.set()
+        time.sleep(0.15)                       # let the last in-window sample arrive
+        if self.proc is not None:
+            self.proc.terminate()
         self.join(timeout=6)
+        t0 = self.t0 or 0.0; t1 = (self.t1 or time.time()) + 0.12
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
         sm = []; mx = 0.0; reasons = set(); pw = 0.0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1])); pw = max(pw, float(r[2]))
                 for n, v in zip(names, r[3:7]):
@@ -179,16 +190,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                    # streaming nvidia-smi needs a moment to come up: start before the warm-up
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
     l0 = solver.launches
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kernel_ms = []
     barrier()
+    if sampler:
+        sampler.mark_start()
     w0 = time.perf_counter()
     for e0, e1 in evs:
         flush.zero_()                      # L2 flush, outside the timed events
@@ -199,6 +212,8 @@ def main():
         kernel_ms.append(solver.last_kernel_ms())
     barrier()
     wall = time.perf_counter() - w0
+    if sampler:
+        sampler.mark_stop()
     launches = solver.launches - l0
     step_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)        # this rank, all K steps
     tt = torch.tensor([step_ms, sum(kernel_ms)], dtype=torch.float64, device=dev)
