@@ -107,6 +107,25 @@ int64_t obca_b200_launch_count(const obca_ctx* ctx);
 float obca_b200_last_kernel_ms(obca_ctx* ctx);
 const char* obca_b200_strerror(int rc);
 
+/* ---- host planner: the callers' side of the solve, batched on the host cores ----------------
+ * obca_b200_astar_batch replaces a_star.solve + rebuild_path + create_reference_path (src/a_star.py:39-102, 137-147,
+ * 189-200; called through closedLoop.update_path, src/closed_loop.py:555-563) for n independent queries, with the
+ * reference's neighbour order, cost, heap tie-breaking and stale-entry rules, so the routes are the same cell for
+ * cell.  HOST pointers.
+ *   grids [n_grids,H,W] uint8, 1 = occupied     grid_index [n] or NULL (every query uses grid 0)
+ *   start_rc, goal_rc [n,2] int32 (row, col)    ref [n,max_len,3] (x, y, yaw)
+ *   ref_len [n]: number of path points (the start cell is excluded, as in the reference); 0 = no route or fewer
+ *           than two points; -len if max_len was too small (the call then returns OBCA_E_SIZE)
+ *   n_threads <= 0: all hardware threads                                                                          */
+int  obca_b200_astar_batch(int n, const uint8_t* grids, int n_grids, int H, int W, const int32_t* grid_index,
+                           const int32_t* start_rc, const int32_t* goal_rc, int max_len, double* ref,
+                           int32_t* ref_len, int n_threads);
+/* closedLoop.update_reference_trajectory (src/closed_loop.py:502-528) for n poses: window of N+1 path points from
+ * the first closest one, clamped to the last.  path_index [n] or NULL (pose q uses path q).  HOST pointers.
+ *   ref [n_paths,max_len,3]  ref_len [n_paths]  x0 [n,3]  xref [n,N+1,3]                                          */
+int  obca_b200_reference_windows(int n, const double* ref, const int32_t* ref_len, int max_len,
+                                 const int32_t* path_index, const double* x0, int N, double* xref);
+
 #ifdef __cplusplus
 }
 #endif

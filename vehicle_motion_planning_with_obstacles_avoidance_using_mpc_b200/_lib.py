@@ -14,10 +14,10 @@ from . import _abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("OBCA_B200_LIB") or os.path.join(CSRC, "libobca_b200.so")   # env override: developer builds
-SOURCES = ["obca_b200.cu"]
+SOURCES = ["obca_b200.cu", "obca_planner.cpp"]
 HEADERS = ["obca_cta.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC,-pthread"]
 
 
 def _stale():
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
 _lib = None
 EXPORTS = ["obca_b200_abi_version", "obca_b200_create", "obca_b200_destroy", "obca_b200_scratch_bytes",
            "obca_b200_solve", "obca_b200_solve_host", "obca_b200_launch_count", "obca_b200_last_kernel_ms",
-           "obca_b200_strerror"]
+           "obca_b200_strerror", "obca_b200_astar_batch", "obca_b200_reference_windows"]
 
 
 def lib():
@@ -75,6 +75,11 @@ def lib():
     L.obca_b200_solve.argtypes = [vp, C.c_int] + [vp] * 7 + [C.POINTER(C.c_int32)] + [vp] * 3 + [C.c_int] + [vp] * 8 + [vp]
     L.obca_b200_solve_host.restype = C.c_int
     L.obca_b200_solve_host.argtypes = [vp] + _abi.SOLVE_ARGTYPES_HOST
+    ip = C.POINTER(C.c_int32)
+    L.obca_b200_astar_batch.restype = C.c_int
+    L.obca_b200_astar_batch.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, vp, ip, C.c_int]
+    L.obca_b200_reference_windows.restype = C.c_int
+    L.obca_b200_reference_windows.argtypes = [C.c_int, vp, ip, C.c_int, ip, vp, C.c_int, vp]
     if L.obca_b200_abi_version() != 2:
         raise RuntimeError("libobca_b200.so ABI version mismatch")
     _lib = L

@@ -122,3 +122,47 @@ def plan_reference(grid, start_pose, goal_pose):
     if route is False or len(route) < 2:
         return None
     return np.asarray(pl.create_reference_path(pl.rebuild_path(route)), float).T
+
+
+def plan_batch(grids, starts, goals, grid_index=None, max_len=None, threads=0):
+    """Many ``plan_reference`` queries at once through the native planner (``obca_b200_astar_batch``,
+    include/obca_b200.h): same routes as ``a_star.solve`` cell for cell, on all host cores.
+
+    ``grids`` (H,W) or (G,H,W) occupancy (1 = occupied); ``starts``/``goals`` (n,3) poses ``[x, y, yaw]`` (or one
+    goal for all); ``grid_index`` (n,) picks the grid of each query.  Returns ``ref`` (n, max_len, 3) and ``ref_len``
+    (n,), 0 where ``plan_reference`` would return None."""
+    import ctypes as C
+    from . import _lib
+    g = np.asarray(grids)
+    if g.ndim == 2:
+        g = g[None]
+    occ = np.ascontiguousarray(g == 1, dtype=np.uint8)
+    G, H, W = occ.shape
+    starts = np.atleast_2d(np.asarray(starts, float)); n = starts.shape[0]
+    goals = np.broadcast_to(np.atleast_2d(np.asarray(goals, float)), (n, np.atleast_2d(goals).shape[1]))
+    s_rc = np.ascontiguousarray(np.stack([starts[:, 1], starts[:, 0]], 1).astype(np.int32))
+    g_rc = np.ascontiguousarray(np.stack([goals[:, 1], goals[:, 0]], 1).astype(np.int32))
+    gi = None if grid_index is None else np.ascontiguousarray(grid_index, dtype=np.int32)
+    max_len = int(max_len or H * W)
+    ref = np.zeros((n, max_len, 3)); ref_len = np.zeros(n, np.int32)
+    ip = C.POINTER(C.c_int32)
+    _lib.check(_lib.lib().obca_b200_astar_batch(
+        n, occ.ctypes.data, G, H, W, None if gi is None else gi.ctypes.data_as(ip), s_rc.ctypes.data_as(ip),
+        g_rc.ctypes.data_as(ip), max_len, ref.ctypes.data, ref_len.ctypes.data_as(ip), int(threads)))
+    return ref, ref_len
+
+
+def reference_windows(ref, ref_len, x0, N, path_index=None):
+    """``update_reference_trajectory`` (closed_loop.py:502-528) for n poses: (n, N+1, 3) windows
+    (``obca_b200_reference_windows``)."""
+    import ctypes as C
+    from . import _lib
+    ref = np.ascontiguousarray(ref, float); ref_len = np.ascontiguousarray(ref_len, np.int32)
+    x0 = np.ascontiguousarray(np.atleast_2d(x0), float); n = x0.shape[0]
+    pi = None if path_index is None else np.ascontiguousarray(path_index, dtype=np.int32)
+    out = np.empty((n, N + 1, 3))
+    ip = C.POINTER(C.c_int32)
+    _lib.check(_lib.lib().obca_b200_reference_windows(
+        n, ref.ctypes.data, ref_len.ctypes.data_as(ip), ref.shape[1], None if pi is None else pi.ctypes.data_as(ip),
+        x0.ctypes.data, int(N), out.ctypes.data))
+    return out

@@ -12,7 +12,7 @@ import dataclasses
 import numpy as np
 
 from . import model_obstacle as mo
-from .a_star import plan_reference
+from .a_star import plan_batch, plan_reference
 
 # closed_loop.py:32-104
 TS = 0.1
@@ -155,15 +155,15 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_se
     # free start cells with clearance; A* once per distinct cell
     cells = [(cx, cy) for cx in range(1, 36) for cy in range(1, 10)
              if grid[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3].sum() == 0]
-    paths = {}
+    # one native batched A* call for every candidate cell (identical to plan_reference per cell)
+    pref, plen_ = plan_batch(grid, [[cx, cy, 0] for cx, cy in cells], [goal])
+    paths = {c: (pref[j, :plen_[j]].T.copy() if plen_[j] > 0 else None) for j, c in enumerate(cells)}
     x0 = np.zeros((B, 3)); xref = np.zeros((B, 3, N + 1))
     n = 0
     static_polys = polys[:nq]
     while n < B:
         cx, cy = cells[rng.integers(len(cells))]
         th0 = rng.uniform(-np.pi / 4, np.pi / 4)
-        if (cx, cy) not in paths:
-            paths[(cx, cy)] = plan_reference(grid, (cx, cy, 0), goal)
         ref = paths[(cx, cy)]
         if ref is None or ref.shape[1] < 3:
             continue
