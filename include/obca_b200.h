@@ -91,6 +91,18 @@ int  obca_b200_solve  (obca_ctx* ctx, int batch,
                        int obstacles_shared,
                        double* x, double* u, double* lam, double* mu, double* T, double* obj,
                        int32_t* status, int32_t* iters, void* cuda_stream);
+/* obca_b200_solve over a work list that lives on the device: work item w (0 <= w < *count_dev) solves instance
+ * index_dev[w]; every per-instance array is indexed by the INSTANCE number, so callers keep one set of arrays for all
+ * instances and hand each solver mode the list of those it should solve (the receding-horizon loop below: FREE /
+ * FIXED_SET / FIXED_NOTERM subsets of one scenario batch, closed_loop.py:382-395) without a host round trip.
+ * `batch` bounds *count_dev and the instance numbers (<= max_batch).  count_dev / index_dev NULL => obca_b200_solve. */
+int  obca_b200_solve_indexed(obca_ctx* ctx, int batch, const int32_t* count_dev, const int32_t* index_dev,
+                       const double* x0, const double* u0, const double* xref, const double* uref,
+                       const double* T_max, const double* term, const double* Ts_inst,
+                       const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
+                       int obstacles_shared,
+                       double* x, double* u, double* lam, double* mu, double* T, double* obj,
+                       int32_t* status, int32_t* iters, void* cuda_stream);
 /* Same call with HOST pointers: stages inputs to the device, solves, copies the results back and
  * synchronises.  This is what the single-problem Python methods (obca.obca_mpc4 ...) use. */
 int  obca_b200_solve_host(obca_ctx* ctx, int batch,
@@ -125,6 +137,55 @@ int  obca_b200_astar_batch(int n, const uint8_t* grids, int n_grids, int H, int 
  *   ref [n_paths,max_len,3]  ref_len [n_paths]  x0 [n,3]  xref [n,N+1,3]                                          */
 int  obca_b200_reference_windows(int n, const double* ref, const int32_t* ref_len, int max_len,
                                  const int32_t* path_index, const double* x0, int N, double* xref);
+
+/* ---- device-side input builder ----------------------------------------------------------------
+ * Half-space rows from raw vertices: obstacleModel.obstacle_H_Represent (src/model_obstacle.py:37-102; same branch
+ * rules, rows not normalised) for the first time block, and the per-step increment db that replaces the N+1
+ * translated copies of problemSetting.rebuild_lObs (src/demo_setting.py:457-473):  b_k = b0 + k*db,
+ * db = (Ts*speed) * (A . (cos, sin)).  DEVICE pointers except edge_ptr; asynchronous on the stream.
+ *   edge_ptr [n_obs+1] host      verts [B, rows + n_obs, 2]: polygon i = its E_i + 1 vertices (clockwise, as the
+ *   reference lists them), polygons back to back      vel [B,n_obs,3] = speed, cos(heading), sin(heading) or NULL
+ *   Ts_inst [B] or NULL (=> ts)   A [B,rows,2]  b0 [B,rows]  db [B,rows] or NULL                                   */
+int  obca_b200_build_rows(int batch, int n_obs, const int32_t* edge_ptr, const double* verts, const double* vel,
+                          const double* Ts_inst, double ts, double* A, double* b0, double* db, void* cuda_stream);
+
+/* ---- device-resident receding-horizon loop -----------------------------------------------------
+ * closedLoop.closed_loop_mpc4 (src/closed_loop.py:323-441) for n_scenarios Monte-Carlo scenarios in lock-step: they
+ * share the static map, the A* path, start and goal; each has one moving rectangle.  Per step, on the device: goal test,
+ * update_obstacle (445-486), sensor (591-630), update_reference_trajectory (502-528), terminal set (371), obstacle
+ * rows, then obca_mpc4 on the scenarios that see nothing, obca_mpc6 on those that do, obca_mpc8 on its failures
+ * (382-395), then the first input is applied (416-419).  No host synchronisation between reset and read. */
+typedef struct {
+  int32_t N;               /* horizon of both phases (closed_loop.py:84,87 with N_free == N_fix)                      */
+  int32_t max_steps;       /* 30 (closed_loop.py:341)                                                                 */
+  int32_t n_static;        /* static obstacles; the moving one is appended after them (demo_setting.py:445-452)       */
+  int32_t rows_static;     /* their half-space rows                                                                   */
+  int32_t path_len;        /* points of the reference path                                                            */
+  int32_t terminal_rule;   /* 0: [x0.x+5, inf) x [1, 9] (closed_loop.py:371); 1: [5, inf) x [x0.y+4, 60] (simulation.py:72) */
+  double  sense;           /* lidar range (senseDis, demo_setting.py:70)                                              */
+  double  goal[2];
+  double  goal_tol;        /* stop when the squared distance to the goal is below this: 0.1 (closed_loop.py:343)      */
+  double  start[3];
+  double  Ts0;             /* sampling time before the first free-time solve: 0.1                                     */
+} obca_loop_params;
+typedef struct obca_loop obca_loop;
+/* p_free / p_set / p_noterm: solver parameters of the three modes (n_obs = n_static, n_static+1, n_static+1).
+ * HOST pointers: edges_static [n_static], A_static [rows_static,2], b_static [rows_static], path [path_len,3]. */
+int  obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const obca_loop_params* lp,
+                           const obca_params* p_free, const obca_params* p_set, const obca_params* p_noterm,
+                           const int32_t* edges_static, const double* A_static, const double* b_static,
+                           const double* path);
+/* HOST: dyn [B,7] = cx, cy, heading, length, width, speed, first step; heading_cs [B,2] = cos, sin of the heading */
+int  obca_b200_loop_reset(obca_loop* l, const double* dyn, const double* heading_cs, void* cuda_stream);
+/* issue n_steps steps on the stream; asynchronous */
+int  obca_b200_loop_run(obca_loop* l, int n_steps, void* cuda_stream);
+/* copy the logs to HOST buffers (any may be NULL) and synchronise: traj [B,max_steps+1,3] (NaN after the last step
+ * taken), steps [B], failed [B], mode_log [B,max_steps] (OBCA_MODE_* or -1), x [B,3], u [B,2], Ts_opt [B],
+ * solves [3] = FREE / FIXED_SET / FIXED_NOTERM solves since reset */
+int  obca_b200_loop_read(obca_loop* l, double* traj, int32_t* steps, int32_t* failed, int32_t* mode_log, double* x,
+                         double* u, double* Ts_opt, int64_t* solves, void* cuda_stream);
+int64_t obca_b200_loop_launch_count(const obca_loop* l);
+int  obca_b200_loop_destroy(obca_loop* l);
 
 #ifdef __cplusplus
 }

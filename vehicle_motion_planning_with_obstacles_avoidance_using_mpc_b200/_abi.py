@@ -35,6 +35,16 @@ class ObcaParams(C.Structure):
     ]
 
 
+class LoopParams(C.Structure):
+    """obca_loop_params of include/obca_b200.h"""
+    _fields_ = [
+        ("N", C.c_int32), ("max_steps", C.c_int32), ("n_static", C.c_int32), ("rows_static", C.c_int32),
+        ("path_len", C.c_int32), ("terminal_rule", C.c_int32),
+        ("sense", C.c_double), ("goal", C.c_double * 2), ("goal_tol", C.c_double), ("start", C.c_double * 3),
+        ("Ts0", C.c_double),
+    ]
+
+
 def is_free(mode):
     return mode in (MODE_FREE, MODE_FREE_STACKED)
 

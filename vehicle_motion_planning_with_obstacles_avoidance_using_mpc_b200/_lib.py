@@ -14,7 +14,7 @@ from . import _abi
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("OBCA_B200_LIB") or os.path.join(CSRC, "libobca_b200.so")   # env override: developer builds
-SOURCES = ["obca_b200.cu", "obca_planner.cpp"]
+SOURCES = ["obca_b200.cu", "obca_loop.cu", "obca_planner.cpp"]
 HEADERS = ["obca_cta.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC,-pthread"]
@@ -43,7 +43,9 @@ def build(force=False, verbose=False):
 _lib = None
 EXPORTS = ["obca_b200_abi_version", "obca_b200_create", "obca_b200_destroy", "obca_b200_scratch_bytes",
            "obca_b200_solve", "obca_b200_solve_host", "obca_b200_launch_count", "obca_b200_last_kernel_ms",
-           "obca_b200_strerror", "obca_b200_astar_batch", "obca_b200_reference_windows"]
+           "obca_b200_strerror", "obca_b200_astar_batch", "obca_b200_reference_windows",
+           "obca_b200_solve_indexed", "obca_b200_build_rows", "obca_b200_loop_create", "obca_b200_loop_reset",
+           "obca_b200_loop_run", "obca_b200_loop_read", "obca_b200_loop_launch_count", "obca_b200_loop_destroy"]
 
 
 def lib():
@@ -80,6 +82,23 @@ def lib():
     L.obca_b200_astar_batch.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, ip, ip, ip, C.c_int, vp, ip, C.c_int]
     L.obca_b200_reference_windows.restype = C.c_int
     L.obca_b200_reference_windows.argtypes = [C.c_int, vp, ip, C.c_int, ip, vp, C.c_int, vp]
+    L.obca_b200_solve_indexed.restype = C.c_int
+    L.obca_b200_solve_indexed.argtypes = [vp, C.c_int, vp, vp] + [vp] * 7 + [ip] + [vp] * 3 + [C.c_int] + [vp] * 8 + [vp]
+    L.obca_b200_build_rows.restype = C.c_int
+    L.obca_b200_build_rows.argtypes = [C.c_int, C.c_int, ip, vp, vp, vp, C.c_double, vp, vp, vp, vp]
+    pp = C.POINTER(_abi.ObcaParams)
+    L.obca_b200_loop_create.restype = C.c_int
+    L.obca_b200_loop_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(_abi.LoopParams), pp, pp, pp, ip, vp, vp, vp]
+    L.obca_b200_loop_reset.restype = C.c_int
+    L.obca_b200_loop_reset.argtypes = [vp, vp, vp, vp]
+    L.obca_b200_loop_run.restype = C.c_int
+    L.obca_b200_loop_run.argtypes = [vp, C.c_int, vp]
+    L.obca_b200_loop_read.restype = C.c_int
+    L.obca_b200_loop_read.argtypes = [vp] * 10
+    L.obca_b200_loop_launch_count.restype = C.c_int64
+    L.obca_b200_loop_launch_count.argtypes = [vp]
+    L.obca_b200_loop_destroy.restype = C.c_int
+    L.obca_b200_loop_destroy.argtypes = [vp]
     if L.obca_b200_abi_version() != 2:
         raise RuntimeError("libobca_b200.so ABI version mismatch")
     _lib = L

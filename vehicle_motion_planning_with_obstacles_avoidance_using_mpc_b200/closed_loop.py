@@ -406,6 +406,116 @@ class ClosedLoopBatch:
                     launches=self.launches, solves=self.solves)
 
 
+class ClosedLoopDevice(ClosedLoopBatch):
+    """``ClosedLoopBatch`` with the whole receding-horizon loop resident on the GPU (``obca_b200_loop_*`` of
+    include/obca_b200.h): scenario state, input builders, work lists and the three solver modes stay in HBM; the host
+    issues the launches of all steps without waiting and reads the logs once at the end."""
+
+    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM, max_steps=30):
+        super().__init__(setting, dyn, N=N, Q_free=Q_free, sense=sense, device=device, init=init, max_steps=max_steps)
+        self._loop = None
+        self._rule = None
+
+    def _params(self, mode, with_dyn):
+        edges = self.edges_s + ([4] if with_dyn else [])
+        free = _abi.is_free(mode)
+        return _abi.make_params(mode, self.N, len(edges), int(sum(edges)), 0.1, self.Q_free if free else self.Q_fix,
+                                self.Q_free if free else self.Q_fix, self.R_free if free else self.R_fix,
+                                self.s.xL, self.s.xU, self.uL, self.uU, self.dmin, self.ego, init=self.init)
+
+    def _create(self, rule):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        lp = _abi.LoopParams(N=self.N, max_steps=self.max_steps, n_static=len(self.edges_s),
+                             rows_static=int(sum(self.edges_s)), path_len=self.path.shape[1], terminal_rule=rule,
+                             sense=self.sense, goal_tol=0.1, Ts0=0.1)
+        lp.goal[0], lp.goal[1] = float(self.s.goalPose[0]), float(self.s.goalPose[1])
+        for j in range(3):
+            lp.start[j] = float(self.s.startPose[j])
+        pf, ps, pn = (self._params(_abi.MODE_FREE, False), self._params(_abi.MODE_FIXED_SET, True),
+                      self._params(_abi.MODE_FIXED_NOTERM, True))
+        edges = np.asarray(self.edges_s, np.int32)
+        A_s = np.ascontiguousarray(self.A_s, float); b_s = np.ascontiguousarray(self.b_s, float)
+        path = np.ascontiguousarray(self.path.T, float)                                  # (M, 3)
+        h = C.c_void_p()
+        _lib.check(L.obca_b200_loop_create(C.byref(h), self.device, self.B, C.byref(lp), C.byref(pf), C.byref(ps),
+                                           C.byref(pn), edges.ctypes.data_as(C.POINTER(C.c_int32)), A_s.ctypes.data,
+                                           b_s.ctypes.data, path.ctypes.data))
+        self._loop, self._rule = h, rule
+
+    def close(self):
+        if self._loop is not None:
+            from . import _lib
+            _lib.lib().obca_b200_loop_destroy(self._loop)
+            self._loop = None
+        super().close()
+
+    def start(self, terminal_rule="shipped", steps=None):
+        """Reset the scenarios and issue ``steps`` (default: all) receding-horizon steps; returns without waiting."""
+        from . import _lib
+        rule = 0 if terminal_rule == "shipped" else 1
+        if self._loop is None or self._rule != rule:
+            self.close()
+            self._create(rule)
+        L = _lib.lib()
+        dyn = np.ascontiguousarray(self.dyn, float)
+        cs = np.ascontiguousarray(np.stack([np.cos(dyn[:, 2]), np.sin(dyn[:, 2])], 1))
+        _lib.check(L.obca_b200_loop_reset(self._loop, dyn.ctypes.data, cs.ctypes.data, None))
+        _lib.check(L.obca_b200_loop_run(self._loop, self.max_steps if steps is None else int(steps), None))
+
+    def read(self):
+        import ctypes as C
+        from . import _lib
+        B, K = self.B, self.max_steps
+        traj = np.empty((B, K + 1, 3)); steps = np.empty(B, np.int32); failed = np.empty(B, np.int32)
+        mode = np.empty((B, K), np.int32); x = np.empty((B, 3)); u = np.empty((B, 2)); ts = np.empty(B)
+        solves = np.zeros(3, np.int64)
+        L = _lib.lib()
+        _lib.check(L.obca_b200_loop_read(self._loop, traj.ctypes.data, steps.ctypes.data, failed.ctypes.data,
+                                         mode.ctypes.data, x.ctypes.data, u.ctypes.data, ts.ctypes.data,
+                                         solves.ctypes.data, None))
+        goal = np.asarray(self.s.goalPose, float)
+        self.solves = int(solves.sum()); self.launches = int(L.obca_b200_loop_launch_count(self._loop))
+        return dict(traj=traj, steps=steps.astype(int), failed=failed.astype(bool),
+                    reached=((x[:, 0] - goal[0]) ** 2 + (x[:, 1] - goal[1]) ** 2 < 0.1), mode=mode.astype(int), x=x, u=u,
+                    Ts_opt=ts, launches=self.launches, solves=self.solves, solves_by_mode=solves.tolist())
+
+    def run(self, terminal_rule="shipped"):
+        self.start(terminal_rule)
+        return self.read()
+
+
+def build_rows_device(verts, vObs, vel=None, Ts=0.1, with_db=True):
+    """``obstacle_H_Represent`` + the time-stacking of ``rebuild_lObs`` on the GPU (``obca_b200_build_rows``).
+
+    ``verts`` CUDA float64 tensor (B, sum(vObs), 2): the polygons' vertices back to back, as the reference lists
+    them; ``vel`` (B, nObs, 3) = speed, cos, sin of each obstacle's heading, or None (static); ``Ts`` float or (B,)
+    tensor.  Returns ``edge_ptr`` (host), ``A`` (B,R,2), ``b0`` (B,R), ``db`` (B,R) with b_k = b0 + k*db."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    vObs = [int(v) for v in vObs]
+    ep = np.concatenate([[0], np.cumsum([v - 1 for v in vObs])]).astype(np.int32)
+    R = int(ep[-1]); B = verts.shape[0]
+    if not verts.is_cuda or verts.dtype != torch.float64 or tuple(verts.shape[1:]) != (sum(vObs), 2):
+        raise ValueError("verts must be a CUDA float64 tensor of shape (B, %d, 2)" % sum(vObs))
+    verts = verts.contiguous()
+    A = torch.empty((B, R, 2), dtype=torch.float64, device=verts.device)
+    b0 = torch.empty((B, R), dtype=torch.float64, device=verts.device)
+    db = torch.empty((B, R), dtype=torch.float64, device=verts.device) if with_db else None
+    tsv = Ts.contiguous() if torch.is_tensor(Ts) else None
+    if vel is not None:
+        vel = vel.contiguous()
+    with torch.cuda.device(verts.device):
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.lib().obca_b200_build_rows(
+            B, len(vObs), ep.ctypes.data_as(C.POINTER(C.c_int32)), verts.data_ptr(),
+            None if vel is None else vel.data_ptr(), None if tsv is None else tsv.data_ptr(),
+            0.0 if tsv is not None else float(Ts), A.data_ptr(), b0.data_ptr(), None if db is None else db.data_ptr(), st))
+    return ep, A, b0, db
+
+
 def demo9_monte_carlo(B, seed=20221209 + 4):
     """SURVEY 8(d) cfg 4: demo9 map, one 2x2 box starting at (8, U[35,55]) heading -pi/2 with speed U[0.2,0.8],
     appearing at step U{0..5}."""

@@ -150,11 +150,15 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
   ex.tid = threadIdx.x; ex.lane = threadIdx.x & 31; ex.warp = threadIdx.x >> 5; ex.nwarps = nwarps;
   ex.stage_warp = (ex.warp == nwarps - 1);
   bool first = true;
+  const unsigned int n_items = kp.count_dev ? (unsigned)*kp.count_dev : (unsigned)kp.batch;
   for (;;) {
-    if (threadIdx.x == 0) s_inst = atomicAdd(kp.counter, 1u);
+    if (threadIdx.x == 0) {
+      const unsigned int w = atomicAdd(kp.counter, 1u);
+      s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
+    }
     __syncthreads();
     const unsigned int inst = s_inst;
-    if (inst >= (unsigned)kp.batch) break;
+    if (inst == 0xffffffffu) break;
 #if defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
     for (int i = 0; i < 16; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
     ex.prof_t = clock64(); ex.phase = 0;
@@ -340,10 +344,12 @@ float obca_b200_last_kernel_ms(obca_ctx* c) {
   return ms;
 }
 
-int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, const double* xref, const double* uref,
-                    const double* T_max, const double* term, const double* Ts_inst, const int32_t* edge_ptr, const double* A,
-                    const double* b0, const double* db, int obstacles_shared, double* x, double* u, double* lam, double* mu,
-                    double* T, double* obj, int32_t* status, int32_t* iters, void* cuda_stream) {
+int obca_b200_solve_indexed(obca_ctx* c, int batch, const int32_t* count_dev, const int32_t* index_dev,
+                            const double* x0, const double* u0, const double* xref, const double* uref,
+                            const double* T_max, const double* term, const double* Ts_inst, const int32_t* edge_ptr,
+                            const double* A, const double* b0, const double* db, int obstacles_shared, double* x, double* u,
+                            double* lam, double* mu, double* T, double* obj, int32_t* status, int32_t* iters,
+                            void* cuda_stream) {
   if (!c || batch < 0 || batch > c->max_batch) return OBCA_E_ARG;
   if (batch == 0) return OBCA_OK;
   if (!x0 || !u0 || !xref || !edge_ptr || !x || !u || !lam || !mu || !T || !obj || !status || !iters) return OBCA_E_ARG;
@@ -375,6 +381,7 @@ int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, 
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
   kp.counter = c->counter; kp.wd_buf = c->wd_buf; kp.wd_stride = c->wd_stride;
+  kp.index = index_dev; kp.count_dev = count_dev;
   if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
   cudaEventRecord(c->ev0, st);
@@ -384,6 +391,14 @@ int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, 
   c->launches += 1;
   if (cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;
+}
+
+int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, const double* xref, const double* uref,
+                    const double* T_max, const double* term, const double* Ts_inst, const int32_t* edge_ptr, const double* A,
+                    const double* b0, const double* db, int obstacles_shared, double* x, double* u, double* lam, double* mu,
+                    double* T, double* obj, int32_t* status, int32_t* iters, void* cuda_stream) {
+  return obca_b200_solve_indexed(c, batch, nullptr, nullptr, x0, u0, xref, uref, T_max, term, Ts_inst, edge_ptr, A, b0, db,
+                                 obstacles_shared, x, u, lam, mu, T, obj, status, iters, cuda_stream);
 }
 
 int obca_b200_solve_host(obca_ctx* c, int batch, const double* x0, const double* u0, const double* xref, const double* uref,

@@ -46,6 +46,8 @@ struct KParams {
   double *x, *u, *lam, *mu, *T, *obj;
   int32_t *status, *iters;
   unsigned int* counter;  // persistent-block work queue
+  const int32_t* index;     // work item w solves instance index[w] (NULL: w itself)
+  const int32_t* count_dev; // number of work items read on the device (NULL: batch)
   double* wd_buf;         // watchdog checkpoints in HBM: one slot of wd_stride doubles per resident block
   int64_t wd_stride;
 };

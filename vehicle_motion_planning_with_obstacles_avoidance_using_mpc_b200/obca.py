@@ -82,7 +82,10 @@ class BatchSolver:
                     status=torch.empty((B,), dtype=torch.int32, device=device),
                     iters=torch.empty((B,), dtype=torch.int32, device=device))
 
-    def solve(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, stream=None, Ts=None):
+    def solve(self, x0, u0, xref, A, b0, db=None, T_max=None, term=None, uref=None, out=None, stream=None, Ts=None,
+              index=None, count=None):
+        """``index`` (int32 CUDA tensor) and ``count`` (int32 CUDA tensor with one element): solve only the instances
+        ``index[:count]``; arrays stay indexed by instance (``obca_b200_solve_indexed``)."""
         import torch
 
         def dp(t, dtype=torch.float64):
@@ -97,11 +100,14 @@ class BatchSolver:
         shared = int(A.dim() == 2)
         if stream is None:
             stream = torch.cuda.current_stream(x0.device).cuda_stream
-        rc = self._L.obca_b200_solve(self._ctx, B, dp(x0), dp(u0), dp(xref), dp(uref), dp(T_max), dp(term), dp(Ts),
-                                     _abi.ptr(self.edge_ptr, C.c_int32), dp(A), dp(b0), dp(db), shared,
-                                     dp(out["x"]), dp(out["u"]), dp(out["lam"]), dp(out["mu"]), dp(out["T"]),
-                                     dp(out["obj"]), dp(out["status"], torch.int32), dp(out["iters"], torch.int32),
-                                     C.c_void_p(stream))
+        if (index is None) != (count is None):
+            raise ValueError("index and count go together")
+        rc = self._L.obca_b200_solve_indexed(self._ctx, B, dp(count, torch.int32), dp(index, torch.int32),
+                                             dp(x0), dp(u0), dp(xref), dp(uref), dp(T_max), dp(term), dp(Ts),
+                                             _abi.ptr(self.edge_ptr, C.c_int32), dp(A), dp(b0), dp(db), shared,
+                                             dp(out["x"]), dp(out["u"]), dp(out["lam"]), dp(out["mu"]), dp(out["T"]),
+                                             dp(out["obj"]), dp(out["status"], torch.int32),
+                                             dp(out["iters"], torch.int32), C.c_void_p(stream))
         _lib.check(rc)
         return out
 
