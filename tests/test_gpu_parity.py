@@ -233,3 +233,35 @@ def test_closed_loop_lockstep_batch_matches_oracle_driver():
     close = [np.abs(og["traj"][i, :n[i] + 1] - oc["traj"][i, :n[i] + 1]).max() <= 1e-3 for i in range(B) if same[i]]
     assert np.mean(close) >= 0.9
     assert (og["mode"] == _abi.MODE_FIXED_SET).any() or (og["mode"] == _abi.MODE_FIXED_NOTERM).any()
+
+
+@pytest.mark.parametrize("name,sides,N,moving", [("ragged_3_to_8_edges", [3, 4, 5, 6, 7, 8], 12, 0),
+                                                 ("longest_horizon", [4, 3], 31, 0),
+                                                 ("twelve_obstacles_48_rows", [4] * 12, 10, 0),
+                                                 ("octagons_moving", [8, 8, 5], 8, 1),
+                                                 ("48_rows_ragged", [8, 8, 8, 8, 8, 4, 4], 6, 0)])
+def test_size_limits_and_ragged_polygons(name, sides, N, moving):
+    """the generic kernels (sizes from the parameter block, 4- and 8-edge variants) at the compiled limits:
+    N + 1 = 32 stages, 12 obstacles, 48 rows, 3..8 edges per obstacle"""
+    b = sc.make_polygon_batch(sides, 160, N, seed=1, moving=moving)
+    prm, a = common.batch_arrays(b)
+    g = _gpu(prm, a); c = _cpu(prm, a)
+    _compare(g, c, min_ok=0.6)
+    _certificate(prm, a, g, b.dmin, b.ego)
+
+
+def test_batch_of_one_and_empty_batch():
+    b = sc.make_batch(2, 3)
+    prm, a = common.batch_arrays(b)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], 8)
+    full = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"])
+    one = s.solve_host(a["x0"][1:2], a["u0"][1:2], a["xref"][1:2], a["A"], a["b0"], a["db"], T_max=a["T_max"][1:2])
+    for k in ("x", "u", "T", "obj", "status", "iters"):
+        assert np.array_equal(one[k][0], full[k][1]), k
+    n0 = s.launches
+    empty = s.solve_host(a["x0"][:0], a["u0"][:0], a["xref"][:0], a["A"], a["b0"], a["db"], T_max=a["T_max"][:0])
+    assert empty["x"].shape == (0, prm.N + 1, 3) and s.launches == n0
+    with pytest.raises(RuntimeError):
+        s.solve_host(np.tile(a["x0"], (3, 1)), np.tile(a["u0"], (3, 1)), np.tile(a["xref"], (3, 1, 1)), a["A"], a["b0"], a["db"],
+                     T_max=np.tile(a["T_max"], 3))                # 9 > max_batch
+    s.close()

@@ -110,3 +110,20 @@ def test_stall_at_acceptable_level():
     assert (c["status"] == 1).all() and (e["status"] == 1).all()
     assert c["iters"].max() <= 55 and e["iters"].max() <= 55
     assert np.abs(c["x"] - e["x"]).max() <= 1e-6 and (np.abs(c["obj"] - e["obj"]) <= 1e-8 * np.abs(c["obj"])).all()
+
+
+SIZE_CASES = [("ragged_3_to_8_edges", [3, 4, 5, 6, 7, 8], 12, 0), ("longest_horizon", [4, 3], 31, 0),
+              ("twelve_obstacles_48_rows", [4] * 12, 10, 0), ("octagons_moving", [8, 8, 5], 8, 1),
+              ("48_rows_ragged", [8, 8, 8, 8, 8, 4, 4], 6, 0)]
+
+
+@pytest.mark.parametrize("name,sides,N,moving", SIZE_CASES)
+def test_size_limits_and_ragged_polygons(name, sides, N, moving):
+    """edge counts 3..8 per obstacle, N + 1 = 32 stages, 12 obstacles, 48 rows: kernel code == oracle"""
+    b = sc.make_polygon_batch(sides, 6, N, seed=1, moving=moving)
+    prm, a = common.batch_arrays(b)
+    c = _oracle(prm, a); e = common.emu_solve(prm, a)
+    assert np.array_equal(c["status"] >= 0, e["status"] >= 0) and (c["status"] >= 0).sum() >= 4
+    ok = c["status"] >= 0
+    assert np.abs(e["x"][ok] - c["x"][ok]).max() <= 1e-6 and np.abs(e["u"][ok] - c["u"][ok]).max() <= 1e-6
+    assert (np.abs(e["obj"][ok] - c["obj"][ok]) / np.abs(c["obj"][ok])).max() <= 1e-7

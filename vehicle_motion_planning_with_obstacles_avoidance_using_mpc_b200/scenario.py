@@ -116,6 +116,40 @@ def update_reference_trajectory(N, ref, x0):
     return ref[:, idx].copy()
 
 
+def sample_instances(rng, grid, static_polys, goal, N, B, free, x_cells=(1, 36), y_cells=(1, 10)):
+    """B start poses on free grid cells (AABB clearance 2) with their A* reference windows; poses whose start or
+    terminal pose collides, or whose T_max (obca.py:961-962) leaves no room for the distance, are redrawn."""
+    cells = [(cx, cy) for cx in range(*x_cells) for cy in range(*y_cells)
+             if grid[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3].sum() == 0]
+    # one native batched A* call for every candidate cell (identical to plan_reference per cell)
+    pref, plen_ = plan_batch(grid, [[cx, cy, 0] for cx, cy in cells], [goal])
+    paths = {c: (pref[j, :plen_[j]].T.copy() if plen_[j] > 0 else None) for j, c in enumerate(cells)}
+    x0 = np.zeros((B, 3)); xref = np.zeros((B, 3, N + 1))
+    n = 0
+    while n < B:
+        cx, cy = cells[rng.integers(len(cells))]
+        th0 = rng.uniform(-np.pi / 4, np.pi / 4)
+        ref = paths[(cx, cy)]
+        if ref is None or ref.shape[1] < 3:
+            continue
+        pose = np.array([cx, cy, th0], float)
+        win = update_reference_trajectory(N, ref, pose)
+        if not pose_clear(pose, static_polys, DMIN + 0.05):
+            continue
+        if free:
+            if not pose_clear(win[:, N], static_polys, DMIN + 0.05):
+                continue
+            # Tmax of obca.py:961-962 must leave room for the distance to cover (SURVEY Q5)
+            Tmax = ((win[0, N] - cx) + (win[1, N] - cy)) / (N * U_U[0] * TS) + 1
+            seg = np.diff(np.concatenate([pose[:2, None], win[:2]], axis=1), axis=1)
+            plen = np.sqrt((seg ** 2).sum(0)).sum()
+            if Tmax * N * U_U[0] * TS < 1.02 * plen + 0.3:
+                continue
+        x0[n] = pose; xref[n] = win
+        n += 1
+    return x0, xref
+
+
 def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_seed=None):
     """cfg 2: N=10, 2 quads, FREE.  cfg 3: N=20, 4 quads, FREE (headline).  cfg 5: cfg 3 + 2 dynamic boxes,
     FIXED_SET with Ts = 2.0 and terminal set [x0.x+5, 99] x [1, 9] (closed_loop.py:371).
@@ -152,36 +186,7 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_se
 
     if pose_seed is not None:
         rng = np.random.default_rng(pose_seed)
-    # free start cells with clearance; A* once per distinct cell
-    cells = [(cx, cy) for cx in range(1, 36) for cy in range(1, 10)
-             if grid[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3].sum() == 0]
-    # one native batched A* call for every candidate cell (identical to plan_reference per cell)
-    pref, plen_ = plan_batch(grid, [[cx, cy, 0] for cx, cy in cells], [goal])
-    paths = {c: (pref[j, :plen_[j]].T.copy() if plen_[j] > 0 else None) for j, c in enumerate(cells)}
-    x0 = np.zeros((B, 3)); xref = np.zeros((B, 3, N + 1))
-    n = 0
-    static_polys = polys[:nq]
-    while n < B:
-        cx, cy = cells[rng.integers(len(cells))]
-        th0 = rng.uniform(-np.pi / 4, np.pi / 4)
-        ref = paths[(cx, cy)]
-        if ref is None or ref.shape[1] < 3:
-            continue
-        pose = np.array([cx, cy, th0], float)
-        win = update_reference_trajectory(N, ref, pose)
-        if not pose_clear(pose, static_polys, DMIN + 0.05):
-            continue
-        if mode == _o.MODE_FREE:
-            if not pose_clear(win[:, N], static_polys, DMIN + 0.05):
-                continue
-            # Tmax of obca.py:961-962 must leave room for the distance to cover
-            Tmax = ((win[0, N] - cx) + (win[1, N] - cy)) / (N * U_U[0] * TS) + 1
-            seg = np.diff(np.concatenate([pose[:2, None], win[:2]], axis=1), axis=1)
-            plen = np.sqrt((seg ** 2).sum(0)).sum()
-            if Tmax * N * U_U[0] * TS < 1.02 * plen + 0.3:
-                continue
-        x0[n] = pose; xref[n] = win
-        n += 1
+    x0, xref = sample_instances(rng, grid, polys[:nq], goal, N, B, mode == _o.MODE_FREE)
     free = mode == _o.MODE_FREE
     ts = None
     if cfg == 5:
@@ -190,4 +195,50 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_se
     return Batch(mode=mode, N=N, Ts=Ts, Q=(Q_FREE if free else Q_FIX).copy(), P=(Q_FREE if free else Q_FIX).copy(),
                  R=[r.copy() for r in (R_FREE if free else R_FIX)], xL=xL, xU=xU, uL=U_L.copy(), uU=U_U.copy(),
                  ego=EGO.copy(), dmin=DMIN, nObs=len(vObs), vObs=vObs, AObs=AObs, bObs=bObs, x0=x0,
+                 u0=np.zeros((B, 2)), xref=xref, terminal_set=ts, polygons=polys)
+
+
+def regular_polygon(cx, cy, radius, sides, phase=0.0):
+    """Clockwise regular polygon, first vertex repeated (the reference's vertex-list convention)."""
+    ang = phase - 2 * np.pi * np.arange(sides) / sides
+    v = [[cx + radius * np.cos(a), cy + radius * np.sin(a)] for a in ang]
+    return v + [v[0]]
+
+
+def make_polygon_batch(sides, B, N, seed=0, map_size=(60, 24), moving=0, mode=None):
+    """A scene of convex polygons with ``sides[i]`` edges each (3..8) on a ``map_size`` field, laid out on a jittered
+    lattice so that they do not touch; the last ``moving`` of them drift (FIXED modes).  Exercises ragged edge counts,
+    the 8-edge kernel variant and the size limits (N + 1 <= 32 stages, 12 obstacles, 48 rows)."""
+    from . import obca as _o
+    rng = np.random.default_rng(seed)
+    W, H = map_size
+    n = len(sides)
+    cols = int(np.ceil(n / 2))
+    while True:
+        polys, info = [], []
+        for i, k in enumerate(sides):
+            cx = 8 + (W - 18) * ((i // 2) + 0.5) / cols + rng.uniform(-0.8, 0.8)
+            cy = (H * 0.27 if i % 2 == 0 else H * 0.73) + rng.uniform(-1.0, 1.0)
+            polys.append(regular_polygon(cx, cy, rng.uniform(1.2, 2.0), int(k), rng.uniform(0, 2 * np.pi)))
+            info.append([0] * 11)
+        goal = (W - 3, H // 2, 0)
+        grid = mo.shape2grid([W, H], [p[:-1] for p in polys])
+        if grid[int(goal[1]), int(goal[0])] == 0 and plan_reference(grid, (1, H // 2, 0), goal) is not None:
+            break
+    if mode is None:
+        mode = _o.MODE_FIXED_SET if moving else _o.MODE_FREE
+    free = mode in (_o.MODE_FREE, _o.MODE_FREE_STACKED)
+    Ts = TS if free else 1.0
+    for i in range(n - moving, n):
+        info[i] = [0, 0, rng.uniform(-np.pi, np.pi), 0, 0, rng.uniform(0.02, 0.08), 0, 0, 0, 0, 0]
+    vObs = [int(k) + 1 for k in sides]
+    AObs, bObs = mo.stacked_H_rep(polys, vObs, info, N, Ts)
+    x0, xref = sample_instances(rng, grid, polys, goal, N, B, free, x_cells=(1, W - 8), y_cells=(1, H - 1))
+    ts = None
+    if mode == _o.MODE_FIXED_SET:
+        ts = np.zeros((B, 2, 2))
+        ts[:, 0, 0] = x0[:, 0] + 3; ts[:, 0, 1] = 99; ts[:, 1, 0] = 0; ts[:, 1, 1] = H
+    return Batch(mode=mode, N=N, Ts=Ts, Q=(Q_FREE if free else Q_FIX).copy(), P=(Q_FREE if free else Q_FIX).copy(),
+                 R=[r.copy() for r in (R_FREE if free else R_FIX)], xL=np.array([0.0, 0.0]), xU=np.array([W - 1.0, H - 1.0]),
+                 uL=U_L.copy(), uU=U_U.copy(), ego=EGO.copy(), dmin=DMIN, nObs=n, vObs=vObs, AObs=AObs, bObs=bObs, x0=x0,
                  u0=np.zeros((B, 2)), xref=xref, terminal_set=ts, polygons=polys)
