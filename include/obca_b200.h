@@ -33,6 +33,18 @@ enum { OBCA_MODE_FREE = 0, OBCA_MODE_FIXED_SET = 1, OBCA_MODE_FIXED_NOTERM = 2, 
  * 2 = A* warm start (poses from xref, T from arc length, inputs by differences, duals from the most
  * separating face) */
 enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
+/* OR-ed into `init`: an instance whose line search, regularisation or progress fails (status -4, -2, -5: where IPOPT
+ * would enter its restoration phase, which this solver does not have) is restarted from the other start points
+ * (WARM -> XREF -> ZERO, XREF -> WARM -> ZERO, ZERO -> WARM -> XREF) before the failure is reported; `iters` is the
+ * total over the attempts.  The problems are non-convex: a restart may end in a different local solution. */
+#define OBCA_INIT_RETRY 16
+/* OR-ed into `init`: OBCA_INIT_SOFT(n), n <= 15.  After a failure of the same kind the solver first keeps the primal
+ * point it reached and starts again from there with fresh multipliers (y = 0, z = 1), slacks (max(d(x), bound_push)),
+ * barrier parameter and filter - at most n times per start point.  This stands in for IPOPT's restoration phase.
+ * OBCA_INIT_KEEP is that start code (internal: contexts are created with ZERO, XREF or WARM). */
+#define OBCA_INIT_KEEP 3
+#define OBCA_INIT_SOFT(n) (((n) & 15) << 8)
+#define OBCA_SOFT_RESTARTS(init) (((init) >> 8) & 15)
 /* per-instance status */
 enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,
        OBCA_ST_LSFAIL = -4, OBCA_ST_STALL = -5 };

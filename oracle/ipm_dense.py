@@ -39,6 +39,7 @@ DEFAULT_OPTS = dict(tol=1e-8, max_iter=3000, mu_init=10.0, kappa_eps=10.0, kappa
                     dc_min=1e-8, lm_cap=1e4, acceptable_tol=1e-6, acceptable_iter=15, filt_max=32,
                     stall_alpha=1e-3, stall_iters=10, sig_min=1e-8,
                     wd_trigger=10, wd_max=3, acc_stall=10,
+                    soft_restarts=0, retry=False, X0=None,
                     init="warm", verbose=False, soc=False, dbg=False)
 
 # status codes (shared with oracle/obca_oracle.c and the CUDA kernel)
@@ -81,7 +82,32 @@ def gname(lay, p, r):
     return "?"
 
 
+_RETRY_ORDER = {"zero": ("zero", "warm", "xref"), "xref": ("xref", "warm", "zero"), "warm": ("warm", "xref", "zero")}
+
+
 def solve(p: nlp.Problem, opts=None):
+    """Recovery sequence (OBCA_INIT_SOFT / OBCA_INIT_RETRY of include/obca_b200.h): an attempt that ends with a failed
+    line search, regularisation or stall is followed by up to ``soft_restarts`` restarts from the point it reached
+    (multipliers, slacks, barrier parameter and filter afresh), then - with ``retry`` - by the other start points;
+    ``iters`` is the total."""
+    o = dict(DEFAULT_OPTS)
+    if opts:
+        o.update(opts)
+    total = 0
+    res = None
+    for init in (_RETRY_ORDER[o["init"]] if o["retry"] else (o["init"],)):
+        for s_ in range(o["soft_restarts"] + 1):
+            res = _solve_once(p, dict(o, init=init) if s_ == 0 else dict(o, init="keep", X0=res["X"]))
+            total += res["iters"]
+            if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL):
+                break
+        if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL):
+            break
+    res["iters"] = total
+    return res
+
+
+def _solve_once(p: nlp.Problem, opts=None):
     o = dict(DEFAULT_OPTS)
     if opts:
         o.update(opts)
@@ -91,7 +117,7 @@ def solve(p: nlp.Problem, opts=None):
     Mw = np.zeros(n); Mw[:lay.ntraj] = 1.0
     sign_rows, sign_cols = nlp.sign_rows(p, lay)
 
-    X = nlp.start_point(p, lay, o["init"])
+    X = np.array(o["X0"], float) if o["init"] == "keep" else nlp.start_point(p, lay, o["init"])
     ev = nlp.evaluate(p, lay, X, want=("c", "d"))
     S = np.maximum(ev["d"], o["bound_push"])
     Z = np.ones(q)

@@ -32,7 +32,7 @@
 
 typedef struct {
   const obca_params* P;
-  int N, nobs, R, free_, has_term, stacked;
+  int N, nobs, R, free_, has_term, stacked, init;
   int eptr[OM + 1];
   double Ts, Tmax, dmin, off, g[4];
   double x0[3], u0[2], term[3];
@@ -177,7 +177,11 @@ static void theta_phi(const prob_t* p, const iter_t* it, const vals_t* v, double
  * ---------------------------------------------------------------------------------------------- */
 static void start_point(const prob_t* p, iter_t* it) {
   const obca_params* P = p->P;
-  int N = p->N, init = P->init;
+  int N = p->N, init = p->init;
+  if (init == OBCA_INIT_KEEP) { /* soft restart: primal point stays, equality multipliers start at 0 */
+    memset(it->yd, 0, sizeof(it->yd)); memset(it->yt, 0, sizeof(it->yt)); memset(it->ye, 0, sizeof(it->ye));
+    return;
+  }
   memset(it, 0, sizeof(*it));
   for (int j = 0; j < 3; ++j) it->z[0][j] = p->x0[j];
   it->T = 1.0;
@@ -1140,8 +1144,21 @@ static void* worker(void* arg) {
     if (p.has_term) for (int j = 0; j < 3; ++j) p.term[j] = J->term[3 * b + j];
     size_t ob = J->shared ? 0 : (size_t)b;
     p.A = J->A + ob * 2 * R; p.b0 = J->b0 + ob * R; p.db = J->db ? J->db + ob * R : 0;
-    int iters = 0;
-    int st = solve_one(&p, w, &iters, 0);
+    /* recovery sequence (include/obca_b200.h): per start point up to n soft restarts from the point reached
+     * (OBCA_INIT_SOFT), then the next start point (OBCA_INIT_RETRY) */
+    static const int order[3][3] = {{0, 2, 1}, {1, 2, 0}, {2, 1, 0}};
+    const int base = (P->init & 15) % 3, retry = (P->init & OBCA_INIT_RETRY) != 0, nsoft = OBCA_SOFT_RESTARTS(P->init);
+    int iters = 0, st = OBCA_ST_MAXITER;
+    for (int a = 0; a < 3; ++a) {
+      for (int s_ = 0; s_ <= nsoft; ++s_) {
+        int it_a = 0;
+        p.init = s_ == 0 ? order[base][a] : OBCA_INIT_KEEP;
+        st = solve_one(&p, w, &it_a, 0);
+        iters += it_a;
+        if (!(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL)) break;
+      }
+      if (!retry || !(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL)) break;
+    }
     const iter_t* it = &w->it;
     for (int k = 0; k <= N; ++k) {
       for (int j = 0; j < 3; ++j) J->x[((size_t)b * (N + 1) + k) * 3 + j] = it->z[k][j];

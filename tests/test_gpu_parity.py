@@ -265,3 +265,49 @@ def test_batch_of_one_and_empty_batch():
         s.solve_host(np.tile(a["x0"], (3, 1)), np.tile(a["u0"], (3, 1)), np.tile(a["xref"], (3, 1, 1)), a["A"], a["b0"], a["db"],
                      T_max=np.tile(a["T_max"], 3))                # 9 > max_batch
     s.close()
+
+
+def test_large_host_batch_goes_through_in_chunks():
+    """solve_host splits a large batch over several streams (copy-back overlaps the next chunk's solve): results are
+    bit-identical to one launch over device tensors, for shared and per-instance obstacle rows, pinned or pageable"""
+    import torch
+    B = 2500
+    b = sc.make_batch(3, B)
+    prm, a = common.batch_arrays(b)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], B)
+    t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
+    o = s.solve(t(a["x0"]), t(a["u0"]), t(a["xref"]), t(a["A"]), t(a["b0"]), None, T_max=t(a["T_max"]))
+    torch.cuda.synchronize()
+    n0 = s.launches
+    h = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"],
+                     out=s.alloc_host_outputs(B, pinned=True))
+    assert s.launches - n0 == 4
+    A_i = np.tile(a["A"][None], (B, 1, 1)); b_i = np.tile(a["b0"][None], (B, 1))
+    h2 = s.solve_host(a["x0"], a["u0"], a["xref"], A_i, b_i, None, T_max=a["T_max"])
+    for k in ("x", "u", "T", "obj", "lam", "mu", "status", "iters"):
+        assert np.array_equal(o[k].cpu().numpy(), h[k]), k
+        assert np.array_equal(h2[k], h[k]), k
+    o2 = s.solve(t(a["x0"]), t(a["u0"]), t(a["xref"]), t(a["A"]), t(a["b0"]), None, T_max=t(a["T_max"]))   # device path after
+    torch.cuda.synchronize()
+    assert np.array_equal(o2["x"].cpu().numpy(), h["x"])
+    s.close()
+
+
+def test_recovery_rules_raise_the_success_rate():
+    """OBCA_INIT_SOFT / OBCA_INIT_RETRY on the GPU: instances that fail from the warm start are recovered as in the
+    oracle, results of the others do not change, every recovered result carries a valid certificate"""
+    B = 2048
+    b = sc.make_batch(3, B)
+    prm0, a = common.batch_arrays(b)
+    prm, _ = common.batch_arrays(b, init=_abi.INIT_WARM | _abi.RECOVER)
+    g0 = _gpu(prm0, a); g = _gpu(prm, a); c = _cpu(prm, a)
+    fail0 = g0["status"] < 0
+    assert fail0.sum() >= 3
+    assert (g["status"] >= 0).mean() >= 0.999 and (c["status"] >= 0).mean() >= 0.999
+    assert (g["status"][fail0] >= 0).sum() >= fail0.sum() - 1
+    ok0 = ~fail0
+    for k in ("x", "u", "T", "obj", "iters", "status"):
+        assert np.array_equal(g[k][ok0], g0[k][ok0]), k                     # first attempt succeeded: nothing changes
+    assert (g["iters"][fail0] > g0["iters"][fail0]).all()
+    _certificate(prm, a, g, b.dmin, b.ego)
+    _compare(g, c, min_ok=0.99)

@@ -58,9 +58,19 @@ static void run(const KParams& kp, int nwarps, int has_uref) {
     int iters = 0;
     double obj = 0;
     std::vector<double> wd(Solver<EMAX>::wd_doubles(ex.T, P.N + 1), 0.0);
-    int st = solve_instance(S, ex, (size_t)b, wd.data(), iters, obj);
+    int st;
+    for (int seq = 0;;) {
+      int it_a = 0;
+      st = solve_instance(S, ex, (size_t)b, wd.data(), it_a, obj);
+      iters += it_a;
+      if (!(P.init >> 4) || !retry_status(st)) break;
+      const int next = next_attempt(P.init, seq);
+      if (next < 0) break;
+      sm.G->init = next;
+    }
     if (st != OBCA_ST_STORED)
       for (int t = 0; t < ex.T; ++t) S.store(t, ex.brs[t], (size_t)b, st, iters, obj);
+    else { kp.obj[b] = obj; kp.iters[b] = iters; }
   }
 }
 

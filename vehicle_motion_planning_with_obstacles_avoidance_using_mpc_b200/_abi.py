@@ -17,6 +17,13 @@ MODE_FREE_STACKED = 3  # obca2, fixtime == 0  obca.py:338-629
 MODE_FIXED_OBCA2 = 4   # obca2, fixtime == 1  (terminal_set optional)
 
 INIT_ZERO, INIT_XREF, INIT_WARM = 0, 1, 2
+INIT_RETRY = 16                       # OBCA_INIT_RETRY: failed attempts restart from the other start points
+RECOVER = INIT_RETRY | (3 << 8)       # + OBCA_INIT_SOFT(3): what the receding-horizon drivers and `obca` use
+
+
+def init_soft(n):
+    """OBCA_INIT_SOFT(n): up to n soft restarts (multipliers, slacks, barrier parameter, filter) per attempt"""
+    return (int(n) & 15) << 8
 
 ST_OK, ST_ACCEPTABLE, ST_MAXITER, ST_REGFAIL, ST_EMPTYBOX, ST_LSFAIL, ST_STALL = 0, 1, -1, -2, -3, -4, -5
 
@@ -50,17 +57,21 @@ def is_free(mode):
 
 
 def make_params(mode, N, n_obs, rows, Ts, P, Q, R, xL, xU, uL, uU, dmin, ego, *, init=INIT_WARM, has_term=None,
-                max_iter=None, tol=1e-8, acceptable_tol=None, acceptable_iter=15, mu_init=10.0, bound_push=0.1, T_min=1e-4):
+                max_iter=None, tol=1e-8, acceptable_tol=None, acceptable_iter=15, mu_init=10.0, bound_push=0.1, T_min=1e-4,
+                soft_restarts=0, retry=False):
     """Solver options default to what the reference passes to IPOPT: mpc4 -> IPOPT defaults (max_iter 3000,
     acceptable_tol 1e-6; obca.py:1044); mpc6/mpc8/obca2-fixed -> max_iter 1000, acceptable_tol 1e-8
-    (obca.py:1538-1539, 1734-1735, 596-598)."""
+    (obca.py:1538-1539, 1734-1735, 596-598).  ``soft_restarts`` / ``retry`` switch on the recovery rules that stand
+    in for IPOPT's restoration phase (OBCA_INIT_SOFT / OBCA_INIT_RETRY in include/obca_b200.h); they can also be
+    OR-ed into ``init`` directly (``init=INIT_WARM | RECOVER``)."""
     if N + 1 > MAX_STAGES or N < 1:
         raise ValueError("horizon N=%d outside 1..%d" % (N, MAX_STAGES - 1))
     if n_obs > MAX_OBS or rows > MAX_ROWS:
         raise ValueError("too many obstacles/rows for one stage (%d obstacles, %d rows)" % (n_obs, rows))
     free = is_free(mode)
     p = ObcaParams()
-    p.mode, p.N, p.n_obs, p.rows, p.init = mode, N, n_obs, rows, init
+    p.mode, p.N, p.n_obs, p.rows = mode, N, n_obs, rows
+    p.init = int(init) | init_soft(soft_restarts) | (INIT_RETRY if retry else 0)
     p.max_iter = (3000 if free else 1000) if max_iter is None else max_iter
     p.has_term = int(mode == MODE_FIXED_SET) if has_term is None else int(has_term)
     p.acceptable_iter = acceptable_iter

@@ -268,7 +268,7 @@ class ClosedLoopBatch:
     All scenarios share the static map, start/goal and hence the A* path; each has its own single moving box
     ``dyn`` rows ``[cx, cy, theta, l, w, v, start_step]`` (B,7).  ``run`` returns the closed-loop logs."""
 
-    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM, max_steps=30,
+    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM | _abi.RECOVER, max_steps=30,
                  solver_factory=None):
         self.s = setting
         self.dyn = np.array(dyn, float)
@@ -304,9 +304,14 @@ class ClosedLoopBatch:
             free = _abi.is_free(mode)
             prm = _abi.make_params(mode, self.N, len(edges), int(ep[-1]), 0.1, self.Q_free if free else self.Q_fix,
                                    self.Q_free if free else self.Q_fix, self.R_free if free else self.R_fix,
-                                   self.s.xL, self.s.xU, self.uL, self.uU, self.dmin, self.ego, init=self.init)
+                                   self.s.xL, self.s.xU, self.uL, self.uU, self.dmin, self.ego, init=self._init_of(mode))
             self._solvers[key] = (self._factory(prm, ep, self.B), ep)
         return self._solvers[key]
+
+    def _init_of(self, mode):
+        """The terminal-set solve has its own fallback (the solve without the set, closed_loop.py:389-395) and is often
+        truly infeasible: it runs without the recovery rules; the other two modes keep them."""
+        return (self.init & 15) if mode == _abi.MODE_FIXED_SET else self.init
 
     def close(self):
         for s, _ in self._solvers.values():
@@ -411,7 +416,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
     include/obca_b200.h): scenario state, input builders, work lists and the three solver modes stay in HBM; the host
     issues the launches of all steps without waiting and reads the logs once at the end."""
 
-    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM, max_steps=30):
+    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM | _abi.RECOVER, max_steps=30):
         super().__init__(setting, dyn, N=N, Q_free=Q_free, sense=sense, device=device, init=init, max_steps=max_steps)
         self._loop = None
         self._rule = None
@@ -421,7 +426,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
         free = _abi.is_free(mode)
         return _abi.make_params(mode, self.N, len(edges), int(sum(edges)), 0.1, self.Q_free if free else self.Q_fix,
                                 self.Q_free if free else self.Q_fix, self.R_free if free else self.R_fix,
-                                self.s.xL, self.s.xU, self.uL, self.uU, self.dmin, self.ego, init=self.init)
+                                self.s.xL, self.s.xU, self.uL, self.uU, self.dmin, self.ego, init=self._init_of(mode))
 
     def _create(self, rule):
         import ctypes as C

@@ -172,9 +172,20 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
 #endif
     int iters = 0;
     double obj = 0.0;
-    const int status = solve_instance(S, ex, (size_t)inst, kp.wd_buf + (size_t)blockIdx.x * kp.wd_stride, iters, obj);
+    int status;
+    for (int seq = 0;;) {   // one pass unless a recovery rule is set and the attempt failed (cold path)
+      int it_a = 0;
+      status = solve_instance(S, ex, (size_t)inst, kp.wd_buf + (size_t)blockIdx.x * kp.wd_stride, it_a, obj);
+      iters += it_a;
+      if (!(kp.P.init >> 4) || !retry_status(status)) break;
+      const int next = next_attempt(kp.P.init, seq);
+      if (next < 0) break;
+      __syncthreads();
+      if (ex.tid == 0) sm.G->init = next;
+      __syncthreads();
+    }
     if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
-    else if (ex.tid == 0) kp.obj[inst] = obj;
+    else if (ex.tid == 0) { kp.obj[inst] = obj; kp.iters[inst] = iters; }
 #if !defined(OBCA_P_PAR)
     if (ex.phase_hits[ex.phase_id & 3] < 0) kp.iters[inst] = -1;   // never true: keeps the member alive
 #endif
@@ -195,6 +206,8 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
 // ======================================================================================================
 typedef void (*kernel_fn)(const obca::KParams, int, int);
 
+#define OBCA_HOST_CHUNKS 4
+
 struct obca_ctx {
   int device;
   int max_batch;
@@ -213,6 +226,9 @@ struct obca_ctx {
   bool timed;
   void* stage;            // host-path staging
   size_t stage_bytes;
+  int slots, cfg_slots;   // launches that may be in flight at once (own work counter and checkpoint slots each)
+  cudaStream_t hs[OBCA_HOST_CHUNKS];   // host path: one stream per chunk of a large batch
+  cudaEvent_t ev_shared;
 };
 
 static int sm_count_of(int device) {
@@ -239,7 +255,7 @@ static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
 }
 
 static int configure(obca_ctx* c, int emax, int has_uref) {
-  if (c->fn && c->cfg_emax == emax && c->cfg_uref == has_uref) return OBCA_OK;
+  if (c->fn && c->cfg_emax == emax && c->cfg_uref == has_uref && c->cfg_slots == c->slots) return OBCA_OK;
   const obca_params& P = c->P;
   const int nb = P.n_obs * (P.N + 1);
   c->nwarps = (nb + 31) / 32 + 1;
@@ -261,14 +277,14 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
   c->grid = sm_count_of(c->device) * per_sm;
   c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
-  const size_t need = (size_t)c->grid * c->wd_stride * sizeof(double);
+  const size_t need = (size_t)c->slots * c->grid * c->wd_stride * sizeof(double);
   if (need > c->wd_bytes) {
     if (c->wd_buf) cudaFree(c->wd_buf);
     c->wd_buf = nullptr; c->wd_bytes = 0;
     if (cudaMalloc(&c->wd_buf, need) != cudaSuccess) { cudaGetLastError(); return OBCA_E_NOMEM; }
     c->wd_bytes = need;
   }
-  c->cfg_emax = emax; c->cfg_uref = has_uref;
+  c->cfg_emax = emax; c->cfg_uref = has_uref; c->cfg_slots = c->slots;
   return OBCA_OK;
 }
 
@@ -302,8 +318,10 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   obca_ctx* c = (obca_ctx*)calloc(1, sizeof(obca_ctx));
   if (!c) return OBCA_E_NOMEM;
   c->device = device; c->max_batch = max_batch; c->P = *p;
-  if (cudaMalloc(&c->counter, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
+  if (cudaMalloc(&c->counter, OBCA_HOST_CHUNKS * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  cudaEventCreateWithFlags(&c->ev_shared, cudaEventDisableTiming);
+  c->slots = 1;
   *out = c;
   return OBCA_OK;
 }
@@ -314,7 +332,8 @@ int obca_b200_destroy(obca_ctx* c) {
   cudaFree(c->counter);
   if (c->stage) cudaFree(c->stage);
   if (c->wd_buf) cudaFree(c->wd_buf);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_shared);
+  for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) if (c->hs[j]) cudaStreamDestroy(c->hs[j]);
   free(c);
   return OBCA_OK;
 }
@@ -344,7 +363,7 @@ float obca_b200_last_kernel_ms(obca_ctx* c) {
   return ms;
 }
 
-int obca_b200_solve_indexed(obca_ctx* c, int batch, const int32_t* count_dev, const int32_t* index_dev,
+static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev, const int32_t* index_dev,
                             const double* x0, const double* u0, const double* xref, const double* uref,
                             const double* T_max, const double* term, const double* Ts_inst, const int32_t* edge_ptr,
                             const double* A, const double* b0, const double* db, int obstacles_shared, double* x, double* u,
@@ -380,17 +399,26 @@ int obca_b200_solve_indexed(obca_ctx* c, int batch, const int32_t* count_dev, co
   kp.x0 = x0; kp.u0 = u0; kp.xref = xref; kp.uref = uref; kp.Tmax = T_max; kp.term = term; kp.Ts_inst = Ts_inst;
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
-  kp.counter = c->counter; kp.wd_buf = c->wd_buf; kp.wd_stride = c->wd_stride;
+  kp.counter = c->counter + slot; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * c->wd_stride; kp.wd_stride = c->wd_stride;
   kp.index = index_dev; kp.count_dev = count_dev;
-  if (cudaMemsetAsync(c->counter, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
+  if (cudaMemsetAsync(c->counter + slot, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
-  cudaEventRecord(c->ev0, st);
+  if (slot == 0) cudaEventRecord(c->ev0, st);
   c->fn<<<grid, c->threads, c->smem_bytes, st>>>(kp, c->nwarps, uref != nullptr);
-  cudaEventRecord(c->ev1, st);
+  if (slot == 0) cudaEventRecord(c->ev1, st);
   c->timed = true;
   c->launches += 1;
   if (cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;
+}
+
+int obca_b200_solve_indexed(obca_ctx* c, int batch, const int32_t* count_dev, const int32_t* index_dev, const double* x0,
+                            const double* u0, const double* xref, const double* uref, const double* T_max, const double* term,
+                            const double* Ts_inst, const int32_t* edge_ptr, const double* A, const double* b0, const double* db,
+                            int obstacles_shared, double* x, double* u, double* lam, double* mu, double* T, double* obj,
+                            int32_t* status, int32_t* iters, void* cuda_stream) {
+  return solve_slot(c, 0, batch, count_dev, index_dev, x0, u0, xref, uref, T_max, term, Ts_inst, edge_ptr, A, b0, db,
+                    obstacles_shared, x, u, lam, mu, T, obj, status, iters, cuda_stream);
 }
 
 int obca_b200_solve(obca_ctx* c, int batch, const double* x0, const double* u0, const double* xref, const double* uref,
@@ -432,22 +460,59 @@ int obca_b200_solve_host(obca_ctx* c, int batch, const double* x0, const double*
   for (int i = 0; i < 10; ++i) {
     d_in[i] = n_in[i] ? d : nullptr;
     if (n_in[i] && !h_in[i]) return OBCA_E_ARG;
-    if (n_in[i] && cudaMemcpyAsync(d, h_in[i], n_in[i] * sizeof(double), cudaMemcpyHostToDevice, 0) != cudaSuccess) return OBCA_E_CUDA;
     d += n_in[i];
   }
-  for (int i = 0; i < 6; ++i) { d_out[i] = d; d += n_out[i]; }
-  int32_t* d_status = (int32_t*)d;
-  int32_t* d_iters = d_status + B;
-  int rc = obca_b200_solve(c, batch, d_in[0], d_in[1], d_in[2], d_in[3], d_in[4], d_in[5], d_in[9], edge_ptr, d_in[6], d_in[7], d_in[8],
-                           obstacles_shared, d_out[0], d_out[1], d_out[2], d_out[3], d_out[4], d_out[5], d_status, d_iters, 0);
-  if (rc != OBCA_OK) return rc;
   for (int i = 0; i < 6; ++i) {
     if (!h_out[i]) return OBCA_E_ARG;
-    if (cudaMemcpyAsync(h_out[i], d_out[i], n_out[i] * sizeof(double), cudaMemcpyDeviceToHost, 0) != cudaSuccess) return OBCA_E_CUDA;
+    d_out[i] = d; d += n_out[i];
   }
-  if (cudaMemcpyAsync(status, d_status, B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0) != cudaSuccess) return OBCA_E_CUDA;
-  if (cudaMemcpyAsync(iters, d_iters, B * sizeof(int32_t), cudaMemcpyDeviceToHost, 0) != cudaSuccess) return OBCA_E_CUDA;
-  if (cudaStreamSynchronize(0) != cudaSuccess) return OBCA_E_CUDA;
+  if (!status || !iters) return OBCA_E_ARG;
+  int32_t* d_status = (int32_t*)d;
+  int32_t* d_iters = d_status + B;
+  // A large batch goes through in chunks on separate streams: the copy-back of one chunk overlaps the solve of the next
+  // and the last blocks of one launch overlap the first of the next.  Small batches take one launch on the default stream.
+  size_t out_doubles = 0;
+  for (int i = 0; i < 6; ++i) out_doubles += n_out[i];
+  const int chunks = (B >= 2048 && out_doubles * sizeof(double) >= (8u << 20)) ? OBCA_HOST_CHUNKS : 1;
+  if (chunks > 1) {
+    c->slots = OBCA_HOST_CHUNKS;
+    for (int j = 0; j < chunks; ++j)
+      if (!c->hs[j] && cudaStreamCreateWithFlags(&c->hs[j], cudaStreamNonBlocking) != cudaSuccess) return OBCA_E_CUDA;
+  }
+  // per-instance element counts (0: absent, or shared by the batch)
+  const size_t per_in[10] = {3, 2, (N + 1) * 3, uref ? N * 2 : 0, T_max ? 1u : 0u, term ? 3u : 0u,
+                             obstacles_shared ? 0 : R * 2, obstacles_shared ? 0 : R, (db && !obstacles_shared) ? R : 0,
+                             Ts_inst ? 1u : 0u};
+  const size_t per_out[6] = {(N + 1) * 3, N * 2, (N + 1) * R, (N + 1) * 4 * no, 1, 1};
+  cudaStream_t s0 = chunks > 1 ? c->hs[0] : (cudaStream_t)0;
+  if (obstacles_shared) {
+    for (int i = 6; i <= 8; ++i)
+      if (n_in[i] && cudaMemcpyAsync(d_in[i], h_in[i], n_in[i] * sizeof(double), cudaMemcpyHostToDevice, s0) != cudaSuccess) return OBCA_E_CUDA;
+    if (chunks > 1 && cudaEventRecord(c->ev_shared, s0) != cudaSuccess) return OBCA_E_CUDA;
+  }
+  for (int j = 0; j < chunks; ++j) {
+    const size_t lo = B * j / chunks, hi = B * (j + 1) / chunks, nb = hi - lo;
+    if (nb == 0) continue;
+    cudaStream_t st = chunks > 1 ? c->hs[j] : (cudaStream_t)0;
+    if (chunks > 1 && j > 0 && obstacles_shared && cudaStreamWaitEvent(st, c->ev_shared, 0) != cudaSuccess) return OBCA_E_CUDA;
+    const double* di[10];
+    for (int i = 0; i < 10; ++i) {
+      di[i] = d_in[i] ? d_in[i] + lo * per_in[i] : nullptr;
+      if (per_in[i] && cudaMemcpyAsync(d_in[i] + lo * per_in[i], h_in[i] + lo * per_in[i], nb * per_in[i] * sizeof(double),
+                                       cudaMemcpyHostToDevice, st) != cudaSuccess) return OBCA_E_CUDA;
+    }
+    int rc = solve_slot(c, j, (int)nb, nullptr, nullptr, di[0], di[1], di[2], di[3], di[4], di[5], di[9], edge_ptr, di[6], di[7], di[8],
+                        obstacles_shared, d_out[0] + lo * per_out[0], d_out[1] + lo * per_out[1], d_out[2] + lo * per_out[2],
+                        d_out[3] + lo * per_out[3], d_out[4] + lo, d_out[5] + lo, d_status + lo, d_iters + lo, st);
+    if (rc != OBCA_OK) return rc;
+    for (int i = 0; i < 6; ++i)
+      if (cudaMemcpyAsync(h_out[i] + lo * per_out[i], d_out[i] + lo * per_out[i], nb * per_out[i] * sizeof(double),
+                          cudaMemcpyDeviceToHost, st) != cudaSuccess) return OBCA_E_CUDA;
+    if (cudaMemcpyAsync(status + lo, d_status + lo, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return OBCA_E_CUDA;
+    if (cudaMemcpyAsync(iters + lo, d_iters + lo, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return OBCA_E_CUDA;
+  }
+  for (int j = 0; j < chunks; ++j)
+    if (cudaStreamSynchronize(chunks > 1 ? c->hs[j] : (cudaStream_t)0) != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;
 }
 

@@ -64,6 +64,7 @@ struct Glob {
   double c_best_E0, c_best_f, c_thmax, c_thmin, c_dw_last;
   double c_wd_th, c_wd_ph, c_wd_dphi, c_wd_alpha, c_wd_pw_th, c_wd_pw_dphi;
   int bad;
+  int init;   // start point of the current attempt (OBCA_INIT_*; set by load, changed by the retry rule)
 };
 
 // shared-memory map of one instance; stage arrays are [element][stage], block arrays [element][block]
@@ -390,6 +391,7 @@ struct Solver {
       for (int j = 0; j < 2; ++j) G.u0[j] = kp.u0[2 * b + j];
       G.Tmax = (free_ && kp.Tmax) ? kp.Tmax[b] : 1.0;
       G.Ts = kp.Ts_inst ? kp.Ts_inst[b] : P.Ts;
+      G.init = (P.init & 15) % 3;
       G.T = 1.0; G.dT = 0.0;
       for (int j = 0; j < 3; ++j) {
         G.term[j] = (has_term && kp.term) ? kp.term[3 * b + j] : 0.0;
@@ -422,10 +424,10 @@ struct Solver {
     pp_of(k, pp);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      sm.st(sm.Z, j, k) = (k == 0) ? pp[j] : (P.init >= OBCA_INIT_XREF ? pp[j] : 0.0);
+      if (sm.G->init != OBCA_INIT_KEEP) sm.st(sm.Z, j, k) = (k == 0) ? pp[j] : (sm.G->init >= OBCA_INIT_XREF ? pp[j] : 0.0);
       sm.st(sm.YD, j, k) = 0.0;
     }
-    if (P.init == OBCA_INIT_WARM && k < N) {
+    if (sm.G->init == OBCA_INIT_WARM && k < N) {
       double pn[3];
       pp_of(k + 1, pn);
       part[0] = sqrt((pn[0] - pp[0]) * (pn[0] - pp[0]) + (pn[1] - pp[1]) * (pn[1] - pp[1]));
@@ -433,7 +435,8 @@ struct Solver {
   }
   OB_HD double start_T(double len) const {
     const Glob& G = *sm.G;
-    if (P.init != OBCA_INIT_WARM || !free_) return 1.0;
+    if (G.init == OBCA_INIT_KEEP) return free_ ? G.T : 1.0;
+    if (G.init != OBCA_INIT_WARM || !free_) return 1.0;
     double T0 = len / (N * P.uU[0] * G.Ts);
     return fmin(fmax(T0, 1.0), fmax(G.Tmax, P.T_min));
   }
@@ -443,7 +446,7 @@ struct Solver {
     if (is_stage(tid)) {
       const int k = stage_lane(tid);
       double u[2] = {0, 0};
-      if (P.init == OBCA_INIT_WARM && k < N) {
+      if (sm.G->init == OBCA_INIT_WARM && k < N) {
         const double h = (free_ ? T0 : 1.0) * G.Ts;
         double pp[3], pn[3];
         pp_of(k, pp); pp_of(k + 1, pn);
@@ -453,17 +456,18 @@ struct Solver {
         u[0] = fmin(fmax(fwd / h, P.uL[0]), P.uU[0]);
         u[1] = fmin(fmax(dth / h, P.uL[1]), P.uU[1]);
       }
-      sm.st(sm.U, 0, k) = u[0]; sm.st(sm.U, 1, k) = u[1];
+      if (G.init != OBCA_INIT_KEEP) { sm.st(sm.U, 0, k) = u[0]; sm.st(sm.U, 1, k) = u[1]; }
       if (k == 0) { G.T = T0; G.yt[0] = G.yt[1] = G.yt[2] = 0.0; }
     }
     if (is_block(tid)) {
       const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
+      br.ye[0] = br.ye[1] = 0.0;
+      if (G.init == OBCA_INIT_KEEP) return;
 #pragma unroll
       for (int j = 0; j < EMAX; ++j) br.lam[j] = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) br.mu[q] = 0.0;
-      br.ye[0] = br.ye[1] = 0.0;
-      if (P.init == OBCA_INIT_WARM) {
+      if (sm.G->init == OBCA_INIT_WARM) {
         double pp[3];
         pp_of(k, pp);
         const double ct = cos(pp[2]), st = sin(pp[2]);
@@ -1643,6 +1647,22 @@ struct Solver {
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
 //   once(f)           run f() on one thread (block-uniform shared state), visible after the next barrier
 // ======================================================================================================
+// start point of attempt a (0, 1, 2) for a context whose first choice is `base` (OBCA_INIT_RETRY, include/obca_b200.h)
+OB_HD int retry_init(int base, int a) {
+  return a == 0 ? base : (a == 1 ? (base == OBCA_INIT_WARM ? OBCA_INIT_XREF : OBCA_INIT_WARM)
+                                 : (base == OBCA_INIT_ZERO ? OBCA_INIT_XREF : OBCA_INIT_ZERO));
+}
+OB_HD bool retry_status(int st) { return st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL; }
+// Recovery sequence after a failed attempt (include/obca_b200.h, OBCA_INIT_SOFT / OBCA_INIT_RETRY): up to n soft
+// restarts from the point reached (multipliers, slacks, barrier parameter and filter start afresh), then the next
+// start point.  `seq` packs (start point index << 4 | soft restarts used); returns the next start code or -1.
+OB_HD int next_attempt(int init_word, int& seq) {
+  const int nsoft = OBCA_SOFT_RESTARTS(init_word), soft = seq & 15, a = seq >> 4;
+  if (soft < nsoft) { seq += 1; return OBCA_INIT_KEEP; }
+  if ((init_word & OBCA_INIT_RETRY) && a < 2) { seq = (a + 1) << 4; return retry_init((init_word & 15) % 3, a + 1); }
+  return -1;
+}
+
 template <int EMAX, class Exec>
 OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, int& iters_out, double& obj_out) {
   const obca_params& P = S.P;
@@ -1883,7 +1903,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   iters_out = iter;
   if (status < 0 && G.c_best_E0 < 1e300) {
     // x, u, lam, mu, T of the stored acceptable point are already in the result arrays
-    ex.once([&]() { S.kp.status[inst] = OBCA_ST_ACCEPTABLE; S.kp.iters[inst] = iter; });
+    ex.once([&]() { S.kp.status[inst] = OBCA_ST_ACCEPTABLE; });   // obj and iters: the caller (totals over the attempts)
     obj_out = G.c_best_f;
     return OBCA_ST_STORED;
   }

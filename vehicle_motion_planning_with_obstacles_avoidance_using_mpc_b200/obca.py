@@ -200,6 +200,9 @@ class obca:
     # closed_loop.py:535-544, whose poses are useless as an initial trajectory), or force INIT_ZERO / INIT_XREF / INIT_WARM
     init = None
     device = -1
+    # recovery rules standing in for IPOPT's restoration phase (soft restarts, then the other start points); OR-ed into
+    # the start point.  0 switches them off.
+    recover = _abi.RECOVER
 
     @staticmethod
     def _auto_init(xref, x0, N):
@@ -215,7 +218,8 @@ class obca:
         r = solve_batch(mode, Ts, P, Q, R, int(N), np.asarray(x0, float).reshape(1, 3), xL, xU, uL, uU,
                         np.asarray(xref, float).reshape(1, 3, int(N) + 1), int(nObs), vObs, AObs, bObs, dmin, ego,
                         np.asarray(u0, float).reshape(1, 2), terminal_set=terminal_set, uref=uref,
-                        init=self._auto_init(xref, x0, int(N)) if self.init is None else self.init, device=self.device,
+                        init=(self._auto_init(xref, x0, int(N)) if self.init is None else self.init) | self.recover,
+                        device=self.device,
                         **opts)
         self.lam, self.mu = r["lam"][0], r["mu"][0]
         self.obj, self.status, self.iters, self.T = float(r["obj"][0]), int(r["status"][0]), int(r["iters"][0]), float(r["T"][0])
