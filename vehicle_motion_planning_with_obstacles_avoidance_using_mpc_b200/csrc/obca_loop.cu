@@ -211,10 +211,12 @@ struct obca_loop {
   LoopDev d;
   obca_ctx* ctx[3];            // FREE, FIXED_SET, FIXED_NOTERM
   int32_t eptr_free[OBCA_MAX_OBS + 1], eptr_fix[OBCA_MAX_OBS + 1];
-  double *lam, *mu, *obj;
+  double *lam, *mu, *lam_free, *mu_free, *obj;
   int32_t* iters;
   void* arena;
   int k;                       // steps issued since the last reset
+  cudaStream_t side;           // the free-time solve of a step runs here, beside the fixed-time chain
+  cudaEvent_t ev_ready, ev_free;
 };
 
 extern "C" {
@@ -240,6 +242,9 @@ int obca_b200_build_rows(int batch, int n_obs, const int32_t* edge_ptr, const do
 int obca_b200_loop_destroy(obca_loop* l) {
   if (!l) return OBCA_E_ARG;
   for (int m = 0; m < 3; ++m) if (l->ctx[m]) obca_b200_destroy(l->ctx[m]);
+  if (l->side) cudaStreamDestroy(l->side);
+  if (l->ev_ready) cudaEventDestroy(l->ev_ready);
+  if (l->ev_free) cudaEventDestroy(l->ev_free);
   if (l->arena) cudaFree(l->arena);
   free(l);
   return OBCA_OK;
@@ -286,7 +291,8 @@ int obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const ob
                o_b0 = take(B * R * 8), o_db = take(B * R * 8), o_x = take(B * S1 * 3 * 8), o_u = take((size_t)B * N * 2 * 8),
                o_T = take(B * 8), o_status = take(B * 4), o_path = take((size_t)M * 3 * 8), o_As = take((size_t)(Rs + 1) * 2 * 8),
                o_bs = take((size_t)(Rs + 1) * 8), o_i0 = take(B * 4), o_i1 = take(B * 4), o_i2 = take(B * 4), o_cnt = take(16),
-               o_tot = take(32), o_lam = take(B * S1 * R * 8), o_mu = take(B * S1 * 4 * no * 8), o_obj = take(B * 8),
+               o_tot = take(32), o_lam = take(B * S1 * R * 8), o_mu = take(B * S1 * 4 * no * 8), o_lamf = take(B * S1 * R * 8),
+               o_muf = take(B * S1 * 4 * no * 8), o_obj = take(B * 8),
                o_it = take(B * 4);
   if (cudaMalloc(&l->arena, off) != cudaSuccess) { cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_NOMEM; }
   char* base = (char*)l->arena;
@@ -304,13 +310,19 @@ int obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const ob
   d.path = (double*)(base + o_path); d.A_s = (double*)(base + o_As); d.b_s = (double*)(base + o_bs);
   d.idx_free = (int32_t*)(base + o_i0); d.idx_set = (int32_t*)(base + o_i1); d.idx_fall = (int32_t*)(base + o_i2);
   d.counts = (int32_t*)(base + o_cnt); d.totals = (unsigned long long*)(base + o_tot);
-  l->lam = (double*)(base + o_lam); l->mu = (double*)(base + o_mu); l->obj = (double*)(base + o_obj); l->iters = (int32_t*)(base + o_it);
+  l->lam = (double*)(base + o_lam); l->mu = (double*)(base + o_mu);
+  l->lam_free = (double*)(base + o_lamf); l->mu_free = (double*)(base + o_muf); l->obj = (double*)(base + o_obj); l->iters = (int32_t*)(base + o_it);
   bool ok = cudaMemcpy(base + o_path, path, (size_t)M * 3 * 8, cudaMemcpyHostToDevice) == cudaSuccess;
   if (Rs > 0) {
     ok = ok && cudaMemcpy(base + o_As, A_static, (size_t)Rs * 2 * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(base + o_bs, b_static, (size_t)Rs * 8, cudaMemcpyHostToDevice) == cudaSuccess;
   }
   if (!ok) { cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&l->ev_free, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_CUDA;
+  }
   l->k = -1;
   *out = l;
   return OBCA_OK;
@@ -339,10 +351,15 @@ int obca_b200_loop_run(obca_loop* l, int n_steps, void* cuda_stream) {
   for (int s = 0; s < n_steps; ++s, ++l->k) {
     if (cudaMemsetAsync(d.counts, 0, 16, st) != cudaSuccess) return OBCA_E_CUDA;
     loop_prepare<<<blocks, 128, 0, st>>>(d, l->k);
+    // the free-time solve (its own list, its own instances) runs beside the fixed-time chain: two short launches
+    // share the GPU instead of each ending in its own tail.  The two sides write disjoint instances of x, u, T, status;
+    // their dual arrays have different row counts per instance, so the free side has its own.
+    if (cudaEventRecord(l->ev_ready, st) != cudaSuccess || cudaStreamWaitEvent(l->side, l->ev_ready, 0) != cudaSuccess) return OBCA_E_CUDA;
     int rc = obca_b200_solve_indexed(l->ctx[0], d.B, d.counts + 0, d.idx_free, d.x0, d.u0, d.xref, nullptr, d.Tmax, nullptr, d.Ts,
-                                     l->eptr_free, d.A_s, d.b_s, nullptr, 1, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status,
-                                     l->iters, st);
+                                     l->eptr_free, d.A_s, d.b_s, nullptr, 1, d.x, d.u, l->lam_free, l->mu_free, d.T, l->obj, d.status,
+                                     l->iters, l->side);
     if (rc != OBCA_OK) return rc;
+    if (cudaEventRecord(l->ev_free, l->side) != cudaSuccess) return OBCA_E_CUDA;
     rc = obca_b200_solve_indexed(l->ctx[1], d.B, d.counts + 1, d.idx_set, d.x0, d.u0, d.xref, nullptr, nullptr, d.term, d.Ts,
                                  l->eptr_fix, d.A, d.b0, d.db, 0, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status, l->iters, st);
     if (rc != OBCA_OK) return rc;
@@ -350,6 +367,7 @@ int obca_b200_loop_run(obca_loop* l, int n_steps, void* cuda_stream) {
     rc = obca_b200_solve_indexed(l->ctx[2], d.B, d.counts + 2, d.idx_fall, d.x0, d.u0, d.xref, nullptr, nullptr, nullptr, d.Ts,
                                  l->eptr_fix, d.A, d.b0, d.db, 0, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status, l->iters, st);
     if (rc != OBCA_OK) return rc;
+    if (cudaStreamWaitEvent(st, l->ev_free, 0) != cudaSuccess) return OBCA_E_CUDA;
     loop_advance<<<blocks, 128, 0, st>>>(d, l->k);
     if (cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
   }
