@@ -24,6 +24,8 @@ KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'sass__inst_executed_shared_loads', 'sass__inst_executed_shared_stores', 'sass__inst_executed_local_loads',
         'sass__inst_executed_local_stores', 'sass__inst_executed_global_loads', 'sass__inst_executed_global_stores',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'sm__icc_request_hit_rate.pct', 'gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed',
+        'gcc__average_cache_request_hit_rate.pct',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',

@@ -18,7 +18,7 @@ def main():
     starts = [f[0] for f in funcs]
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cub = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))   # the solver's
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
     lines = []; cur = None; infn = False
     for l in dis:

@@ -19,7 +19,7 @@ def main():
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    cub = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
     # instruction index -> source line, for the requested kernel
     lines = []
