@@ -91,3 +91,53 @@ def test_two_rank_gloo_equals_single_rank(B):
     for k in ("x", "u", "lam", "mu", "T", "obj", "status", "iters"):
         assert got[k].shape == ref[k].shape, k
         assert np.array_equal(got[k], ref[k]), k
+
+
+def _cl_driver(dyn):
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import closed_loop as cl, demo_setting as ds
+    s = ds.problemSetting("demo9"); s.senseDis = 8
+    return cl.ClosedLoopBatch(s, dyn, N=5, Q_free=0.5, sense=8.0, max_steps=4,
+                              solver_factory=lambda prm, ep, cap: common.OracleSolver(prm, ep, cap, nthreads=2))
+
+
+def _cl_dyn(B):
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import closed_loop as cl
+    dyn = cl.demo9_monte_carlo(B)
+    dyn[:, 1] = np.linspace(12, 24, B); dyn[:, 6] = 0          # close enough to be detected within the first steps
+    return dyn
+
+
+def _cl_worker(rank, world, port, B, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = sharding.closed_loop_sharded(_cl_driver, _cl_dyn(B), rank, world, dst=0)
+        if rank == 0:
+            q.put(out)
+        else:
+            assert out is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [5, 1])
+def test_closed_loop_shards_by_scenario(B):
+    """cfg 4 across two ranks: scenario shards run independently, one gather of the packed logs; equal to one rank
+    (B = 1: the second rank's shard is empty)"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cl_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    drv = _cl_driver(_cl_dyn(B))
+    ref = drv.run()
+    one = sharding.closed_loop_sharded(_cl_driver, _cl_dyn(B), 0, 1)
+    for k in ("traj", "mode", "x", "u", "Ts_opt", "steps", "failed", "reached"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+        assert np.array_equal(one[k], ref[k], equal_nan=True), k
+    assert got["solves"] == ref["solves"] and got["launches"] >= ref["launches"]

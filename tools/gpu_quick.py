@@ -1,5 +1,5 @@
 import os, sys, time, numpy as np
-sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))
 import obca_testlib as common
 from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om, scenario as sc
 import torch

@@ -57,8 +57,10 @@ def main():
     print("  %-10s %8s %12s %14s %14s" % ("phase", "share", "cycles/iter", "block-warp work", "stage-warp work"))
     print("  sweep sub-steps: %.1f per iteration, %.0f cycles each (stage warp, clock64 around body + warp barrier)" % (
         buf[32 + 14] / max(1, it.sum()), buf[32 + 15] / max(1, buf[32 + 14])))
+    # work columns: cycles warp 0 (a block warp) / the stage warp spent inside the phase's par() bodies, before the barrier
     for i, (n, v) in enumerate(zip(names, buf[:14])):
-        print("  %-12s %6.2f %%  %10.0f" % (n, 100.0 * v / tot, v / max(1, it.sum())))
+        print("  %-12s %6.2f %%  %10.0f %14.0f %14.0f" % (n, 100.0 * v / tot, v / max(1, it.sum()), buf[16 + i] / max(1, it.sum()),
+                                                      buf[32 + i] / max(1, it.sum()) if i < 14 else 0))
 
 
 if __name__ == "__main__":

@@ -105,3 +105,64 @@ def solve_sharded(solver, arrays, B, rank, world, device, dst=0, group=None):
         return unpack_gathered(packed, packed.buf[None], B), packed
     full = gather_packed(packed, dst=dst, group=group)
     return (unpack_gathered(packed, full, B) if full is not None else None), packed
+
+
+def closed_loop_sharded(make_driver, dyn, rank, world, dst=0, group=None, terminal_rule="shipped"):
+    """cfg 4 across ranks: scenarios are independent, so rank r runs the closed loops of its contiguous
+    shard of ``dyn`` with no per-step communication; the logs are packed into one buffer per rank and gathered once.
+
+    ``make_driver(dyn_shard)`` builds a ``ClosedLoopBatch`` / ``ClosedLoopDevice`` for that shard.  Returns the logs of
+    all scenarios in global order on ``dst`` (dict of NumPy arrays, same keys as ``ClosedLoopBatch.run``) and None
+    elsewhere."""
+    import torch
+    import torch.distributed as dist
+    dyn = np.asarray(dyn, float)
+    B = dyn.shape[0]
+    lo, hi, per = shard_range(B, rank, world)
+    o = None
+    if hi > lo:
+        drv = make_driver(dyn[lo:hi])
+        try:
+            o = drv.run(terminal_rule)
+        finally:
+            drv.close()
+    K = None if o is None else o["traj"].shape[1] - 1
+    use_cuda = world > 1 and dist.get_backend(group) == "nccl"
+    if world > 1:                      # every rank must know the log length even if its shard is empty
+        k_t = torch.tensor([K if K is not None else -1], dtype=torch.int64, device="cuda" if use_cuda else "cpu")
+        dist.all_reduce(k_t, op=dist.ReduceOp.MAX, group=group)
+        K = int(k_t[0])
+    # packed row per scenario: traj (K+1)*3 | mode K | x 3 | u 2 | Ts_opt | steps | failed | reached
+    W = (K + 1) * 3 + K + 3 + 2 + 1 + 3
+    buf = torch.zeros((per, W), dtype=torch.float64)
+    if o is not None:
+        n = hi - lo
+        cols = [o["traj"].reshape(n, -1), o["mode"].astype(float), o["x"], o["u"], o["Ts_opt"][:, None],
+                o["steps"][:, None].astype(float), o["failed"][:, None].astype(float), o["reached"][:, None].astype(float)]
+        buf[:n] = torch.as_tensor(np.concatenate(cols, axis=1))
+    counts = torch.tensor([0 if o is None else o["solves"], 0 if o is None else o["launches"]], dtype=torch.float64)
+    if world == 1:
+        full, cnt = buf[None], counts[None]
+    else:
+        send = torch.cat([buf.reshape(-1), counts])
+        if use_cuda:
+            send = send.cuda()
+        if rank == dst:
+            rows = [torch.empty_like(send) for _ in range(world)]
+            dist.gather(send, rows, dst=dst, group=group)
+            allr = torch.stack(rows).cpu()
+            full = allr[:, :-2].reshape(world, per, W); cnt = allr[:, -2:]
+        else:
+            dist.gather(send, None, dst=dst, group=group)
+            return None
+    flat = full.reshape(-1, W)[:B].numpy()
+    c = 0
+    def take(n):
+        nonlocal c
+        v = flat[:, c:c + n]; c += n
+        return v
+    out = dict(traj=take((K + 1) * 3).reshape(B, K + 1, 3).copy(), mode=np.rint(take(K)).astype(int), x=take(3).copy(),
+               u=take(2).copy(), Ts_opt=take(1)[:, 0].copy(), steps=np.rint(take(1)[:, 0]).astype(int),
+               failed=take(1)[:, 0] > 0.5, reached=take(1)[:, 0] > 0.5)
+    out["solves"] = int(cnt[:, 0].sum()); out["launches"] = int(cnt[:, 1].sum())
+    return out
