@@ -160,12 +160,6 @@ def _solve_once(p: nlp.Problem, opts=None):
         if E0 <= tol:
             status = 0
             break
-        acc_lvl = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
-        if acc_lvl:
-            if best is None or E0 < 0.1 * best[0]:  # IPOPT stores the acceptable point (here: a new copy per decade) ...
-                best = (E0, X.copy(), S.copy(), y.copy(), Z.copy())
-            if E0 < 0.5 * e_min:
-                e_min, e_min_iter = E0, it
         if E0 <= o["acceptable_tol"]:
             acc_count += 1
             if acc_count >= o["acceptable_iter"]:
@@ -190,6 +184,13 @@ def _solve_once(p: nlp.Problem, opts=None):
                 changed = True
             else:
                 break
+        # acceptable level, judged after the barrier update: the iteration that lowers mu to its final value counts
+        acc_lvl = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
+        if acc_lvl:
+            if best is None or E0 < 0.1 * best[0]:  # IPOPT stores the acceptable point (here: a new copy per decade) ...
+                best = (E0, X.copy(), S.copy(), y.copy(), Z.copy())
+            if E0 < 0.5 * e_min:
+                e_min, e_min_iter = E0, it
         if changed and filt is not None:
             filt = []
             nfilt_wr = 0

@@ -874,16 +874,6 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     double sd = fmax(s_max, (sumy + sumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, sumz / q_in) / s_max;
     E0 = fmax(fmax(e1 / sd, e2), szmax / sc);
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
-    /* acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
-     * complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of
-     * the OBCA dual polytope; same condition as at_floor below) */
-    const int acc_lvl = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
-    if (acc_lvl) {
-      /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
-       * ("Solved To Acceptable Level") */
-      if (E0 < 0.1 * best_E0) { best_E0 = E0; w->best = *it; }   /* a new copy per decade of improvement */
-      if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
-    }
     if (E0 <= P->acceptable_tol) {
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
@@ -909,6 +899,17 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       if (F.active) { F.n = 0; F.wr = 0; }
       if (assemble(p, it, v, mu, &w->q, w->blk)) { status = OBCA_ST_REGFAIL; break; }
       theta_phi(p, it, v, mu, &th, &ph0, &cmax);
+    }
+    /* acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
+     * complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of
+     * the OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the
+     * iteration that lowers mu to its final value already counts */
+    const int acc_lvl = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
+    if (acc_lvl) {
+      /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
+       * ("Solved To Acceptable Level") */
+      if (E0 < 0.1 * best_E0) { best_E0 = E0; w->best = *it; }   /* a new copy per decade of improvement */
+      if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
     }
     double tau = fmax(tau_min, 1 - mu);
     double dc = 0.0;

@@ -133,23 +133,23 @@ def test_recovery_rules_soft_restart_and_other_start_points():
     """OBCA_INIT_SOFT / OBCA_INIT_RETRY (stand-ins for IPOPT's restoration phase): instances whose line search fails
     from the A* warm start are solved after a soft restart or from another start point, in the kernel code as in the
     oracle; instances that succeed at once are untouched by the flags"""
-    b = sc.make_batch(3, 2048)
+    b = sc.make_batch(3, 8192)
     prm, a = common.batch_arrays(b)
-    idx = np.array([9, 17, 518, 631, 713, 942, 1205, 0, 1, 2])            # the first seven fail without recovery
+    idx = np.array([17, 518, 2832, 7048, 0, 1, 2])                        # the first four fail without recovery
+    nf = 4
     sub = {k: (v[idx] if (v is not None and k in ("x0", "u0", "xref", "T_max")) else v) for k, v in a.items()}
-    c0 = _oracle(prm, sub)
-    assert (c0["status"][:7] < 0).all() and (c0["status"][7:] == 0).all()
+    c0 = _oracle(prm, sub); e0 = common.emu_solve(prm, sub)
+    assert (c0["status"][:nf] < 0).all() and (c0["status"][nf:] == 0).all() and (e0["status"][:nf] < 0).all()
     prm_r, _ = common.batch_arrays(b, init=_abi.INIT_WARM | _abi.RECOVER)
     assert prm_r.init == 2 | 16 | (3 << 8)
     c = _oracle(prm_r, sub); e = common.emu_solve(prm_r, sub)
-    assert (c["status"] >= 0).sum() >= 9 and (e["status"] >= 0).sum() >= 9
+    assert (c["status"] >= 0).all() and (e["status"] >= 0).all()
     for r in (c, e):                                                       # untouched where the first attempt succeeds
-        assert np.array_equal(r["iters"][7:], c0["iters"][7:]) and np.abs(r["x"][7:] - c0["x"][7:]).max() <= 1e-9
-        assert (r["iters"][:7] > c0["iters"][:7]).all()                    # totals over the attempts
-    both = (c["status"] >= 0) & (e["status"] >= 0)
-    # recovered instances end at a local solution with a valid certificate; most at the same one in both implementations
-    same = np.abs(c["obj"][both] - e["obj"][both]) <= 1e-6 * np.abs(c["obj"][both])
+        assert np.array_equal(r["iters"][nf:], c0["iters"][nf:]) and np.abs(r["x"][nf:] - c0["x"][nf:]).max() <= 1e-9
+        assert (r["iters"][:nf] > c0["iters"][:nf]).all()                  # totals over the attempts
+    # recovered instances end at a local solution; most at the same one in both implementations
+    same = np.abs(c["obj"] - e["obj"]) <= 1e-6 * np.abs(c["obj"])
     assert same.mean() >= 0.7
     prm_s, _ = common.batch_arrays(b, soft_restarts=2)
     assert prm_s.init == 2 | (2 << 8)
-    assert (_oracle(prm_s, sub)["status"] >= 0).sum() >= 8
+    assert (_oracle(prm_s, sub)["status"] >= 0).sum() >= nf + 1

@@ -1729,20 +1729,6 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     const double sd = fmax(s_max, (Esumy + Esumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, Esumz / q_in) / s_max;
     E0 = fmax(fmax(Ee1 / sd, Ee2), Eszmax / sc);
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
-    // acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
-    // complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of the
-    // OBCA dual polytope; same condition as at_floor below)
-    const bool acc_lvl = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && Eth <= 1e-6 && E0 <= 1e-3);
-    if (acc_lvl) {
-      // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails later
-      // on.  The store goes straight to the result arrays: no on-chip copy is kept.
-      if (E0 < 0.1 * G.c_best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
-        ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
-        ex.once([&]() { G.c_best_E0 = E0; G.c_best_f = Ef; });   // after the barrier: everyone has evaluated the test
-        have_best = true;
-      }
-      if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
-    }
     if (E0 <= P.acceptable_tol) {
       if (++acc_count >= P.acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
@@ -1763,6 +1749,21 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
         changed = true;
       } else
         break;
+    }
+    // acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
+    // complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of the
+    // OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the iteration that lowers
+    // mu to its final value already counts (otherwise a point that is left again one noisy step later is never stored)
+    const bool acc_lvl = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && Eth <= 1e-6 && E0 <= 1e-3);
+    if (acc_lvl) {
+      // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails later
+      // on.  The store goes straight to the result arrays: no on-chip copy is kept.
+      if (E0 < 0.1 * G.c_best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
+        ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
+        ex.once([&]() { G.c_best_E0 = E0; G.c_best_f = Ef; });   // after the barrier: everyone has evaluated the test
+        have_best = true;
+      }
+      if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
     }
     if (changed && f_active) { f_n = 0; f_wr = 0; }
     if (changed) in_wd = 0;   // a new barrier problem: the current point becomes an ordinary iterate
