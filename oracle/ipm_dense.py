@@ -354,7 +354,7 @@ def _solve_once(p: nlp.Problem, opts=None):
         if restored:
             it += 1
             continue
-        at_floor = E0 <= o["acceptable_tol"] or (mu <= tol / 10 * (1 + 1e-12) and th <= 1e-6 and E0 <= 1e-3)
+        at_floor = E0 <= o["acceptable_tol"] or (mu <= 1e-6 and th <= 1e-6 and E0 <= 1e-3)
         if not accepted:
             status = ST_ACCEPTABLE if at_floor else ST_LSFAIL
             break

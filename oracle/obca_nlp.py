@@ -135,6 +135,30 @@ def build_problem(mode, Ts, P, Q, R, N, x0, xL, xU, uL, uU, xref, nObs, vObs, AO
                    Tmax=float(Tmax), term=term)
 
 
+def problem_from_abi(prm, edge_ptr, x0, u0, xref, A, b0, db=None, Ts=None, T_max=None, term=None, uref=None) -> Problem:
+    """A Problem from ABI-level arrays of ONE instance (include/obca_b200.h layouts: xref (N+1,3), A (R,2), b0 (R,),
+    db (R,) with b_k = b0 + k*db) and the obca_params struct - what the C oracle and the kernel are handed."""
+    N = int(prm.N)
+    ep = np.asarray(edge_ptr, int)
+    A = np.asarray(A, float); b0 = np.asarray(b0, float)
+    stacked = int(prm.mode) != MODE_FREE and db is not None
+    b = np.stack([b0 + (k * np.asarray(db, float) if stacked else 0.0) for k in range(N + 1)])
+    sym = lambda M: 0.5 * (M + M.T)
+    m = lambda v, shape: np.array(list(v), float).reshape(shape)
+    ego = m(prm.ego, 4)
+    L = ego[0] + ego[2]; W = ego[1] + ego[3]
+    free = int(prm.mode) in (MODE_FREE, MODE_FREE_STACKED)
+    return Problem(mode=int(prm.mode), N=N, Ts=float(prm.Ts if Ts is None else Ts), Q=sym(m(prm.Q, (3, 3))), P=sym(m(prm.P, (3, 3))),
+                   R1=sym(m(prm.R1, (2, 2))), R2=sym(m(prm.R2, (2, 2))), x0=np.asarray(x0, float).reshape(3),
+                   u0=np.asarray(u0, float).reshape(2), xref=np.ascontiguousarray(np.asarray(xref, float).reshape(N + 1, 3).T),
+                   uref=np.zeros((2, N)) if uref is None else np.ascontiguousarray(np.asarray(uref, float).reshape(N, 2).T),
+                   xL=m(prm.xL, 2), xU=m(prm.xU, 2), uL=m(prm.uL, 2), uU=m(prm.uU, 2), amax=m(prm.acc_max, 2),
+                   edges=np.diff(ep), A=np.tile(A[None], (N + 1, 1, 1)), b=b, dmin=float(prm.dmin),
+                   g=np.array([L / 2, W / 2, L / 2, W / 2]), off=float(L / 2 - ego[2]), tcost=tuple(prm.time_cost),
+                   Tmin=float(prm.T_min), Tmax=float(T_max) if (free and T_max is not None) else 1.0,
+                   term=None if term is None else np.asarray(term, float).reshape(3))
+
+
 class Layout:
     """Index maps of the compact NLP (variables X, equalities c, inequalities g >= 0)."""
 

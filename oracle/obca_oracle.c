@@ -1060,9 +1060,9 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     /* IPOPT returns Solved_To_Acceptable_Level when it cannot make progress from a point that meets the
      * acceptable tolerance; near a degenerate vertex of the OBCA dual polytope the step noise floor is
      * above tol, so this is how such instances end
-     * (second clause: at the final barrier parameter, primal feasible to 1e-6 and complementary, with only
+     * (second clause: barrier parameter at most 1e-6, primal feasible to 1e-6 and complementary, with only
      * the dual infeasibility sitting on the rounding-noise floor of the degenerate-vertex linear algebra) */
-    int at_floor = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
+    int at_floor = (E0 <= P->acceptable_tol) || (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3);
     if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
     if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }

@@ -132,3 +132,14 @@ def emu_solve(params, a, Ts=None, uref=None):
     if rc != 0:
         raise RuntimeError("obca_emu_solve rc=%d" % rc)
     return out
+
+
+def recovery_cases(init):
+    """tests/golden/recovery_cases.npz (closed-loop FIXED_NOTERM solves that fail from the warm start and that the
+    recovery rules solve; made by tests/golden/make_recovery_cases.py) -> (params with ``init``, ABI arrays, Ts)"""
+    d = np.load(os.path.join(GOLDEN, "recovery_cases.npz"))
+    prm = _abi.ObcaParams.from_buffer_copy(d["params"].tobytes())
+    prm.init = init
+    a = dict(x0=d["x0"], u0=d["u0"], xref=d["xref"], edge_ptr=d["edge_ptr"], A=d["A"], b0=d["b0"], db=d["db"], T_max=None,
+             term=None)
+    return prm, a, d["Ts"]

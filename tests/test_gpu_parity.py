@@ -294,20 +294,46 @@ def test_large_host_batch_goes_through_in_chunks():
 
 
 def test_recovery_rules_raise_the_success_rate():
-    """OBCA_INIT_SOFT / OBCA_INIT_RETRY on the GPU: instances that fail from the warm start are recovered as in the
-    oracle, results of the others do not change, every recovered result carries a valid certificate"""
-    B = 8192
-    b = sc.make_batch(3, B)
-    prm0, a = common.batch_arrays(b)
-    prm, _ = common.batch_arrays(b, init=_abi.INIT_WARM | _abi.RECOVER)
-    g0 = _gpu(prm0, a); g = _gpu(prm, a); c = _cpu(prm, a)
-    fail0 = g0["status"] < 0
-    assert 3 <= fail0.sum() <= 20
-    assert (g["status"] >= 0).mean() >= 0.999 and (c["status"] >= 0).mean() >= 0.999
-    assert (g["status"][fail0] >= 0).sum() >= fail0.sum() // 2
-    ok0 = ~fail0
+    """OBCA_INIT_SOFT / OBCA_INIT_RETRY on the GPU: closed-loop solves that fail from the warm start are recovered as in
+    the oracle, every recovered result carries a valid certificate; results of instances whose first attempt succeeds
+    do not change"""
+    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM)
+    prm, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.RECOVER)
+
+    def gpu(p):
+        s = obca_mod.BatchSolver(p, a["edge_ptr"], a["x0"].shape[0])
+        try:
+            return s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], Ts=Ts)
+        finally:
+            s.close()
+    from oracle import c_oracle
+    g0 = gpu(prm0); g = gpu(prm)
+    c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], Ts=Ts)
+    assert (g0["status"] < 0).sum() >= 5
+    assert (g["status"] >= 0).all() and (c["status"] >= 0).all()
+    assert (g["iters"][g0["status"] < 0] > g0["iters"][g0["status"] < 0]).all()
+    same = np.abs(g["obj"] - c["obj"]) <= 1e-6 * np.maximum(1.0, np.abs(c["obj"]))
+    assert same.mean() >= 0.5                                               # non-convex: restarts may end elsewhere
+    # certificate of every recovered result (per-instance obstacle rows)
+    ego = np.array(list(prm.ego)); L = ego[0] + ego[2]; W = ego[1] + ego[3]
+    gv = np.array([L / 2, W / 2, L / 2, W / 2]); off = L / 2 - ego[2]
+    ep = a["edge_ptr"]
+    for b_ in range(a["x0"].shape[0]):
+        for k in range(prm.N + 1):
+            bk = a["b0"][b_] + k * a["db"][b_]
+            th = g["x"][b_, k, 2]; ct, st = np.cos(th), np.sin(th)
+            tx = g["x"][b_, k, 0] + off * ct; ty = g["x"][b_, k, 1] + off * st
+            for i in range(prm.n_obs):
+                lam = g["lam"][b_, k, ep[i]:ep[i + 1]]; mu = g["mu"][b_, k, 4 * i:4 * i + 4]
+                Ai = a["A"][b_, ep[i]:ep[i + 1]]
+                a1, a2 = lam @ Ai[:, 0], lam @ Ai[:, 1]
+                assert (lam >= -1e-9).all() and (mu >= -1e-9).all() and a1 * a1 + a2 * a2 <= 1 + 1e-6
+                assert -(mu @ gv) + tx * a1 + ty * a2 - lam @ bk[ep[i]:ep[i + 1]] >= prm.dmin - 1e-6
+    # a batch that needs no recovery is untouched by the flags
+    b = sc.make_batch(3, 512)
+    p0, a3 = common.batch_arrays(b); p1, _ = common.batch_arrays(b, soft_restarts=3, retry=True)
+    r0 = _gpu(p0, a3); r1 = _gpu(p1, a3)
+    ok = r0["status"] >= 0
+    assert ok.mean() >= 0.99
     for k in ("x", "u", "T", "obj", "iters", "status"):
-        assert np.array_equal(g[k][ok0], g0[k][ok0]), k                     # first attempt succeeded: nothing changes
-    assert (g["iters"][fail0] > g0["iters"][fail0]).all()
-    _certificate(prm, a, g, b.dmin, b.ego)
-    _compare(g, c, min_ok=0.99)
+        assert np.array_equal(r0[k][ok], r1[k][ok]), k

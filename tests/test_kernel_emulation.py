@@ -130,26 +130,27 @@ def test_size_limits_and_ragged_polygons(name, sides, N, moving):
 
 
 def test_recovery_rules_soft_restart_and_other_start_points():
-    """OBCA_INIT_SOFT / OBCA_INIT_RETRY (stand-ins for IPOPT's restoration phase): instances whose line search fails
-    from the A* warm start are solved after a soft restart or from another start point, in the kernel code as in the
-    oracle; instances that succeed at once are untouched by the flags"""
-    b = sc.make_batch(3, 8192)
-    prm, a = common.batch_arrays(b)
-    idx = np.array([17, 518, 2832, 7048, 0, 1, 2])                        # the first four fail without recovery
-    nf = 4
-    sub = {k: (v[idx] if (v is not None and k in ("x0", "u0", "xref", "T_max")) else v) for k, v in a.items()}
-    c0 = _oracle(prm, sub); e0 = common.emu_solve(prm, sub)
-    assert (c0["status"][:nf] < 0).all() and (c0["status"][nf:] == 0).all() and (e0["status"][:nf] < 0).all()
-    prm_r, _ = common.batch_arrays(b, init=_abi.INIT_WARM | _abi.RECOVER)
+    """OBCA_INIT_SOFT / OBCA_INIT_RETRY (stand-ins for IPOPT's restoration phase): closed-loop solves whose line search
+    fails from the warm start are solved after a soft restart or from another start point, in the kernel code as in
+    the oracle; instances that succeed at once are untouched by the flags"""
+    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM)
+    solve = lambda prm: c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], Ts=Ts)
+    c0 = solve(prm0); e0 = common.emu_solve(prm0, a, Ts=Ts)
+    assert (c0["status"] < 0).all() and (e0["status"] < 0).sum() >= 5
+    prm_r, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.RECOVER)
     assert prm_r.init == 2 | 16 | (3 << 8)
-    c = _oracle(prm_r, sub); e = common.emu_solve(prm_r, sub)
+    c = solve(prm_r); e = common.emu_solve(prm_r, a, Ts=Ts)
     assert (c["status"] >= 0).all() and (e["status"] >= 0).all()
-    for r in (c, e):                                                       # untouched where the first attempt succeeds
-        assert np.array_equal(r["iters"][nf:], c0["iters"][nf:]) and np.abs(r["x"][nf:] - c0["x"][nf:]).max() <= 1e-9
-        assert (r["iters"][:nf] > c0["iters"][:nf]).all()                  # totals over the attempts
+    assert (c["iters"] > c0["iters"]).all()                                # totals over the attempts
     # recovered instances end at a local solution; most at the same one in both implementations
-    same = np.abs(c["obj"] - e["obj"]) <= 1e-6 * np.abs(c["obj"])
-    assert same.mean() >= 0.7
-    prm_s, _ = common.batch_arrays(b, soft_restarts=2)
-    assert prm_s.init == 2 | (2 << 8)
-    assert (_oracle(prm_s, sub)["status"] >= 0).sum() >= nf + 1
+    same = np.abs(c["obj"] - e["obj"]) <= 1e-6 * np.maximum(1.0, np.abs(c["obj"]))
+    assert same.mean() >= 0.5
+    prm_s, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.init_soft(3))
+    assert (solve(prm_s)["status"] >= 0).sum() >= 2
+    # first attempt succeeds: nothing changes
+    b = sc.make_batch(2, 6)
+    p0, a2 = common.batch_arrays(b); p1, _ = common.batch_arrays(b, soft_restarts=3, retry=True)
+    assert p1.init == prm_r.init
+    r0 = _oracle(p0, a2); r1 = _oracle(p1, a2); e1 = common.emu_solve(p1, a2)
+    assert (r0["status"] >= 0).all() and np.array_equal(r0["iters"], r1["iters"]) and np.array_equal(r0["x"], r1["x"])
+    assert np.array_equal(e1["iters"], r0["iters"])
