@@ -291,6 +291,20 @@ def test_large_host_batch_goes_through_in_chunks():
     torch.cuda.synchronize()
     assert np.array_equal(o2["x"].cpu().numpy(), h["x"])
     s.close()
+    # fixed-time mode: terminal sets, moving-obstacle increments and per-instance sampling times ride in the chunks too
+    B = 2100
+    b = sc.make_batch(5, B)
+    prm, a = common.batch_arrays(b)
+    Ts = np.linspace(1.5, 2.5, B)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], B)
+    o = s.solve(t(a["x0"]), t(a["u0"]), t(a["xref"]), t(a["A"]), t(a["b0"]), t(a["db"]), term=t(a["term"]), Ts=t(Ts))
+    torch.cuda.synchronize()
+    n0 = s.launches
+    h = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], term=a["term"], Ts=Ts)
+    assert s.launches - n0 == 4
+    for k in ("x", "u", "obj", "lam", "mu", "status", "iters"):
+        assert np.array_equal(o[k].cpu().numpy(), h[k]), k
+    s.close()
 
 
 def test_recovery_rules_raise_the_success_rate():
