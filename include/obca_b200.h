@@ -44,6 +44,9 @@ enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
  * OBCA_INIT_KEEP is that start code (internal: contexts are created with ZERO, XREF or WARM). */
 #define OBCA_INIT_KEEP 3
 #define OBCA_INIT_SOFT(n) (((n) & 15) << 8)
+/* no further pass is started once the passes of an instance add up to this many iterations (recovered instances of the
+ * closed-loop workload need 80 at the median and 216 at most; an instance that fails all twelve passes would run 350-800) */
+#define OBCA_RECOVERY_BUDGET 300
 #define OBCA_SOFT_RESTARTS(init) (((init) >> 8) & 15)
 /* per-instance status */
 enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,

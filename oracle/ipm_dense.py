@@ -82,6 +82,7 @@ def gname(lay, p, r):
     return "?"
 
 
+RECOVERY_BUDGET = 300      # OBCA_RECOVERY_BUDGET: no further pass once the passes add up to this many iterations
 _RETRY_ORDER = {"zero": ("zero", "warm", "xref"), "xref": ("xref", "warm", "zero"), "warm": ("warm", "xref", "zero")}
 
 
@@ -99,9 +100,9 @@ def solve(p: nlp.Problem, opts=None):
         for s_ in range(o["soft_restarts"] + 1):
             res = _solve_once(p, dict(o, init=init) if s_ == 0 else dict(o, init="keep", X0=res["X"]))
             total += res["iters"]
-            if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL):
+            if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL) or total >= RECOVERY_BUDGET:
                 break
-        if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL):
+        if res["status"] not in (ST_LSFAIL, ST_REGFAIL, ST_STALL) or total >= RECOVERY_BUDGET:
             break
     res["iters"] = total
     return res

@@ -1156,9 +1156,9 @@ static void* worker(void* arg) {
         p.init = s_ == 0 ? order[base][a] : OBCA_INIT_KEEP;
         st = solve_one(&p, w, &it_a, 0);
         iters += it_a;
-        if (!(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL)) break;
+        if (!(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL) || iters >= OBCA_RECOVERY_BUDGET) break;
       }
-      if (!retry || !(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL)) break;
+      if (!retry || !(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL) || iters >= OBCA_RECOVERY_BUDGET) break;
     }
     const iter_t* it = &w->it;
     for (int k = 0; k <= N; ++k) {

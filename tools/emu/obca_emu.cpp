@@ -63,7 +63,7 @@ static void run(const KParams& kp, int nwarps, int has_uref) {
       int it_a = 0;
       st = solve_instance(S, ex, (size_t)b, wd.data(), it_a, obj);
       iters += it_a;
-      if (!(P.init >> 4) || !retry_status(st)) break;
+      if (!(P.init >> 4) || !retry_status(st) || iters >= OBCA_RECOVERY_BUDGET) break;
       const int next = next_attempt(P.init, seq);
       if (next < 0) break;
       sm.G->init = next;

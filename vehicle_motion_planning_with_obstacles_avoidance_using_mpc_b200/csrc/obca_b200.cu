@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
       int it_a = 0;
       status = solve_instance(S, ex, (size_t)inst, kp.wd_buf + (size_t)blockIdx.x * kp.wd_stride, it_a, obj);
       iters += it_a;
-      if (!(kp.P.init >> 4) || !retry_status(status)) break;
+      if (!(kp.P.init >> 4) || !retry_status(status) || iters >= OBCA_RECOVERY_BUDGET) break;
       const int next = next_attempt(kp.P.init, seq);
       if (next < 0) break;
       __syncthreads();
