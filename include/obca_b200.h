@@ -182,6 +182,10 @@ typedef struct {
   double  goal_tol;        /* stop when the squared distance to the goal is below this: 0.1 (closed_loop.py:343)      */
   double  start[3];
   double  Ts0;             /* sampling time before the first free-time solve: 0.1                                     */
+  int32_t speculative;     /* != 0: run the solve without the terminal set beside the one with it on every detected
+                              scenario and take its result where the other fails (same results; worth it where the
+                              terminal-set solve mostly fails, wasteful where it mostly succeeds)                     */
+  int32_t reserved;
 } obca_loop_params;
 typedef struct obca_loop obca_loop;
 /* p_free / p_set / p_noterm: solver parameters of the three modes (n_obs = n_static, n_static+1, n_static+1).

@@ -114,3 +114,9 @@ def test_device_loop_matches_host_loop(rule):
     assert ((od["mode"] == _abi.MODE_FIXED_SET) | (od["mode"] == _abi.MODE_FIXED_NOTERM)).any()
     for k in ("traj", "steps", "failed", "mode"):
         assert np.array_equal(od[k], od2[k], equal_nan=True), k  # deterministic across runs
+    # speculative fallback: the solve without the terminal set runs beside the one with it; same results
+    sp = cl.ClosedLoopDevice(_setting(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps, speculative=True)
+    os_ = sp.run(rule); sp.close()
+    for k in ("traj", "steps", "failed", "mode", "Ts_opt"):
+        assert np.array_equal(od[k], os_[k], equal_nan=True), k
+    assert os_["solves"] == od["solves"]

@@ -61,8 +61,9 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return main_sharded(B)
     which = sys.argv[2] if len(sys.argv) > 2 else "both"
-    for kind, cls in (("host", cl.ClosedLoopBatch), ("device", cl.ClosedLoopDevice)):
-        if which not in (kind, "both"):
+    spec = lambda *a, **k: cl.ClosedLoopDevice(*a, speculative=True, **k)
+    for kind, cls in (("host", cl.ClosedLoopBatch), ("device", cl.ClosedLoopDevice), ("device, speculative fallback", spec)):
+        if which not in (kind.split(",")[0], "both"):
             continue
         s = ds.problemSetting("demo9"); s.senseDis = 8
         drv = cls(s, cl.demo9_monte_carlo(B), N=5, Q_free=0.5, sense=8.0)

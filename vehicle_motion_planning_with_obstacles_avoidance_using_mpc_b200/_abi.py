@@ -48,7 +48,7 @@ class LoopParams(C.Structure):
         ("N", C.c_int32), ("max_steps", C.c_int32), ("n_static", C.c_int32), ("rows_static", C.c_int32),
         ("path_len", C.c_int32), ("terminal_rule", C.c_int32),
         ("sense", C.c_double), ("goal", C.c_double * 2), ("goal_tol", C.c_double), ("start", C.c_double * 3),
-        ("Ts0", C.c_double),
+        ("Ts0", C.c_double), ("speculative", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -416,8 +416,12 @@ class ClosedLoopDevice(ClosedLoopBatch):
     include/obca_b200.h): scenario state, input builders, work lists and the three solver modes stay in HBM; the host
     issues the launches of all steps without waiting and reads the logs once at the end."""
 
-    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM | _abi.RECOVER, max_steps=30):
+    def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM | _abi.RECOVER, max_steps=30,
+                 speculative=False):
+        """``speculative``: solve without the terminal set beside the solve with it on every detected scenario (same
+        results as the sequential fallback; pays off where the terminal-set solve mostly fails)."""
         super().__init__(setting, dyn, N=N, Q_free=Q_free, sense=sense, device=device, init=init, max_steps=max_steps)
+        self.speculative = bool(speculative)
         self._loop = None
         self._rule = None
 
@@ -434,7 +438,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
         L = _lib.lib()
         lp = _abi.LoopParams(N=self.N, max_steps=self.max_steps, n_static=len(self.edges_s),
                              rows_static=int(sum(self.edges_s)), path_len=self.path.shape[1], terminal_rule=rule,
-                             sense=self.sense, goal_tol=0.1, Ts0=0.1)
+                             sense=self.sense, goal_tol=0.1, Ts0=0.1, speculative=int(self.speculative))
         lp.goal[0], lp.goal[1] = float(self.s.goalPose[0]), float(self.s.goalPose[1])
         for j in range(3):
             lp.start[j] = float(self.s.startPose[j])

@@ -74,6 +74,11 @@ struct LoopDev {
   // solver inputs / outputs (indexed by scenario)
   double *xref, *Tmax, *term, *A, *b0, *db, *x, *u, *T;
   int32_t* status;
+  // speculative fallback (lp.speculative): the solve without the terminal set runs beside the one with it, on every
+  // detected scenario, into its own result arrays; loop_fallback takes them where the terminal-set solve failed
+  int speculative;
+  double *x2, *u2;
+  int32_t* status2;
   // shared constants
   const double *path, *A_s, *b_s;
   // work lists
@@ -155,6 +160,7 @@ __global__ void loop_prepare(const LoopDev L, int k) {
   }
   L.cur[b] = OBCA_MODE_FIXED_SET;
   L.idx_set[atomicAdd(&L.counts[1], 1)] = b;
+  if (L.speculative) L.idx_fall[atomicAdd(&L.counts[2], 1)] = b;
 }
 
 // failures of the terminal-set solve go to the solve without it (closed_loop.py:389-395)
@@ -163,14 +169,22 @@ __global__ void loop_fallback(const LoopDev L) {
   if (b >= L.B) return;
   if (L.cur[b] == OBCA_MODE_FIXED_SET && L.status[b] < 0) {
     L.cur[b] = OBCA_MODE_FIXED_NOTERM;
-    L.idx_fall[atomicAdd(&L.counts[2], 1)] = b;
+    if (!L.speculative) { L.idx_fall[atomicAdd(&L.counts[2], 1)] = b; return; }
+    atomicAdd(&L.counts[3], 1);                                   // fallback results actually used
+    L.status[b] = L.status2[b];
+    const size_t nx = (size_t)L.S1 * 3, nu = (size_t)L.N * 2;
+    for (size_t q = 0; q < nx; ++q) L.x[b * nx + q] = L.x2[b * nx + q];
+    for (size_t q = 0; q < nu; ++q) L.u[b * nu + q] = L.u2[b * nu + q];
   }
 }
 
 // apply the first input / take the predicted state (closed_loop.py:416-419)
 __global__ void loop_advance(const LoopDev L, int k) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) for (int m = 0; m < 3; ++m) L.totals[m] += (unsigned long long)L.counts[m];
+  if (b == 0) {
+    L.totals[0] += (unsigned long long)L.counts[0]; L.totals[1] += (unsigned long long)L.counts[1];
+    L.totals[2] += (unsigned long long)L.counts[L.speculative ? 3 : 2];
+  }
   if (b >= L.B) return;
   const int mode = L.cur[b];
   if (mode < 0) return;
@@ -216,7 +230,10 @@ struct obca_loop {
   void* arena;
   int k;                       // steps issued since the last reset
   cudaStream_t side;           // the free-time solve of a step runs here, beside the fixed-time chain
-  cudaEvent_t ev_ready, ev_free;
+  cudaStream_t side2;          // speculative fallback solve
+  cudaEvent_t ev_ready, ev_free, ev_spec;
+  double *lam2, *mu2, *obj2, *T2;
+  int32_t* iters2;
 };
 
 extern "C" {
@@ -243,6 +260,8 @@ int obca_b200_loop_destroy(obca_loop* l) {
   if (!l) return OBCA_E_ARG;
   for (int m = 0; m < 3; ++m) if (l->ctx[m]) obca_b200_destroy(l->ctx[m]);
   if (l->side) cudaStreamDestroy(l->side);
+  if (l->side2) cudaStreamDestroy(l->side2);
+  if (l->ev_spec) cudaEventDestroy(l->ev_spec);
   if (l->ev_ready) cudaEventDestroy(l->ev_ready);
   if (l->ev_free) cudaEventDestroy(l->ev_free);
   if (l->arena) cudaFree(l->arena);
@@ -291,7 +310,8 @@ int obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const ob
                o_b0 = take(B * R * 8), o_db = take(B * R * 8), o_x = take(B * S1 * 3 * 8), o_u = take((size_t)B * N * 2 * 8),
                o_T = take(B * 8), o_status = take(B * 4), o_path = take((size_t)M * 3 * 8), o_As = take((size_t)(Rs + 1) * 2 * 8),
                o_bs = take((size_t)(Rs + 1) * 8), o_i0 = take(B * 4), o_i1 = take(B * 4), o_i2 = take(B * 4), o_cnt = take(16),
-               o_tot = take(32), o_lam = take(B * S1 * R * 8), o_mu = take(B * S1 * 4 * no * 8), o_lamf = take(B * S1 * R * 8),
+               o_tot = take(32), o_lam = take(B * S1 * R * 8), o_mu = take(B * S1 * 4 * no * 8), o_lamf = take(B * S1 * R * 8), o_lam2 = take(B * S1 * R * 8), o_mu2 = take(B * S1 * 4 * no * 8), o_x2 = take(B * S1 * 3 * 8),
+               o_u2 = take((size_t)B * N * 2 * 8), o_st2 = take(B * 4), o_obj2 = take(B * 8), o_it2 = take(B * 4), o_T2 = take(B * 8),
                o_muf = take(B * S1 * 4 * no * 8), o_obj = take(B * 8),
                o_it = take(B * 4);
   if (cudaMalloc(&l->arena, off) != cudaSuccess) { cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_NOMEM; }
@@ -311,7 +331,9 @@ int obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const ob
   d.idx_free = (int32_t*)(base + o_i0); d.idx_set = (int32_t*)(base + o_i1); d.idx_fall = (int32_t*)(base + o_i2);
   d.counts = (int32_t*)(base + o_cnt); d.totals = (unsigned long long*)(base + o_tot);
   l->lam = (double*)(base + o_lam); l->mu = (double*)(base + o_mu);
-  l->lam_free = (double*)(base + o_lamf); l->mu_free = (double*)(base + o_muf); l->obj = (double*)(base + o_obj); l->iters = (int32_t*)(base + o_it);
+  l->lam_free = (double*)(base + o_lamf); l->mu_free = (double*)(base + o_muf);
+  l->lam2 = (double*)(base + o_lam2); l->mu2 = (double*)(base + o_mu2); l->obj2 = (double*)(base + o_obj2); l->iters2 = (int32_t*)(base + o_it2); l->T2 = (double*)(base + o_T2);
+  d.x2 = (double*)(base + o_x2); d.u2 = (double*)(base + o_u2); d.status2 = (int32_t*)(base + o_st2); d.speculative = lp->speculative != 0; l->obj = (double*)(base + o_obj); l->iters = (int32_t*)(base + o_it);
   bool ok = cudaMemcpy(base + o_path, path, (size_t)M * 3 * 8, cudaMemcpyHostToDevice) == cudaSuccess;
   if (Rs > 0) {
     ok = ok && cudaMemcpy(base + o_As, A_static, (size_t)Rs * 2 * 8, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -320,7 +342,9 @@ int obca_b200_loop_create(obca_loop** out, int device, int n_scenarios, const ob
   if (!ok) { cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_CUDA; }
   if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&l->ev_free, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&l->ev_free, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&l->side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&l->ev_spec, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError(); obca_b200_loop_destroy(l); return OBCA_E_CUDA;
   }
   l->k = -1;
@@ -360,13 +384,24 @@ int obca_b200_loop_run(obca_loop* l, int n_steps, void* cuda_stream) {
                                      l->iters, l->side);
     if (rc != OBCA_OK) return rc;
     if (cudaEventRecord(l->ev_free, l->side) != cudaSuccess) return OBCA_E_CUDA;
+    if (d.speculative) {   // solve without the terminal set on every detected scenario, beside the solve with it
+      if (cudaStreamWaitEvent(l->side2, l->ev_ready, 0) != cudaSuccess) return OBCA_E_CUDA;
+      rc = obca_b200_solve_indexed(l->ctx[2], d.B, d.counts + 2, d.idx_fall, d.x0, d.u0, d.xref, nullptr, nullptr, nullptr, d.Ts,
+                                   l->eptr_fix, d.A, d.b0, d.db, 0, d.x2, d.u2, l->lam2, l->mu2, l->T2, l->obj2, d.status2, l->iters2,
+                                   l->side2);
+      if (rc != OBCA_OK) return rc;
+      if (cudaEventRecord(l->ev_spec, l->side2) != cudaSuccess) return OBCA_E_CUDA;
+    }
     rc = obca_b200_solve_indexed(l->ctx[1], d.B, d.counts + 1, d.idx_set, d.x0, d.u0, d.xref, nullptr, nullptr, d.term, d.Ts,
                                  l->eptr_fix, d.A, d.b0, d.db, 0, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status, l->iters, st);
     if (rc != OBCA_OK) return rc;
+    if (d.speculative && cudaStreamWaitEvent(st, l->ev_spec, 0) != cudaSuccess) return OBCA_E_CUDA;
     loop_fallback<<<blocks, 128, 0, st>>>(d);
-    rc = obca_b200_solve_indexed(l->ctx[2], d.B, d.counts + 2, d.idx_fall, d.x0, d.u0, d.xref, nullptr, nullptr, nullptr, d.Ts,
-                                 l->eptr_fix, d.A, d.b0, d.db, 0, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status, l->iters, st);
-    if (rc != OBCA_OK) return rc;
+    if (!d.speculative) {
+      rc = obca_b200_solve_indexed(l->ctx[2], d.B, d.counts + 2, d.idx_fall, d.x0, d.u0, d.xref, nullptr, nullptr, nullptr, d.Ts,
+                                   l->eptr_fix, d.A, d.b0, d.db, 0, d.x, d.u, l->lam, l->mu, d.T, l->obj, d.status, l->iters, st);
+      if (rc != OBCA_OK) return rc;
+    }
     if (cudaStreamWaitEvent(st, l->ev_free, 0) != cudaSuccess) return OBCA_E_CUDA;
     loop_advance<<<blocks, 128, 0, st>>>(d, l->k);
     if (cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
