@@ -33,6 +33,11 @@ enum { OBCA_MODE_FREE = 0, OBCA_MODE_FIXED_SET = 1, OBCA_MODE_FIXED_NOTERM = 2, 
  * 2 = A* warm start (poses from xref, T from arc length, inputs by differences, duals from the most
  * separating face) */
 enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
+/* 4 = the caller's own guess: the poses are read from the OUTPUT array x [B,N+1,3] before it is overwritten and the
+ * rest of the start point is built from them as for OBCA_INIT_WARM (a route from a global planner where xref is only
+ * start and goal - closed_loop.py:113-120 -, or the previous plan shifted by one step).  With OBCA_INIT_RETRY the
+ * other start points follow as for WARM. */
+#define OBCA_INIT_GUESS 4
 /* OR-ed into `init`: an instance whose line search, regularisation or progress fails (status -4, -2, -5: where IPOPT
  * would enter its restoration phase, which this solver does not have) is restarted from the other start points
  * (WARM -> XREF -> ZERO, XREF -> WARM -> ZERO, ZERO -> WARM -> XREF) before the failure is reported; `iters` is the
@@ -43,14 +48,25 @@ enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
  * barrier parameter and filter - at most n times per start point.  This stands in for IPOPT's restoration phase.
  * OBCA_INIT_KEEP is that start code (internal: contexts are created with ZERO, XREF or WARM). */
 #define OBCA_INIT_KEEP 3
+/* OR-ed into `init`: switch the feasibility-restoration phase off (a failed line search is then reported at once, or
+ * handed to the restart rules above) */
+#define OBCA_INIT_NORESTO 32
 #define OBCA_INIT_SOFT(n) (((n) & 15) << 8)
 /* no further pass is started once the passes of an instance add up to this many iterations (recovered instances of the
  * closed-loop workload need 80 at the median and 216 at most; an instance that fails all twelve passes would run 350-800) */
 #define OBCA_RECOVERY_BUDGET 300
 #define OBCA_SOFT_RESTARTS(init) (((init) >> 8) & 15)
 /* per-instance status */
-enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,
-       OBCA_ST_LSFAIL = -4, OBCA_ST_STALL = -5 };
+/* 0: optimality error <= tol.  1: IPOPT's "Solved To Acceptable Level" (error <= acceptable_tol for acceptable_iter
+ * iterations, or the run could not progress from such a point).  2: the run ended on the rounding-noise floor of a
+ * degenerate vertex of the OBCA dual polytope - primal infeasibility <= 1e-6, barrier parameter <= 1e-6, and only the
+ * (scaled) dual infeasibility above acceptable_tol, at most 1e-3; the objective is constant to ~10 digits there, but
+ * this is looser than anything IPOPT reports as success, hence its own code.  feas <=> status >= 0. */
+enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_FLOOR = 2, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,
+       OBCA_ST_LSFAIL = -4, OBCA_ST_STALL = -5,
+       OBCA_ST_INFEASIBLE = -6,   /* the restoration phase converged to a local minimiser of the constraint violation
+                                     that is infeasible (IPOPT: "Converged to a point of local infeasibility")       */
+       OBCA_ST_RESTOFAIL = -7 };  /* the restoration phase itself failed (IPOPT: "Restoration Failed")               */
 /* return codes */
 enum { OBCA_OK = 0, OBCA_E_ARG = -1, OBCA_E_NODEVICE = -2, OBCA_E_CUDA = -3, OBCA_E_NOMEM = -4, OBCA_E_SIZE = -5 };
 

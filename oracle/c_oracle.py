@@ -41,7 +41,7 @@ def lib():
 
 
 def solve(params, x0, u0, xref, edge_ptr, A, b0, db=None, T_max=None, term=None, uref=None, nthreads=1, trace=None,
-          Ts=None):
+          Ts=None, guess=None):
     """ABI-level arrays (see include/obca_b200.h) -> dict of outputs.  x0 (B,3), u0 (B,2), xref (B,N+1,3)."""
     L = lib()
     f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
@@ -49,7 +49,8 @@ def solve(params, x0, u0, xref, edge_ptr, A, b0, db=None, T_max=None, term=None,
     B = x0.shape[0]
     N, R, no = params.N, params.rows, params.n_obs
     shared = int(A.ndim == 2)
-    out = dict(x=np.zeros((B, N + 1, 3)), u=np.zeros((B, N, 2)), lam=np.zeros((B, N + 1, R)),
+    out = dict(x=np.zeros((B, N + 1, 3)) if guess is None else np.array(guess, dtype=np.float64).reshape(B, N + 1, 3),
+               u=np.zeros((B, N, 2)), lam=np.zeros((B, N + 1, R)),
                mu=np.zeros((B, N + 1, 4 * no)), T=np.zeros(B), obj=np.zeros(B),
                status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
     ep = np.ascontiguousarray(edge_ptr, dtype=np.int32)

@@ -108,18 +108,33 @@ def solve(p: nlp.Problem, opts=None):
     return res
 
 
-def _solve_once(p: nlp.Problem, opts=None):
+class Model:
+    """What the interior-point loop needs from an NLP: layout, evaluation, start point."""
+
+    def __init__(self, p: nlp.Problem):
+        self.p = p
+        self.lay = nlp.Layout(p)
+
+    def evaluate(self, X, y=None, zi=None, want=("f", "g", "c", "J", "d", "Jd", "W")):
+        return nlp.evaluate(self.p, self.lay, X, y, zi, want=want)
+
+    def start(self, init):
+        return nlp.start_point(self.p, self.lay, init)
+
+
+def _solve_once(p: nlp.Problem, opts=None, model=None):
     o = dict(DEFAULT_OPTS)
     if opts:
         o.update(opts)
-    lay = nlp.Layout(p)
+    model = Model(p) if model is None else model
+    lay = model.lay
     n, m, q = lay.n, lay.m, lay.q
     res = dict(status=-1, iters=0, lay=lay)
     Mw = np.zeros(n); Mw[:lay.ntraj] = 1.0
     sign_rows, sign_cols = nlp.sign_rows(p, lay)
 
-    X = np.array(o["X0"], float) if o["init"] == "keep" else nlp.start_point(p, lay, o["init"])
-    ev = nlp.evaluate(p, lay, X, want=("c", "d"))
+    X = np.array(o["X0"], float) if o["init"] == "keep" else model.start(o["init"])
+    ev = model.evaluate(X, want=("c", "d"))
     S = np.maximum(ev["d"], o["bound_push"])
     Z = np.ones(q)
     y = np.zeros(m)
@@ -145,13 +160,13 @@ def _solve_once(p: nlp.Problem, opts=None):
         return max(e1, e2, e3), (e1, e2, e3)
 
     def phi_theta(X, S, mu):
-        e = nlp.evaluate(p, lay, X, want=("f", "c", "d"))
+        e = model.evaluate(X, want=("f", "c", "d"))
         return e["f"] - mu * np.log(S).sum(), np.abs(e["c"]).sum() + np.abs(e["d"] - S).sum(), e["c"], e["d"]
 
     it = 0
     hist = []
     while True:
-        ev = nlp.evaluate(p, lay, X, y, Z)
+        ev = model.evaluate(X, y, Z)
         f, gr, c, Jm, d, Jd, W = ev["f"], ev["g"], ev["c"], ev["J"], ev["d"], ev["Jd"], ev["W"]
         E0, parts = err(gr, Jm, Jd, c, d, S, y, Z, 0.0)
         th = np.abs(c).sum() + np.abs(d - S).sum()

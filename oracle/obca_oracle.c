@@ -37,7 +37,22 @@ typedef struct {
   double Ts, Tmax, dmin, off, g[4];
   double x0[3], u0[2], term[3];
   const double *xref, *uref, *A, *b0, *db;
+  const double* guess;   /* OBCA_INIT_GUESS: the caller's poses [N+1,3] (read from the output array x before it is written) */
+  /* feasibility restoration (resto != 0): the problem solved is
+   *     min  rho sum(n) + rho sum(pt + nt) + zeta/2 |D_R ((z,u,T) - (z,u,T)_R)|^2
+   *     s.t. dynamics, OBCA equalities, sign rows as they are;  d_i(X) + n_i - S_i = 0, n_i >= 0 for the row classes in
+   *          rmask;  z_N - r_N - pt + nt = 0, pt, nt >= 0 (free modes)
+   * (IPOPT's restoration problem, Waechter & Biegler 2006 sec. 3.3, with the rows that are always consistent kept hard) */
+  int resto, rmask;
+  double rho, zeta;
+  double mu0;        /* > 0: barrier parameter this pass starts from (instead of params.mu_init)                    */
+  double th_ref;     /* restoration: violation of the original problem at the point where it was called              */
+  double zR[NS][3], uR[NS][2], TR;
 } prob_t;
+
+/* row classes that the restoration phase relaxes (bits of prob_t.rmask) */
+enum { CLS_XY = 1, CLS_UB = 2, CLS_TB = 4, CLS_TM = 8, CLS_NORM = 16, CLS_DIST = 32, CLS_SIGN = 0 };
+#define RELAXED(p, cls) ((p)->resto && ((p)->rmask & (cls)))
 
 /* iterate: primal X, slacks S, multipliers y (eq) and Z (ineq) */
 typedef struct {
@@ -48,6 +63,10 @@ typedef struct {
    * Tb [T-Tmin,Tmax-T]; tm [xN-ts0,yN-ts1,ts2-yN]; per (k,i): lam rows, mu rows, norm, dist */
   double Sxy[NS][4], Sub[NS][8], STb[2], Stm[3], Sl[NS][RM], Sm[NS][4 * OM], Sn[NS][OM], Sd[NS][OM];
   double Zxy[NS][4], Zub[NS][8], ZTb[2], Ztm[3], Zl[NS][RM], Zm[NS][4 * OM], Zn[NS][OM], Zd[NS][OM];
+  /* restoration only: relaxation n >= 0 of a row and the multiplier V of that bound; terminal equality pt, nt */
+  double nxy[NS][4], nub[NS][8], nTb[2], ntm[3], nn[NS][OM], nd[NS][OM];
+  double Vxy[NS][4], Vub[NS][8], VTb[2], Vtm[3], Vn[NS][OM], Vd[NS][OM];
+  double pt[3], nt[3], Vpt[3], Vnt[3];
 } iter_t;
 
 /* constraint values at a point */
@@ -140,36 +159,70 @@ static void eval_values(const prob_t* p, const iter_t* it, vals_t* v) {
   v->f = f;
 }
 
-/* visit every inequality: fn(ctx, d, &S, &Z) */
-#define FOR_INEQ(p, it, v, BODY)                                                                   \
+/* visit every inequality row: value d_, slack S_, multiplier Z_ and - in the restoration phase, for the relaxed row
+ * classes - the relaxation variable n_ and its bound multiplier V_ (NULL otherwise) */
+#define ROW_(cls, dv, Sp, Zp, np_, Vp, ...)                                                        \
+  { double d_ = (dv); double* S_ = (Sp); double* Z_ = (Zp);                                          \
+    double* n_ = RELAXED(p_, cls) ? (np_) : 0; double* V_ = n_ ? (Vp) : 0; (void)d_; (void)S_; (void)Z_; (void)n_; (void)V_; __VA_ARGS__ }
+#define FOR_INEQ(p, it, v, ...)                                                                     \
   do {                                                                                             \
-    int N_ = (p)->N;                                                                               \
+    const prob_t* p_ = (p);                                                                        \
+    int N_ = p_->N;                                                                                \
     for (int k = 0; k <= N_; ++k) {                                                                \
-      if (k >= 1) for (int j = 0; j < 4; ++j) { double d_ = (v)->dxy[k][j]; double* S_ = &(it)->Sxy[k][j]; double* Z_ = &(it)->Zxy[k][j]; BODY } \
-      if (k < N_) for (int j = 0; j < 8; ++j) { double d_ = (v)->dub[k][j]; double* S_ = &(it)->Sub[k][j]; double* Z_ = &(it)->Zub[k][j]; BODY } \
-      for (int r = 0; r < (p)->R; ++r) { double d_ = (it)->lam[k][r]; double* S_ = &(it)->Sl[k][r]; double* Z_ = &(it)->Zl[k][r]; BODY } \
-      for (int r = 0; r < 4 * (p)->nobs; ++r) { double d_ = (it)->mu[k][r]; double* S_ = &(it)->Sm[k][r]; double* Z_ = &(it)->Zm[k][r]; BODY } \
-      for (int i = 0; i < (p)->nobs; ++i) { double d_ = (v)->dn[k][i]; double* S_ = &(it)->Sn[k][i]; double* Z_ = &(it)->Zn[k][i]; BODY } \
-      for (int i = 0; i < (p)->nobs; ++i) { double d_ = (v)->dd[k][i]; double* S_ = &(it)->Sd[k][i]; double* Z_ = &(it)->Zd[k][i]; BODY } \
+      if (k >= 1) for (int j = 0; j < 4; ++j) ROW_(CLS_XY, (v)->dxy[k][j], &(it)->Sxy[k][j], &(it)->Zxy[k][j], &(it)->nxy[k][j], &(it)->Vxy[k][j], __VA_ARGS__) \
+      if (k < N_) for (int j = 0; j < 8; ++j) ROW_(CLS_UB, (v)->dub[k][j], &(it)->Sub[k][j], &(it)->Zub[k][j], &(it)->nub[k][j], &(it)->Vub[k][j], __VA_ARGS__) \
+      for (int r = 0; r < p_->R; ++r) ROW_(CLS_SIGN, (it)->lam[k][r], &(it)->Sl[k][r], &(it)->Zl[k][r], (double*)0, (double*)0, __VA_ARGS__) \
+      for (int r = 0; r < 4 * p_->nobs; ++r) ROW_(CLS_SIGN, (it)->mu[k][r], &(it)->Sm[k][r], &(it)->Zm[k][r], (double*)0, (double*)0, __VA_ARGS__) \
+      for (int i = 0; i < p_->nobs; ++i) ROW_(CLS_NORM, (v)->dn[k][i], &(it)->Sn[k][i], &(it)->Zn[k][i], &(it)->nn[k][i], &(it)->Vn[k][i], __VA_ARGS__) \
+      for (int i = 0; i < p_->nobs; ++i) ROW_(CLS_DIST, (v)->dd[k][i], &(it)->Sd[k][i], &(it)->Zd[k][i], &(it)->nd[k][i], &(it)->Vd[k][i], __VA_ARGS__) \
     }                                                                                              \
-    if ((p)->free_) for (int j = 0; j < 2; ++j) { double d_ = (v)->dTb[j]; double* S_ = &(it)->STb[j]; double* Z_ = &(it)->ZTb[j]; BODY } \
-    if ((p)->has_term) for (int j = 0; j < 3; ++j) { double d_ = (v)->dtm[j]; double* S_ = &(it)->Stm[j]; double* Z_ = &(it)->Ztm[j]; BODY } \
+    if (p_->free_) for (int j = 0; j < 2; ++j) ROW_(CLS_TB, (v)->dTb[j], &(it)->STb[j], &(it)->ZTb[j], &(it)->nTb[j], &(it)->VTb[j], __VA_ARGS__) \
+    if (p_->has_term) for (int j = 0; j < 3; ++j) ROW_(CLS_TM, (v)->dtm[j], &(it)->Stm[j], &(it)->Ztm[j], &(it)->ntm[j], &(it)->Vtm[j], __VA_ARGS__) \
   } while (0)
 
+/* restoration objective: rho (sum n + sum pt + sum nt) + zeta/2 |D_R ((z,u,T) - reference)|^2, D_R = min(1, 1/|reference|) */
+static double dr2(double ref) { double a = fabs(ref); return a > 1.0 ? 1.0 / (a * a) : 1.0; }
+static double resto_objective(const prob_t* p, const iter_t* it, const vals_t* v) {
+  double f = 0, sn = 0;
+  int N = p->N;
+  for (int k = 0; k <= N; ++k) {
+    if (k >= 1) for (int j = 0; j < 3; ++j) { double e = it->z[k][j] - p->zR[k][j]; f += dr2(p->zR[k][j]) * e * e; }
+    if (k < N) for (int j = 0; j < 2; ++j) { double e = it->u[k][j] - p->uR[k][j]; f += dr2(p->uR[k][j]) * e * e; }
+  }
+  if (p->free_) { double e = it->T - p->TR; f += dr2(p->TR) * e * e; }
+  iter_t* itm = (iter_t*)it;
+  FOR_INEQ(p, itm, v, { if (n_) sn += *n_; });
+  if (p->free_) for (int j = 0; j < 3; ++j) sn += it->pt[j] + it->nt[j];
+  return 0.5 * p->zeta * f + p->rho * sn;
+}
+
+/* th: constraint violation (1-norm) of the problem being solved, ph: its barrier function, cmax: max-norm violation,
+ * th_orig: violation of the ORIGINAL problem at (X, S) (what the restoration phase is there to reduce) */
 static void theta_phi(const prob_t* p, const iter_t* it, const vals_t* v, double mu, double* th, double* ph,
-                      double* cmax) {
-  double t = 0, lg = 0, cm = 0;
+                      double* cmax, double* th_orig) {
+  double t = 0, lg = 0, cm = 0, to = 0;
   int N = p->N;
   for (int k = 0; k <= N; ++k) {
     if (k < N) for (int j = 0; j < 3; ++j) { t += fabs(v->cd[k][j]); cm = fmax(cm, fabs(v->cd[k][j])); }
     for (int j = 0; j < 2 * p->nobs; ++j) { t += fabs(v->ce[k][j]); cm = fmax(cm, fabs(v->ce[k][j])); }
   }
-  if (p->free_) for (int j = 0; j < 3; ++j) { t += fabs(v->ct[j]); cm = fmax(cm, fabs(v->ct[j])); }
+  to = t;
+  if (p->free_) for (int j = 0; j < 3; ++j) {
+    double c = v->ct[j];
+    to += fabs(c);
+    if (p->resto) { c += -it->pt[j] + it->nt[j]; lg += log(it->pt[j]) + log(it->nt[j]); }
+    t += fabs(c); cm = fmax(cm, fabs(c));
+  }
   iter_t* itm = (iter_t*)it;
-  FOR_INEQ(p, itm, v, { (void)Z_; t += fabs(d_ - *S_); cm = fmax(cm, fabs(d_ - *S_)); lg += log(*S_); });
+  FOR_INEQ(p, itm, v, {
+    double r_ = d_ - *S_;
+    to += fabs(r_);
+    if (n_) { r_ += *n_; lg += log(*n_); }
+    t += fabs(r_); cm = fmax(cm, fabs(r_)); lg += log(*S_); });
   *th = t;
-  *ph = v->f - mu * lg;
+  *ph = (p->resto ? resto_objective(p, it, v) : v->f) - mu * lg;
   if (cmax) *cmax = cm;
+  if (th_orig) *th_orig = to;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -185,14 +238,15 @@ static void start_point(const prob_t* p, iter_t* it) {
   memset(it, 0, sizeof(*it));
   for (int j = 0; j < 3; ++j) it->z[0][j] = p->x0[j];
   it->T = 1.0;
+  const double* src = (init == OBCA_INIT_GUESS) ? p->guess : p->xref;   /* poses the start point is built from */
   if (init >= OBCA_INIT_XREF)
     for (int k = 1; k <= N; ++k)
-      for (int j = 0; j < 3; ++j) it->z[k][j] = p->xref[3 * k + j];
-  if (init == OBCA_INIT_WARM) {
+      for (int j = 0; j < 3; ++j) it->z[k][j] = src[3 * k + j];
+  if (init == OBCA_INIT_WARM || init == OBCA_INIT_GUESS) {
     double Pp[NS][3];
     for (int j = 0; j < 3; ++j) Pp[0][j] = p->x0[j];
     for (int k = 1; k <= N; ++k)
-      for (int j = 0; j < 3; ++j) Pp[k][j] = p->xref[3 * k + j];
+      for (int j = 0; j < 3; ++j) Pp[k][j] = src[3 * k + j];
     double len = 0;
     for (int k = 0; k < N; ++k) len += sqrt(pow(Pp[k + 1][0] - Pp[k][0], 2) + pow(Pp[k + 1][1] - Pp[k][1], 2));
     double h = p->Ts;
@@ -249,6 +303,26 @@ static void start_point(const prob_t* p, iter_t* it) {
  * spans 1e-9 .. 1e+16 near convergence and cond(M) must not be squared.
  * ---------------------------------------------------------------------------------------------- */
 #define SIG_MIN 1e-8 /* primal regularisation of the OBCA duals: curvature of a sign row is max(Z/S, SIG_MIN) */
+
+/* sigma = Z/S and the step-form right-hand side  t - Z = (mu - S Z)/S - sigma (d - S)  of one inequality */
+static void sig_t(double S, double Z, double d, double mu, double* sig, double* t) {
+  *sig = Z / S;
+  *t = (mu - S * Z) / S - (*sig) * (d - S);
+}
+/* the same for a row relaxed by the restoration phase:  d + n - S = 0, n >= 0 with cost rho n and bound multiplier V
+ * (stationarity in n: rho - Z - V = 0).  Eliminating dS, dn, dV from the Newton equations leaves
+ *     dZ = t - sigma (grad d . dX),   sigma = 1 / (S/Z + n/V),   t = -sigma [(d + n - S) + (mu - n (rho - Z))/V - (mu - S Z)/Z]
+ * which tends to the ordinary row as n -> 0 */
+static void sig_t_relaxed(double S, double Z, double n, double V, double d, double mu, double rho, double* sig, double* t) {
+  *sig = 1.0 / (S / Z + n / V);
+  *t = -(*sig) * ((d + n - S) + (mu - n * (rho - Z)) / V - (mu - S * Z) / Z);
+}
+/* steps of slack and relaxation of such a row from the step dZ of its multiplier */
+static void relaxed_steps(double S, double Z, double n, double V, double mu, double rho, double dZ, double* dS, double* dn) {
+  *dS = (mu - S * Z - S * dZ) / Z;
+  double dV = (rho - Z - V) - dZ;
+  *dn = (mu - n * V - n * dV) / V;
+}
 
 typedef struct {
   double L[5][5];                  /* R^T */
@@ -324,6 +398,26 @@ static void cn_inv(const blk_t* b, const double v[2], double o[2]) {
   o[1] = (v[1] - b->Ci[1] * b->a2 * av) * b->Ci[0];
 }
 
+/* norm and dist rows of block (k, i): sigma and step-form right-hand side (dist: divided by sigma) */
+static void rows_nd(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, double* sn, double* tn,
+                    double* sd, double* tds) {
+  double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
+  if (RELAXED(p, CLS_NORM))
+    sig_t_relaxed(Sn, Zn, it->nn[k][i], it->Vn[k][i], v->dn[k][i], mu, p->rho, sn, tn);
+  else {
+    *sn = Zn / Sn;
+    *tn = (mu - Sn * Zn) / Sn - (*sn) * (v->dn[k][i] - Sn); /* step form: t - Z */
+  }
+  if (RELAXED(p, CLS_DIST)) {
+    double t;
+    sig_t_relaxed(Sd, Zd, it->nd[k][i], it->Vd[k][i], v->dd[k][i], mu, p->rho, sd, &t);
+    *tds = t / (*sd);
+  } else {
+    *sd = Zd / Sd;
+    *tds = (mu - Sd * Zd) / Zd - (v->dd[k][i] - Sd);        /* (td - Zd) / sd */
+  }
+}
+
 /* builds the block factorisation; if Hp/rp != NULL adds this block's Schur complement to the pose
  * Hessian (3x3) and reduced gradient (3) */
 static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, blk_t* b,
@@ -345,10 +439,9 @@ static int block_setup(const prob_t* p, const iter_t* it, const vals_t* v, doubl
     for (int a = 0; a < 5; ++a) { b->g0[a] += yv[a] * t * di; yh[a] = yv[a] * sq; }
     qr5_insert(b->L, yh);
   }
-  double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
-  double sn = Zn / Sn, sd = Zd / Sd;
-  double tn = (mu - Sn * Zn) / Sn - sn * (v->dn[k][i] - Sn); /* step form: t - Z */
-  double tds = (mu - Sd * Zd) / Zd - (v->dd[k][i] - Sd);     /* (td - Zd) / sd */
+  double Zn = it->Zn[k][i], Zd = it->Zd[k][i];
+  double sn, tn, sd, tds;
+  rows_nd(p, it, v, mu, k, i, &sn, &tn, &sd, &tds);
   {
     /* Cn = 2 Zn I + 4 sn a a^T has eigenpairs (2 Zn + 4 sn |a|^2, a/|a|) and (2 Zn, a_perp); when the norm
      * row is active sn ~ 1e10 and Cn^-1 is numerically singular, so it is only ever used in this spectral
@@ -420,6 +513,7 @@ typedef struct {
   double lam[NS][RM], mu[NS][4 * OM];
   double yd[NS][3], yt[3], ye[NS][2 * OM]; /* NEW multipliers y + dy (the step is this minus y) */
   double Sxy[NS][4], Sub[NS][8], STb[2], Stm[3], Sl[NS][RM], Sm[NS][4 * OM], Sn[NS][OM], Sd[NS][OM];
+  double nxy[NS][4], nub[NS][8], nTb[2], ntm[3], nn[NS][OM], nd[NS][OM], pt[3], nt[3]; /* restoration only */
 } dir_t;
 
 static void block_backsub(const prob_t* p, const iter_t* it, const vals_t* v, double mu, int k, int i, const blk_t* b,
@@ -454,12 +548,21 @@ static void block_backsub(const prob_t* p, const iter_t* it, const vals_t* v, do
    * stationarity rows stay consistent without multiplying a rounding error by sigma; when inactive the
    * slack step comes from the primal direction.  (dZ = mu/S - Z - sigma dS is applied by the caller.) */
   double Sn = it->Sn[k][i], Zn = it->Zn[k][i], Sd = it->Sd[k][i], Zd = it->Zd[k][i];
-  double sn = Zn / Sn, sd = Zd / Sd;
+  double sn, tn, sd, tds;
+  rows_nd(p, it, v, mu, k, i, &sn, &tn, &sd, &tds);
   double ada = b->a1 * da1 + b->a2 * da2;
   if (sn >= 1.0) /* tau_a = eta_a + h_a = Cn (alpha^T dw)  =>  a . (alpha^T dw) = a . tau_a / (2 Zn + 4 sn |a|^2) */
     ada = (b->a1 * (et[0] + ht[0]) + b->a2 * (et[1] + ht[1])) / (2 * Zn + 4 * sn * (b->a1 * b->a1 + b->a2 * b->a2));
-  d->Sn[k][i] = -2 * ada + (v->dn[k][i] - Sn);
-  if (sd >= 1.0) {
+  if (RELAXED(p, CLS_NORM))
+    relaxed_steps(Sn, Zn, it->nn[k][i], it->Vn[k][i], mu, p->rho, tn - sn * (-2 * ada), &d->Sn[k][i], &d->nn[k][i]);
+  else
+    d->Sn[k][i] = -2 * ada + (v->dn[k][i] - Sn);
+  if (RELAXED(p, CLS_DIST)) {
+    double gd = qdw;                                  /* grad dist . (dw, dpose) */
+    if (k >= 1) for (int c = 0; c < 3; ++c) gd += b->dpose[c] * dp[c];
+    double dZ = (sd >= 1.0) ? -et[2] : sd * (tds - gd);
+    relaxed_steps(Sd, Zd, it->nd[k][i], it->Vd[k][i], mu, p->rho, dZ, &d->Sd[k][i], &d->nd[k][i]);
+  } else if (sd >= 1.0) {
     double dZ = -et[2];
     d->Sd[k][i] = (mu - Sd * Zd - Sd * dZ) / Zd;
   } else {
@@ -480,12 +583,8 @@ typedef struct {
   double Fth[NS][2], FT[NS][3], Bv[NS][2], Bw[NS]; /* d z+/d theta (x,y), d z+/d T, d z+/d v (x,y), d th+/d w */
 } stageqp_t;
 
-/* sigma = Z/S and the step-form right-hand side  t - Z = (mu - S Z)/S - sigma (d - S)  of one inequality */
-static void sig_t(double S, double Z, double d, double mu, double* sig, double* t) {
-  *sig = Z / S;
-  *t = (mu - S * Z) / S - (*sig) * (d - S);
-}
-
+#define SIGT(cls, S_, Z_, n_, V_, d_, sg_, t_)                                                          \
+  do { if (RELAXED(p, cls)) sig_t_relaxed(S_, Z_, n_, V_, d_, mu, p->rho, sg_, t_); else sig_t(S_, Z_, d_, mu, sg_, t_); } while (0)
 static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double mu, stageqp_t* q, blk_t (*blk)[OM]) {
   const obca_params* P = p->P;
   int N = p->N;
@@ -499,10 +598,13 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
     double* gf = q->gf[k];
     const double* z = it->z[k];
     double ct = cos(z[2]), st = sin(z[2]);
-    /* (1) tracking */
+    /* (1) tracking; restoration: proximity to the reference point instead of the objective */
     const double* M = (k < N) ? P->Q : P->P;
     double e[3];
     for (int j = 0; j < 3; ++j) e[j] = z[j] - p->xref[3 * k + j];
+    if (p->resto) {
+      if (k >= 1) for (int a = 0; a < 3; ++a) { double w_ = p->zeta * dr2(p->zR[k][a]); gf[a] += w_ * (z[a] - p->zR[k][a]); H[a][a] += w_; }
+    } else
     for (int a = 0; a < 3; ++a) {
       double s = 0;
       for (int b = 0; b < 3; ++b) {
@@ -516,6 +618,9 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
       /* (2) input cost */
       double uu[2] = {u[0], u[1]};
       if (p->uref) { uu[0] -= p->uref[2 * k]; uu[1] -= p->uref[2 * k + 1]; }
+      if (p->resto) {
+        for (int a = 0; a < 2; ++a) { double w_ = p->zeta * dr2(p->uR[k][a]); gf[6 + a] += w_ * (u[a] - p->uR[k][a]); H[6 + a][6 + a] += w_; }
+      } else
       for (int a = 0; a < 2; ++a) {
         double s = 0;
         for (int b = 0; b < 2; ++b) {
@@ -525,7 +630,7 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
         gf[6 + a] += s;
       }
       /* (3) acceleration cost between u_{k-1} (state 3,4) and u_k, k >= 1 */
-      if (k >= 1) {
+      if (k >= 1 && !p->resto) {
         double du[2] = {u[0] - it->u[k - 1][0], u[1] - it->u[k - 1][1]}, qv[2], Aacc = 0;
         for (int a = 0; a < 2; ++a) {
           qv[a] = 0;
@@ -572,14 +677,14 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
       const double* up = (k == 0) ? p->u0 : it->u[k - 1];
       for (int j = 0; j < 2; ++j) {
         double sg, t;
-        sig_t(it->Sub[k][j], it->Zub[k][j], v->dub[k][j], mu, &sg, &t);
+        SIGT(CLS_UB, it->Sub[k][j], it->Zub[k][j], it->nub[k][j], it->Vub[k][j], v->dub[k][j], &sg, &t);
         H[6 + j][6 + j] += sg; r[6 + j] += t; gL[6 + j] -= it->Zub[k][j];
-        sig_t(it->Sub[k][2 + j], it->Zub[k][2 + j], v->dub[k][2 + j], mu, &sg, &t);
+        SIGT(CLS_UB, it->Sub[k][2 + j], it->Zub[k][2 + j], it->nub[k][2 + j], it->Vub[k][2 + j], v->dub[k][2 + j], &sg, &t);
         H[6 + j][6 + j] += sg; r[6 + j] -= t; gL[6 + j] += it->Zub[k][2 + j];
         double ga = (up[j] - u[j]) / h;
         double s4, t4, s6, t6;
-        sig_t(it->Sub[k][4 + j], it->Zub[k][4 + j], v->dub[k][4 + j], mu, &s4, &t4);
-        sig_t(it->Sub[k][6 + j], it->Zub[k][6 + j], v->dub[k][6 + j], mu, &s6, &t6);
+        SIGT(CLS_UB, it->Sub[k][4 + j], it->Zub[k][4 + j], it->nub[k][4 + j], it->Vub[k][4 + j], v->dub[k][4 + j], &s4, &t4);
+        SIGT(CLS_UB, it->Sub[k][6 + j], it->Zub[k][6 + j], it->nub[k][6 + j], it->Vub[k][6 + j], v->dub[k][6 + j], &s6, &t6);
         /* Jacobian of (ga) wrt (up_j, u_j, T) */
         double jv[3] = {(k >= 1) ? 1.0 / h : 0.0, -1.0 / h, p->free_ ? -ga / T : 0.0};
         int ix[3] = {3 + j, 6 + j, 5};
@@ -604,28 +709,33 @@ static int assemble(const prob_t* p, const iter_t* it, const vals_t* v, double m
     if (k >= 1)
       for (int j = 0; j < 2; ++j) {
         double sg, t;
-        sig_t(it->Sxy[k][j], it->Zxy[k][j], v->dxy[k][j], mu, &sg, &t);
+        SIGT(CLS_XY, it->Sxy[k][j], it->Zxy[k][j], it->nxy[k][j], it->Vxy[k][j], v->dxy[k][j], &sg, &t);
         H[j][j] += sg; r[j] += t; gL[j] -= it->Zxy[k][j];
-        sig_t(it->Sxy[k][2 + j], it->Zxy[k][2 + j], v->dxy[k][2 + j], mu, &sg, &t);
+        SIGT(CLS_XY, it->Sxy[k][2 + j], it->Zxy[k][2 + j], it->nxy[k][2 + j], it->Vxy[k][2 + j], v->dxy[k][2 + j], &sg, &t);
         H[j][j] += sg; r[j] -= t; gL[j] += it->Zxy[k][2 + j];
       }
     if (k == 0 && p->free_) {
       /* (4) time cost and (8) T bounds live in stage 0 */
-      gf[5] += (N + 1) * (P->time_cost[0] + 2 * P->time_cost[1] * T);
-      H[5][5] += 2 * (N + 1) * P->time_cost[1];
+      if (p->resto) {
+        double w_ = p->zeta * dr2(p->TR);
+        gf[5] += w_ * (T - p->TR); H[5][5] += w_;
+      } else {
+        gf[5] += (N + 1) * (P->time_cost[0] + 2 * P->time_cost[1] * T);
+        H[5][5] += 2 * (N + 1) * P->time_cost[1];
+      }
       double sg, t;
-      sig_t(it->STb[0], it->ZTb[0], v->dTb[0], mu, &sg, &t);
+      SIGT(CLS_TB, it->STb[0], it->ZTb[0], it->nTb[0], it->VTb[0], v->dTb[0], &sg, &t);
       H[5][5] += sg; r[5] += t; gL[5] -= it->ZTb[0];
-      sig_t(it->STb[1], it->ZTb[1], v->dTb[1], mu, &sg, &t);
+      SIGT(CLS_TB, it->STb[1], it->ZTb[1], it->nTb[1], it->VTb[1], v->dTb[1], &sg, &t);
       H[5][5] += sg; r[5] -= t; gL[5] += it->ZTb[1];
     }
     if (k == N && p->has_term) {
       double sg, t;
-      sig_t(it->Stm[0], it->Ztm[0], v->dtm[0], mu, &sg, &t);
+      SIGT(CLS_TM, it->Stm[0], it->Ztm[0], it->ntm[0], it->Vtm[0], v->dtm[0], &sg, &t);
       H[0][0] += sg; r[0] += t; gL[0] -= it->Ztm[0];
-      sig_t(it->Stm[1], it->Ztm[1], v->dtm[1], mu, &sg, &t);
+      SIGT(CLS_TM, it->Stm[1], it->Ztm[1], it->ntm[1], it->Vtm[1], v->dtm[1], &sg, &t);
       H[1][1] += sg; r[1] += t; gL[1] -= it->Ztm[1];
-      sig_t(it->Stm[2], it->Ztm[2], v->dtm[2], mu, &sg, &t);
+      SIGT(CLS_TM, it->Stm[2], it->Ztm[2], it->ntm[2], it->Vtm[2], v->dtm[2], &sg, &t);
       H[1][1] += sg; r[1] -= t; gL[1] += it->Ztm[2];
     }
     if (k == N && p->free_) for (int j = 0; j < 3; ++j) gL[j] += it->yt[j];
@@ -653,7 +763,11 @@ typedef struct {
   double P[NS][6][6], p[NS][6], K[NS][2][6], kap[NS][2];
 } ricc_t;
 
-static int riccati(const prob_t* p, const stageqp_t* q, const vals_t* v, double dw, double dc, ricc_t* R) {
+/* terminal equality in regularised form  dz_N - dc_a dy_a = -ct_a:  the Levenberg-Marquardt folding of the ordinary
+ * iteration (dc_a = dc, ct_a = c_a) or - restoration - the elimination of pt, nt (dc_a = pt/Vpt + nt/Vnt) */
+typedef struct { double dc[3], ct[3]; } termreg_t;
+
+static int riccati(const prob_t* p, const stageqp_t* q, const vals_t* v, double dw, const termreg_t* tr, ricc_t* R) {
   int N = p->N;
   /* terminal */
   for (int a = 0; a < 6; ++a) {
@@ -663,7 +777,7 @@ static int riccati(const prob_t* p, const stageqp_t* q, const vals_t* v, double 
   for (int a = 0; a < 3; ++a) {
     R->P[N][a][a] += dw;
     /* regularised terminal equality  dz_N - dc dy = -c  =>  dy = (dz_N + c)/dc */
-    if (p->free_) { R->P[N][a][a] += 1.0 / dc; R->p[N][a] -= v->ct[a] / dc; }
+    if (p->free_) { R->P[N][a][a] += 1.0 / tr->dc[a]; R->p[N][a] -= tr->ct[a] / tr->dc[a]; }
   }
   for (int k = N - 1; k >= 0; --k) {
     /* At = [A B] (6x8): next xi = At (xi,u) + c */
@@ -722,8 +836,8 @@ static int riccati(const prob_t* p, const stageqp_t* q, const vals_t* v, double 
   return 0;
 }
 
-static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const vals_t* v, const ricc_t* R, double dc,
-                    dir_t* d) {
+static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const vals_t* v, const ricc_t* R,
+                    const termreg_t* tr, dir_t* d) {
   int N = p->N;
   double xi[6] = {0, 0, 0, 0, 0, 0};
   if (p->free_) xi[5] = R->p[0][5] / R->P[0][5][5];
@@ -752,14 +866,14 @@ static void forward(const prob_t* p, const iter_t* it, const stageqp_t* q, const
     memcpy(xi, xn, sizeof(xi));
     for (int j = 0; j < 3; ++j) d->z[k + 1][j] = xn[j];
   }
-  if (p->free_) for (int j = 0; j < 3; ++j) d->yt[j] = it->yt[j] + (d->z[N][j] + v->ct[j]) / dc;
+  if (p->free_) for (int j = 0; j < 3; ++j) d->yt[j] = it->yt[j] + (d->z[N][j] + tr->ct[j]) / tr->dc[j];
 }
 
 /* ------------------------------------------------------------------------------------------------
  * the interior-point loop (oracle/ipm_dense.py solve(), soc = False)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
-  iter_t it, tr, best, wd; /* best: stored acceptable point; wd: watchdog reference iterate */
+  iter_t it, tr, best, wd, fail; /* best: stored acceptable point; wd: watchdog reference iterate; fail: point of failure */
   vals_t v, vt;
   stageqp_t q;
   blk_t blk[NS][OM];
@@ -769,6 +883,22 @@ typedef struct {
 
 typedef void (*trace_fn)(int it, double f, double th, double E0, double mu, double dw, double alpha);
 static trace_fn g_trace = 0;
+/* restoration phase: required reduction of the violation per call (IPOPT's kappa_resto is 0.9 together with its filter;
+ * here the filter restarts, so the reduction asked for is larger), penalty rho (IPOPT: 1000), relaxed row classes
+ * (state box, terminal set, OBCA distance rows; relaxing the input / acceleration / norm rows as well made no
+ * difference on the BASELINE batches and the T bounds must stay hard - measured), rounds per attempt.
+ * The setter is a developer hook for exactly those measurements. */
+static double g_kappa_resto = 0.1, g_resto_tol = 1e-8, g_feas_tol = 1e-6, g_rho = 1000.0;
+static int g_rmask = CLS_XY | CLS_TM | CLS_DIST, g_max_resto = 4, g_post_mode = 4;
+void obca_oracle_set_resto(double kappa, double rtol, double rho, int rmask, int max_resto, int post_mode) {
+  g_kappa_resto = kappa; g_resto_tol = rtol; g_rho = rho; g_rmask = rmask; g_max_resto = max_resto; g_post_mode = post_mode;
+}
+static int g_stall_iters = 10;
+void obca_oracle_set_stall(int n) { g_stall_iters = n; }
+static int g_budget = OBCA_RECOVERY_BUDGET;
+void obca_oracle_set_budget(int n) { g_budget = n; }
+static int g_verbose = 0;
+void obca_oracle_set_verbose(int v) { g_verbose = v; }
 static int g_acc_stall = 10;                  /* iterations without halving the error at the acceptable level */
 void obca_oracle_set_acc_stall(int n) { g_acc_stall = n; }
 static int g_wd_trigger = 10, g_wd_max = 3;   /* watchdog: shortened steps before it starts / full steps on trust */
@@ -792,6 +922,18 @@ static void apply_step(const prob_t* p, const iter_t* it, const dir_t* d, double
     for (int j = 0; j < 2; ++j) o->STb[j] = it->STb[j] + a * d->STb[j];
   }
   if (p->has_term) for (int j = 0; j < 3; ++j) o->Stm[j] = it->Stm[j] + a * d->Stm[j];
+  if (p->resto) {
+    for (int k = 0; k <= N; ++k) {
+      if (k >= 1) for (int j = 0; j < 4; ++j) o->nxy[k][j] = it->nxy[k][j] + a * d->nxy[k][j];
+      if (k < N) for (int j = 0; j < 8; ++j) o->nub[k][j] = it->nub[k][j] + a * d->nub[k][j];
+      for (int i = 0; i < p->nobs; ++i) { o->nn[k][i] = it->nn[k][i] + a * d->nn[k][i]; o->nd[k][i] = it->nd[k][i] + a * d->nd[k][i]; }
+    }
+    for (int j = 0; j < 2; ++j) o->nTb[j] = it->nTb[j] + a * d->nTb[j];
+    for (int j = 0; j < 3; ++j) {
+      o->ntm[j] = it->ntm[j] + a * d->ntm[j];
+      o->pt[j] = it->pt[j] + a * d->pt[j]; o->nt[j] = it->nt[j] + a * d->nt[j];
+    }
+  }
 }
 
 static double objective_of(const prob_t* p, const iter_t* it) {
@@ -802,7 +944,7 @@ static double objective_of(const prob_t* p, const iter_t* it) {
   return f;
 }
 
-static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out) {
+static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out, double* mu_out) {
   const obca_params* P = p->P;
   int N = p->N;
   iter_t* it = &w->it;
@@ -811,19 +953,69 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   const double s_max = 100.0, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99, kappa_sigma = 1e10;
   const double dw_first = 1e-4, dw_min = 1e-20, dw_max = 1e20, kw_plus_first = 100.0, kw_plus = 8.0, kw_minus = 1.0 / 3.0;
   const double dc_min = 1e-8, lm_cap = 1e4, stall_alpha = 1e-3;
-  const int stall_iters = 10;
+  const int stall_iters = g_stall_iters;
   const double g_th = 1e-5, g_ph = 1e-8, s_th = 1.1, s_ph = 2.3, eta_ph = 1e-8;
   double tol = P->tol;
 
-  start_point(p, it);
-  eval_values(p, it, v);
-  FOR_INEQ(p, it, v, { *S_ = fmax(d_, P->bound_push); *Z_ = 1.0; });
-  double mu = P->mu_init;
+  double mu = (p->mu0 > 0) ? p->mu0 : P->mu_init;
+  if (g_verbose) fprintf(stderr, "  -- pass: resto %d init %d mu %.2e\n", p->resto, p->init, mu);
+  if (p->resto) {
+    /* restoration starts from the iterate of the failed pass (IPOPT: x, s kept; n, p on the central path of the
+     * residual they absorb so that the relaxed rows start satisfied; bound multipliers min(rho, z); y = 0) */
+    if (g_post_mode & 4) {
+      /* project the point onto the rows the restoration problem keeps hard, so that it starts feasible for its own
+       * constraints: poses by rolling the inputs out through the dynamics, OBCA duals pushed inside their sign
+       * bounds, mu_1..4 so that the two OBCA equalities hold */
+      double T = p->free_ ? it->T : 1.0, h = T * p->Ts;
+      for (int k = 0; k < N; ++k) {
+        const double* z = it->z[k];
+        it->z[k + 1][0] = z[0] + h * it->u[k][0] * cos(z[2]);
+        it->z[k + 1][1] = z[1] + h * it->u[k][0] * sin(z[2]);
+        it->z[k + 1][2] = z[2] + h * it->u[k][1];
+      }
+      for (int k = 0; k <= N; ++k) {
+        double ct = cos(it->z[k][2]), st = sin(it->z[k][2]);
+        for (int i = 0; i < p->nobs; ++i) {
+          double a1 = 0, a2 = 0;
+          for (int r = p->eptr[i]; r < p->eptr[i + 1]; ++r) {
+            it->lam[k][r] = fmax(it->lam[k][r], P->bound_push);
+            a1 += p->A[2 * r] * it->lam[k][r]; a2 += p->A[2 * r + 1] * it->lam[k][r];
+          }
+          double c1 = ct * a1 + st * a2, c2 = -st * a1 + ct * a2;
+          double* m = &it->mu[k][4 * i];
+          double b1 = fmax(fmin(m[0], m[2]), P->bound_push), b2 = fmax(fmin(m[1], m[3]), P->bound_push);
+          m[0] = b1 + fmax(-c1, 0); m[2] = b1 + fmax(c1, 0);
+          m[1] = b2 + fmax(-c2, 0); m[3] = b2 + fmax(c2, 0);
+        }
+      }
+    }
+    eval_values(p, it, v);
+    memset(it->yd, 0, sizeof(it->yd)); memset(it->yt, 0, sizeof(it->yt)); memset(it->ye, 0, sizeof(it->ye));
+    const double rho = p->rho;
+    FOR_INEQ(p, it, v, {
+      if (g_post_mode & 2) *Z_ = fmin(*Z_, rho); else { *Z_ = 1.0; *S_ = fmax(d_, P->bound_push); }
+      if (n_) {
+        double c_ = d_ - *S_, h_ = (mu - rho * c_) / (2 * rho);
+        *n_ = h_ + sqrt(h_ * h_ + mu * c_ / (2 * rho));      /* c - p + n = 0 with p n on the central path   */
+        *S_ += c_ + *n_;                                     /* the slack absorbs p (it carries no cost)       */
+        *V_ = mu / *n_;
+      } });
+    if (p->free_) for (int j = 0; j < 3; ++j) {
+      double c_ = v->ct[j], h_ = (mu - rho * c_) / (2 * rho);
+      it->nt[j] = h_ + sqrt(h_ * h_ + mu * c_ / (2 * rho));
+      it->pt[j] = c_ + it->nt[j];
+      it->Vpt[j] = mu / it->pt[j]; it->Vnt[j] = mu / it->nt[j];
+    }
+  } else {
+    start_point(p, it);
+    eval_values(p, it, v);
+    FOR_INEQ(p, it, v, { *S_ = fmax(d_, P->bound_push); *Z_ = 1.0; });
+  }
   filt_t F;
   memset(&F, 0, sizeof(F));
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
   double dw_last = 0.0, E0 = 0, best_E0 = 1e300, e_min = 1e300;
-  int e_min_iter = 0;
+  int e_min_iter = 0, best_lvl = 0;
   /* watchdog (Chamberlain et al.; IPOPT's watchdog, triggered earlier): after WD_TRIGGER consecutive shortened steps a
    * rejected full step is taken anyway from a saved reference iterate; if within WD_MAX further full steps no point
    * acceptable to the reference is reached, the reference is restored and ordinary backtracking resumes there */
@@ -832,6 +1024,14 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   double wd_th = 0, wd_ph = 0, wd_dphi = 0, wd_alpha = 1;
   int m_eq = 3 * N + (p->free_ ? 3 : 0) + 2 * p->nobs * (N + 1);
   int q_in = 4 * N + 8 * N + (p->free_ ? 2 : 0) + (p->has_term ? 3 : 0) + (p->R + 6 * p->nobs) * (N + 1);
+  if (p->resto) { /* the bounds n >= 0 (and pt, nt >= 0) count as inequalities of the restoration problem */
+    iter_t* itc = it;
+    FOR_INEQ(p, itc, v, { if (n_) q_in++; });
+    if (p->free_) q_in += 6;
+  }
+  double th_orig = 0, rs_best = 1e300;
+  int rs_iter = 0;
+  enum { RESTO_STALL = 15, RESTO_MAXITER = 200 };
 
   for (;;) {
     eval_values(p, it, v);
@@ -867,12 +1067,33 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
         }
       }
       if (p->free_) { e1 = fmax(e1, fabs(gT)); for (int j = 0; j < 3; ++j) sumy += fabs(it->yt[j]); }
-      FOR_INEQ(p, it, v, { (void)d_; sumz += *Z_; double sz = (*S_) * (*Z_); szmax = fmax(szmax, sz); szmin = fmin(szmin, sz); });
-      theta_phi(p, it, v, mu, &th, &ph0, &cmax);
+      FOR_INEQ(p, it, v, { (void)d_; sumz += *Z_; double sz = (*S_) * (*Z_); szmax = fmax(szmax, sz); szmin = fmin(szmin, sz);
+        if (n_) { sumz += *V_; sz = (*n_) * (*V_); szmax = fmax(szmax, sz); szmin = fmin(szmin, sz);
+                  e1 = fmax(e1, fabs(p->rho - *Z_ - *V_)); } });
+      if (p->resto && p->free_) for (int j = 0; j < 3; ++j) {
+        double sp = it->pt[j] * it->Vpt[j], sn_ = it->nt[j] * it->Vnt[j];
+        sumz += it->Vpt[j] + it->Vnt[j];
+        szmax = fmax(szmax, fmax(sp, sn_)); szmin = fmin(szmin, fmin(sp, sn_));
+        e1 = fmax(e1, fmax(fabs(p->rho - it->yt[j] - it->Vpt[j]), fabs(p->rho + it->yt[j] - it->Vnt[j])));
+      }
+      theta_phi(p, it, v, mu, &th, &ph0, &cmax, &th_orig);
       e2 = cmax;
     }
     double sd = fmax(s_max, (sumy + sumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, sumz / q_in) / s_max;
     E0 = fmax(fmax(e1 / sd, e2), szmax / sc);
+    if (p->resto) {
+      /* the restoration phase ends as soon as the violation of the original problem has dropped to kappa_resto times
+       * what it was (IPOPT: 0.9, plus acceptance by the filter of the original problem - here that filter starts
+       * afresh); if instead its own problem converges the point is a local minimiser of the violation */
+      if (th_orig <= fmax(g_kappa_resto * p->th_ref, g_feas_tol)) { status = OBCA_ST_OK; break; }
+      if (E0 <= fmax(tol, g_resto_tol)) { status = OBCA_ST_INFEASIBLE; break; }
+      /* the violation has stopped decreasing (1 % in RESTO_STALL iterations) although the restoration problem's own
+       * constraints hold: a local minimiser of the violation, reported as such (its dual error sits on the noise floor
+       * of the regularised steps and would never reach tol) */
+      if (th_orig < 0.99 * rs_best) { rs_best = th_orig; rs_iter = iter; }
+      if (iter - rs_iter >= RESTO_STALL && th <= 1e-6 * fmax(1.0, th_orig)) { status = OBCA_ST_INFEASIBLE; break; }
+      if (iter >= RESTO_MAXITER) { status = OBCA_ST_RESTOFAIL; break; }
+    }
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
     if (E0 <= P->acceptable_tol) {
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
@@ -894,34 +1115,43 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       } else
         break;
     }
+    if (changed && p->resto) ((prob_t*)p)->zeta = sqrt(mu);   /* IPOPT: proximity weight sqrt(mu) (the caller's copy) */
     if (changed) {
       in_wd = 0; /* a new barrier problem: the current point becomes an ordinary iterate */
       if (F.active) { F.n = 0; F.wr = 0; }
       if (assemble(p, it, v, mu, &w->q, w->blk)) { status = OBCA_ST_REGFAIL; break; }
-      theta_phi(p, it, v, mu, &th, &ph0, &cmax);
+      theta_phi(p, it, v, mu, &th, &ph0, &cmax, 0);
     }
     /* acceptable level: IPOPT's acceptable tolerance, or - at the final barrier parameter - primal feasible to 1e-6,
      * complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of
      * the OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the
      * iteration that lowers mu to its final value already counts */
-    const int acc_lvl = (E0 <= P->acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && th <= 1e-6 && E0 <= 1e-3);
-    if (acc_lvl) {
+    const int acc_lvl = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    if (acc_lvl && !p->resto) {
       /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
-       * ("Solved To Acceptable Level") */
-      if (E0 < 0.1 * best_E0) { best_E0 = E0; w->best = *it; }   /* a new copy per decade of improvement */
+       * ("Solved To Acceptable Level"); a point that only meets the noise-floor level is reported as such */
+      if (E0 < 0.1 * best_E0) { best_E0 = E0; best_lvl = acc_lvl; w->best = *it; }   /* a new copy per decade of improvement */
       if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
     }
     double tau = fmax(tau_min, 1 - mu);
-    double dc = 0.0;
-    if (p->free_) {
+    termreg_t trg;
+    memset(&trg, 0, sizeof(trg));
+    if (p->free_ && p->resto) {
+      for (int j = 0; j < 3; ++j) {
+        double pp = it->pt[j], nn_ = it->nt[j], Vp = it->Vpt[j], Vn = it->Vnt[j], y = it->yt[j];
+        trg.dc[j] = pp / Vp + nn_ / Vn;
+        trg.ct[j] = (v->ct[j] - pp + nn_) - (mu - pp * (p->rho - y)) / Vp + (mu - nn_ * (p->rho + y)) / Vn;
+      }
+    } else if (p->free_) {
       double cm = fmax(fabs(v->ct[0]), fmax(fabs(v->ct[1]), fabs(v->ct[2])));
-      dc = fmax(dc_min, cm / lm_cap);
+      double dc = fmax(dc_min, cm / lm_cap);
+      for (int j = 0; j < 3; ++j) { trg.dc[j] = dc; trg.ct[j] = v->ct[j]; }
     }
     /* inertia correction */
     double dw = 0.0;
     int regfail = 0;
     for (;;) {
-      if (riccati(p, &w->q, v, dw, dc, &w->R) == 0) break;
+      if (riccati(p, &w->q, v, dw, &trg, &w->R) == 0) break;
       if (dw == 0.0)
         dw = (dw_last == 0.0) ? dw_first : fmax(dw_min, kw_minus * dw_last);
       else
@@ -930,7 +1160,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     }
     if (regfail) { status = OBCA_ST_REGFAIL; break; }
     if (dw > 0) dw_last = dw;
-    forward(p, it, &w->q, v, &w->R, dc, d);
+    forward(p, it, &w->q, v, &w->R, &trg, d);
     /* back-substitute the blocks; slack directions */
     double Dphi = 0;
     for (int k = 0; k <= N; ++k) {
@@ -968,6 +1198,27 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       d->Stm[1] = d->z[N][1] + (v->dtm[1] - it->Stm[1]);
       d->Stm[2] = -d->z[N][1] + (v->dtm[2] - it->Stm[2]);
     }
+    if (p->resto) {
+      /* relaxed rows: the ordinary slack step above is g + (d - S) with g = grad d . dX; the row's multiplier step is
+       * dZ = t - sigma g, and slack and relaxation follow from their complementarity conditions */
+#define RELAX_FIX(cls, Sx, Zx, nx, Vx, dx, dSx, dnx)                                                  \
+      do { if (RELAXED(p, cls)) { double sg_, t_, g_ = (dSx) - ((dx) - (Sx));                          \
+        sig_t_relaxed(Sx, Zx, nx, Vx, dx, mu, p->rho, &sg_, &t_);                                      \
+        relaxed_steps(Sx, Zx, nx, Vx, mu, p->rho, t_ - sg_ * g_, &(dSx), &(dnx)); } } while (0)
+      for (int k = 0; k <= N; ++k) {
+        if (k >= 1) for (int j = 0; j < 4; ++j) RELAX_FIX(CLS_XY, it->Sxy[k][j], it->Zxy[k][j], it->nxy[k][j], it->Vxy[k][j], v->dxy[k][j], d->Sxy[k][j], d->nxy[k][j]);
+        if (k < N) for (int j = 0; j < 8; ++j) RELAX_FIX(CLS_UB, it->Sub[k][j], it->Zub[k][j], it->nub[k][j], it->Vub[k][j], v->dub[k][j], d->Sub[k][j], d->nub[k][j]);
+      }
+      if (p->free_) for (int j = 0; j < 2; ++j) RELAX_FIX(CLS_TB, it->STb[j], it->ZTb[j], it->nTb[j], it->VTb[j], v->dTb[j], d->STb[j], d->nTb[j]);
+      if (p->has_term) for (int j = 0; j < 3; ++j) RELAX_FIX(CLS_TM, it->Stm[j], it->Ztm[j], it->ntm[j], it->Vtm[j], v->dtm[j], d->Stm[j], d->ntm[j]);
+#undef RELAX_FIX
+      if (p->free_) for (int j = 0; j < 3; ++j) {
+        double dy = d->yt[j] - it->yt[j], y = it->yt[j];
+        double dVp = (p->rho - y - it->Vpt[j]) - dy, dVn = (p->rho + y - it->Vnt[j]) + dy;
+        d->pt[j] = (mu - it->pt[j] * it->Vpt[j] - it->pt[j] * dVp) / it->Vpt[j];
+        d->nt[j] = (mu - it->nt[j] * it->Vnt[j] - it->nt[j] * dVn) / it->Vnt[j];
+      }
+    }
     /* fraction to the boundary on S and Z;  dZ = mu/S - Z - Sigma dS  (not stored) */
     double a_max = 1.0, a_z = 1.0, sls = 0;
     {
@@ -990,7 +1241,61 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       if (p->free_) for (int j = 0; j < 2; ++j) STEP_INEQ(it->STb[j], it->ZTb[j], d->STb[j]);
       if (p->has_term) for (int j = 0; j < 3; ++j) STEP_INEQ(it->Stm[j], it->Ztm[j], d->Stm[j]);
     }
+    if (p->resto) {
+      /* the bounds n >= 0 and their multipliers V (dV = (rho - Z - V) - dZ); cost rho n enters the directional derivative */
+      double rdn = 0;
+#define STEP_RELAX(cls, Sx, Zx, dSx, nx, Vx, dnx)                                                      \
+      do { if (RELAXED(p, cls)) { double dZ_ = mu / (Sx) - (Zx) - ((Zx) / (Sx)) * (dSx);               \
+        double dV_ = (p->rho - (Zx) - (Vx)) - dZ_;                                                     \
+        if ((dnx) < 0) a_max = fmin(a_max, -tau * (nx) / (dnx));                                       \
+        if (dV_ < 0) a_z = fmin(a_z, -tau * (Vx) / dV_);                                               \
+        sls += (dnx) / (nx); rdn += (dnx); } } while (0)
+      for (int k = 0; k <= N; ++k) {
+        if (k >= 1) for (int j = 0; j < 4; ++j) STEP_RELAX(CLS_XY, it->Sxy[k][j], it->Zxy[k][j], d->Sxy[k][j], it->nxy[k][j], it->Vxy[k][j], d->nxy[k][j]);
+        if (k < N) for (int j = 0; j < 8; ++j) STEP_RELAX(CLS_UB, it->Sub[k][j], it->Zub[k][j], d->Sub[k][j], it->nub[k][j], it->Vub[k][j], d->nub[k][j]);
+        for (int i = 0; i < p->nobs; ++i) STEP_RELAX(CLS_NORM, it->Sn[k][i], it->Zn[k][i], d->Sn[k][i], it->nn[k][i], it->Vn[k][i], d->nn[k][i]);
+        for (int i = 0; i < p->nobs; ++i) STEP_RELAX(CLS_DIST, it->Sd[k][i], it->Zd[k][i], d->Sd[k][i], it->nd[k][i], it->Vd[k][i], d->nd[k][i]);
+      }
+      if (p->free_) for (int j = 0; j < 2; ++j) STEP_RELAX(CLS_TB, it->STb[j], it->ZTb[j], d->STb[j], it->nTb[j], it->VTb[j], d->nTb[j]);
+      if (p->has_term) for (int j = 0; j < 3; ++j) STEP_RELAX(CLS_TM, it->Stm[j], it->Ztm[j], d->Stm[j], it->ntm[j], it->Vtm[j], d->ntm[j]);
+#undef STEP_RELAX
+      if (p->free_) for (int j = 0; j < 3; ++j) {
+        double dy = d->yt[j] - it->yt[j], y = it->yt[j];
+        double dVp = (p->rho - y - it->Vpt[j]) - dy, dVn = (p->rho + y - it->Vnt[j]) + dy;
+        if (d->pt[j] < 0) a_max = fmin(a_max, -tau * it->pt[j] / d->pt[j]);
+        if (d->nt[j] < 0) a_max = fmin(a_max, -tau * it->nt[j] / d->nt[j]);
+        if (dVp < 0) a_z = fmin(a_z, -tau * it->Vpt[j] / dVp);
+        if (dVn < 0) a_z = fmin(a_z, -tau * it->Vnt[j] / dVn);
+        sls += d->pt[j] / it->pt[j] + d->nt[j] / it->nt[j]; rdn += d->pt[j] + d->nt[j];
+      }
+      Dphi += p->rho * rdn;
+    }
     Dphi -= mu * sls;
+    if (g_verbose > 1) { /* DEBUG: directional consistency of the Newton step by finite differences */
+      double eps = 1e-7;
+      apply_step(p, it, d, eps, &w->tr);
+      eval_values(p, &w->tr, &w->vt);
+      double worst[8] = {0}; const char* nm[8] = {"dyn", "e", "term", "xy", "ub", "norm", "dist", "Tb/tm"};
+      for (int k = 0; k <= N; ++k) {
+        if (k < N) for (int j = 0; j < 3; ++j) worst[0] = fmax(worst[0], fabs((w->vt.cd[k][j] - (1 - eps) * v->cd[k][j]) / eps));
+        for (int j = 0; j < 2 * p->nobs; ++j) worst[1] = fmax(worst[1], fabs((w->vt.ce[k][j] - (1 - eps) * v->ce[k][j]) / eps));
+#define RES(dv, S, n, rel) ((dv) - (S) + ((rel) ? (n) : 0.0))
+        if (k >= 1) for (int j = 0; j < 4; ++j) worst[3] = fmax(worst[3], fabs((RES(w->vt.dxy[k][j], w->tr.Sxy[k][j], w->tr.nxy[k][j], RELAXED(p, CLS_XY)) - (1 - eps) * RES(v->dxy[k][j], it->Sxy[k][j], it->nxy[k][j], RELAXED(p, CLS_XY))) / eps));
+        if (k < N) for (int j = 0; j < 8; ++j) worst[4] = fmax(worst[4], fabs((RES(w->vt.dub[k][j], w->tr.Sub[k][j], w->tr.nub[k][j], RELAXED(p, CLS_UB)) - (1 - eps) * RES(v->dub[k][j], it->Sub[k][j], it->nub[k][j], RELAXED(p, CLS_UB))) / eps));
+        for (int i = 0; i < p->nobs; ++i) {
+          worst[5] = fmax(worst[5], fabs((RES(w->vt.dn[k][i], w->tr.Sn[k][i], w->tr.nn[k][i], RELAXED(p, CLS_NORM)) - (1 - eps) * RES(v->dn[k][i], it->Sn[k][i], it->nn[k][i], RELAXED(p, CLS_NORM))) / eps));
+          worst[6] = fmax(worst[6], fabs((RES(w->vt.dd[k][i], w->tr.Sd[k][i], w->tr.nd[k][i], RELAXED(p, CLS_DIST)) - (1 - eps) * RES(v->dd[k][i], it->Sd[k][i], it->nd[k][i], RELAXED(p, CLS_DIST))) / eps));
+        }
+      }
+      if (p->free_) for (int j = 0; j < 3; ++j) {
+        double r1 = w->vt.ct[j] + (p->resto ? -w->tr.pt[j] + w->tr.nt[j] : 0), r0 = v->ct[j] + (p->resto ? -it->pt[j] + it->nt[j] : 0);
+        worst[2] = fmax(worst[2], fabs((r1 - (1 - eps) * r0) / eps));
+      }
+      fprintf(stderr, "      lin-check:");
+      for (int c = 0; c < 7; ++c) fprintf(stderr, " %s %.1e", nm[c], worst[c]);
+      double dmaxn = 0; for (int k = 0; k <= N; ++k) { for (int j = 0; j < 3; ++j) dmaxn = fmax(dmaxn, fabs(d->z[k][j])); }
+      fprintf(stderr, " |dz| %.1e dT %.1e a_max %.1e a_z %.1e Dphi %.2e\n", dmaxn, d->T, a_max, a_z, Dphi);
+    }
     if (!F.active) {
       F.thmax = 1e4 * fmax(1.0, th); F.thmin = 1e-4 * fmax(1.0, th);
       F.active = 1; F.n = 0; F.wr = 0;
@@ -1026,7 +1331,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       apply_step(p, it, d, a, &w->tr);
       eval_values(p, &w->tr, &w->vt);
       double tht, pht;
-      theta_phi(p, &w->tr, &w->vt, mu, &tht, &pht, 0);
+      theta_phi(p, &w->tr, &w->vt, mu, &tht, &pht, 0, 0);
       if (in_wd) {
         /* watchdog: only full steps, judged against the reference iterate */
         ACCEPT_TEST(accepted, tht, pht, wd_th, wd_ph, wd_dphi, wd_alpha);
@@ -1056,16 +1361,17 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     }
 #undef ACCEPT_TEST
     if (restored) { iter++; continue; }
-    if (g_trace) g_trace(iter, v->f, th, E0, mu, dw, accepted ? a : -1.0);
+    if (g_trace) g_trace(iter, p->resto ? th_orig : v->f, th, E0, mu, dw, accepted ? a : -1.0);
     /* IPOPT returns Solved_To_Acceptable_Level when it cannot make progress from a point that meets the
      * acceptable tolerance; near a degenerate vertex of the OBCA dual polytope the step noise floor is
      * above tol, so this is how such instances end
      * (second clause: barrier parameter at most 1e-6, primal feasible to 1e-6 and complementary, with only
      * the dual infeasibility sitting on the rounding-noise floor of the degenerate-vertex linear algebra) */
-    int at_floor = (E0 <= P->acceptable_tol) || (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3);
-    if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
+    int at_floor = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    if (p->resto) at_floor = 0;
+    if (!accepted) { status = at_floor ? at_floor : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
-    if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (nstall >= stall_iters) { status = at_floor ? at_floor : OBCA_ST_STALL; break; }
     if (accepted != 3) { wd_block = 0; n_short = (a < a_max) ? n_short + 1 : 0; }
     else if (!in_wd) n_short = 0;   /* watchdog succeeded */
     if (accepted == 1) {
@@ -1082,6 +1388,27 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
         Zn_ = fmin(fmax(Zn_, mu / (kappa_sigma * Sn_)), kappa_sigma * mu / Sn_); \
         (Zarr) = Zn_; } while (0)
       iter_t* tr = &w->tr; /* holds X + a dX, S + a dS of the accepted trial */
+      if (p->resto) { /* multipliers of n >= 0 first: their step needs the row's current Z */
+#define UPD_V(cls, Sx, Zx, dSx, Vx, nnew)                                                              \
+        do { if (RELAXED(p, cls)) { double dZ_ = mu / (Sx) - (Zx) - ((Zx) / (Sx)) * (dSx);             \
+          double Vn_ = (Vx) + a_z * ((p->rho - (Zx) - (Vx)) - dZ_);                                    \
+          (Vx) = fmin(fmax(Vn_, mu / (kappa_sigma * (nnew))), kappa_sigma * mu / (nnew)); } } while (0)
+        for (int k = 0; k <= N; ++k) {
+          if (k >= 1) for (int j = 0; j < 4; ++j) UPD_V(CLS_XY, it->Sxy[k][j], it->Zxy[k][j], d->Sxy[k][j], it->Vxy[k][j], tr->nxy[k][j]);
+          if (k < N) for (int j = 0; j < 8; ++j) UPD_V(CLS_UB, it->Sub[k][j], it->Zub[k][j], d->Sub[k][j], it->Vub[k][j], tr->nub[k][j]);
+          for (int i = 0; i < p->nobs; ++i) UPD_V(CLS_NORM, it->Sn[k][i], it->Zn[k][i], d->Sn[k][i], it->Vn[k][i], tr->nn[k][i]);
+          for (int i = 0; i < p->nobs; ++i) UPD_V(CLS_DIST, it->Sd[k][i], it->Zd[k][i], d->Sd[k][i], it->Vd[k][i], tr->nd[k][i]);
+        }
+        if (p->free_) for (int j = 0; j < 2; ++j) UPD_V(CLS_TB, it->STb[j], it->ZTb[j], d->STb[j], it->VTb[j], tr->nTb[j]);
+        if (p->has_term) for (int j = 0; j < 3; ++j) UPD_V(CLS_TM, it->Stm[j], it->Ztm[j], d->Stm[j], it->Vtm[j], tr->ntm[j]);
+#undef UPD_V
+        if (p->free_) for (int j = 0; j < 3; ++j) {
+          double dy = d->yt[j] - it->yt[j], y = it->yt[j];
+          double Vp = it->Vpt[j] + a_z * ((p->rho - y - it->Vpt[j]) - dy), Vn = it->Vnt[j] + a_z * ((p->rho + y - it->Vnt[j]) + dy);
+          it->Vpt[j] = fmin(fmax(Vp, mu / (kappa_sigma * tr->pt[j])), kappa_sigma * mu / tr->pt[j]);
+          it->Vnt[j] = fmin(fmax(Vn, mu / (kappa_sigma * tr->nt[j])), kappa_sigma * mu / tr->nt[j]);
+        }
+      }
       for (int k = 0; k <= N; ++k) {
         if (k >= 1) for (int j = 0; j < 4; ++j) UPD_Z(it->Sxy[k][j], it->Zxy[k][j], d->Sxy[k][j], tr->Sxy[k][j]);
         if (k < N) for (int j = 0; j < 8; ++j) UPD_Z(it->Sub[k][j], it->Zub[k][j], d->Sub[k][j], tr->Sub[k][j]);
@@ -1101,10 +1428,72 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
     }
     iter++;
   }
-  if (status < 0 && best_E0 < 1e300) { *it = w->best; status = OBCA_ST_ACCEPTABLE; E0 = best_E0; }
+  if (status < 0 && best_E0 < 1e300) { *it = w->best; status = best_lvl; E0 = best_E0; }
+  else if (status < 0 && in_wd) *it = w->wd;   /* failed on a step taken on trust: the point reached is the watchdog's reference */
   *iters_out = iter;
   if (err_out) *err_out = E0;
+  if (mu_out) *mu_out = mu;
   return status;
+}
+
+static int failed_search(int st) { return st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL; }
+/* outcomes after which another start point may still succeed (the problems are non-convex) */
+static int failed_attempt(int st) { return failed_search(st) || st == OBCA_ST_INFEASIBLE || st == OBCA_ST_RESTOFAIL; }
+
+/* One attempt = the interior-point pass and, where its line search / regularisation / progress fails, IPOPT's remedy:
+ * the feasibility-restoration phase from the point reached (same algorithm on the restoration problem, see prob_t),
+ * then the original problem again from the restored point with multipliers, slacks, barrier parameter and filter
+ * afresh.  Where the restoration phase cannot reduce the violation (a local minimiser of the violation - e.g. a
+ * predicted pose inside an obstacle, where the OBCA distance has no gradient - or its own line search fails) the fresh
+ * start is taken from the point of failure instead.  At most g_max_resto rounds, within the iteration budget; every
+ * call of the restoration phase has to get below kappa_resto times the lowest violation seen so far. */
+static int solve_attempt(const prob_t* p, work_t* w, int* iters_io, int use_resto) {
+  int it_a = 0;
+  double mu_end = 0;
+  int st = solve_one(p, w, &it_a, 0, &mu_end);
+  *iters_io += it_a;
+  if (g_verbose) fprintf(stderr, "  pass init=%d: status %d iters %d mu %.1e\n", p->init, st, it_a, mu_end);
+  double th_goal = 1e300;
+  int infeasible = 0;
+  for (int nres = 0; use_resto && failed_search(st) && nres < g_max_resto && *iters_io < g_budget; ++nres) {
+    prob_t pr = *p;
+    eval_values(p, &w->it, &w->v);
+    double th, ph, cmax, th_orig;
+    theta_phi(p, &w->it, &w->v, mu_end, &th, &ph, &cmax, &th_orig);
+    int st_r = OBCA_ST_OK;
+    it_a = 0;
+    /* called at an almost feasible point (IPOPT aborts there): nothing to restore, only the fresh start below */
+    if (th_orig > g_feas_tol) {
+      w->fail = w->it;
+      pr.resto = 1; pr.rmask = g_rmask; pr.rho = g_rho;
+      for (int k = 0; k <= p->N; ++k) {
+        for (int j = 0; j < 3; ++j) pr.zR[k][j] = w->it.z[k][j];
+        for (int j = 0; j < 2; ++j) pr.uR[k][j] = w->it.u[k][j];
+      }
+      pr.TR = w->it.T;
+      th_goal = fmin(th_goal, th_orig);
+      pr.th_ref = th_goal;
+      pr.mu0 = fmax(mu_end, cmax);
+      pr.zeta = sqrt(pr.mu0);
+      st_r = solve_one(&pr, w, &it_a, 0, 0);
+      *iters_io += it_a;
+      if (g_verbose) {
+        eval_values(p, &w->it, &w->v);
+        double th2, to2;
+        theta_phi(p, &w->it, &w->v, mu_end, &th2, &ph, &cmax, &to2);
+        fprintf(stderr, "  restoration: th_ref %.3e mu0 %.1e -> status %d iters %d th_orig %.3e\n", th_orig, pr.mu0, st_r, it_a, to2);
+      }
+      if (st_r < 0) w->it = w->fail; else th_goal *= g_kappa_resto;
+      infeasible = (st_r == OBCA_ST_INFEASIBLE);
+    }
+    prob_t pk = *p;
+    pk.init = OBCA_INIT_KEEP;
+    st = solve_one(&pk, w, &it_a, 0, &mu_end);
+    *iters_io += it_a;
+    if (g_verbose) fprintf(stderr, "  pass keep: status %d iters %d mu %.1e\n", st, it_a, mu_end);
+  }
+  if (failed_search(st) && infeasible) st = OBCA_ST_INFEASIBLE;
+  return st;
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -1147,18 +1536,20 @@ static void* worker(void* arg) {
     p.A = J->A + ob * 2 * R; p.b0 = J->b0 + ob * R; p.db = J->db ? J->db + ob * R : 0;
     /* recovery sequence (include/obca_b200.h): per start point up to n soft restarts from the point reached
      * (OBCA_INIT_SOFT), then the next start point (OBCA_INIT_RETRY) */
-    static const int order[3][3] = {{0, 2, 1}, {1, 2, 0}, {2, 1, 0}};
-    const int base = (P->init & 15) % 3, retry = (P->init & OBCA_INIT_RETRY) != 0, nsoft = OBCA_SOFT_RESTARTS(P->init);
+    static const int order[4][4] = {{0, 2, 1, -1}, {1, 2, 0, -1}, {2, 1, 0, -1}, {OBCA_INIT_GUESS, 2, 1, 0}};
+    const int has_guess = (P->init & 15) == OBCA_INIT_GUESS;
+    const int base = has_guess ? 3 : (P->init & 15) % 3, retry = (P->init & OBCA_INIT_RETRY) != 0, nsoft = OBCA_SOFT_RESTARTS(P->init);
+    double guess[NS * 3];
+    if (has_guess) { memcpy(guess, J->x + (size_t)b * 3 * (N + 1), sizeof(double) * 3 * (N + 1)); p.guess = guess; }
     int iters = 0, st = OBCA_ST_MAXITER;
-    for (int a = 0; a < 3; ++a) {
+    const int use_resto = (P->init & OBCA_INIT_NORESTO) == 0;
+    for (int a = 0; a < 4 && order[base][a] >= 0; ++a) {
       for (int s_ = 0; s_ <= nsoft; ++s_) {
-        int it_a = 0;
         p.init = s_ == 0 ? order[base][a] : OBCA_INIT_KEEP;
-        st = solve_one(&p, w, &it_a, 0);
-        iters += it_a;
-        if (!(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL) || iters >= OBCA_RECOVERY_BUDGET) break;
+        st = solve_attempt(&p, w, &iters, use_resto);
+        if (!failed_attempt(st) || iters >= g_budget) break;
       }
-      if (!retry || !(st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL) || iters >= OBCA_RECOVERY_BUDGET) break;
+      if (!retry || !failed_attempt(st) || iters >= g_budget) break;
     }
     const iter_t* it = &w->it;
     for (int k = 0; k <= N; ++k) {

@@ -17,7 +17,9 @@ MODE_FREE_STACKED = 3  # obca2, fixtime == 0  obca.py:338-629
 MODE_FIXED_OBCA2 = 4   # obca2, fixtime == 1  (terminal_set optional)
 
 INIT_ZERO, INIT_XREF, INIT_WARM = 0, 1, 2
+INIT_GUESS = 4                        # OBCA_INIT_GUESS: poses of the start point are read from the output array x
 INIT_RETRY = 16                       # OBCA_INIT_RETRY: failed attempts restart from the other start points
+INIT_NORESTO = 32                     # OBCA_INIT_NORESTO: no feasibility-restoration phase
 RECOVER = INIT_RETRY | (3 << 8)       # + OBCA_INIT_SOFT(3): what the receding-horizon drivers and `obca` use
 
 
@@ -26,6 +28,8 @@ def init_soft(n):
     return (int(n) & 15) << 8
 
 ST_OK, ST_ACCEPTABLE, ST_MAXITER, ST_REGFAIL, ST_EMPTYBOX, ST_LSFAIL, ST_STALL = 0, 1, -1, -2, -3, -4, -5
+ST_INFEASIBLE, ST_RESTOFAIL = -6, -7
+ST_FLOOR = 2                          # ended on the rounding-noise floor (see include/obca_b200.h)
 
 MAX_STAGES, MAX_OBS, MAX_ROWS = 32, 12, 48
 

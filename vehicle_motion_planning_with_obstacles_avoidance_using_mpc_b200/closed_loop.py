@@ -311,7 +311,7 @@ class ClosedLoopBatch:
     def _init_of(self, mode):
         """The terminal-set solve has its own fallback (the solve without the set, closed_loop.py:389-395) and is often
         truly infeasible: it runs without the recovery rules; the other two modes keep them."""
-        return (self.init & 15) if mode == _abi.MODE_FIXED_SET else self.init
+        return ((self.init & 15) | _abi.INIT_NORESTO) if mode == _abi.MODE_FIXED_SET else self.init
 
     def close(self):
         for s, _ in self._solvers.values():
