@@ -1019,7 +1019,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
   /* watchdog (Chamberlain et al.; IPOPT's watchdog, triggered earlier): after WD_TRIGGER consecutive shortened steps a
    * rejected full step is taken anyway from a saved reference iterate; if within WD_MAX further full steps no point
    * acceptable to the reference is reached, the reference is restored and ordinary backtracking resumes there */
-  const int WD_TRIGGER = g_wd_trigger, WD_MAX = g_wd_max;
+  const int WD_TRIGGER = g_wd_trigger, WD_MAX = p->resto ? 0 : g_wd_max;   /* no watchdog in the restoration pass */
   int in_wd = 0, wd_count = 0, wd_block = 0, n_short = 0;
   double wd_th = 0, wd_ph = 0, wd_dphi = 0, wd_alpha = 1;
   int m_eq = 3 * N + (p->free_ ? 3 : 0) + 2 * p->nobs * (N + 1);
@@ -1093,12 +1093,13 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       if (th_orig < 0.99 * rs_best) { rs_best = th_orig; rs_iter = iter; }
       if (iter - rs_iter >= RESTO_STALL && th <= 1e-6 * fmax(1.0, th_orig)) { status = OBCA_ST_INFEASIBLE; break; }
       if (iter >= RESTO_MAXITER) { status = OBCA_ST_RESTOFAIL; break; }
-    }
+    } else {
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
     if (E0 <= P->acceptable_tol) {
       if (++acc_count >= P->acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
       acc_count = 0;
+    }
     /* stall at the acceptable level: an acceptable point is stored, the barrier parameter is final and the error has
      * not halved for ACC_STALL iterations - the iterate is wandering on the noise floor (objective constant to 10
      * digits).  End like IPOPT does when it cannot progress from an acceptable point: with the stored point. */
@@ -1115,7 +1116,6 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
       } else
         break;
     }
-    if (changed && p->resto) ((prob_t*)p)->zeta = sqrt(mu);   /* IPOPT: proximity weight sqrt(mu) (the caller's copy) */
     if (changed) {
       in_wd = 0; /* a new barrier problem: the current point becomes an ordinary iterate */
       if (F.active) { F.n = 0; F.wr = 0; }

@@ -307,12 +307,12 @@ def test_large_host_batch_goes_through_in_chunks():
     s.close()
 
 
-def test_recovery_rules_raise_the_success_rate():
-    """OBCA_INIT_SOFT / OBCA_INIT_RETRY on the GPU: closed-loop solves that fail from the warm start are recovered as in
-    the oracle, every recovered result carries a valid certificate; results of instances whose first attempt succeeds
-    do not change"""
-    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM)
-    prm, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.RECOVER)
+def test_restoration_phase_raises_the_success_rate():
+    """The feasibility-restoration phase on the GPU: closed-loop solves whose line search fails from the warm start
+    (status -4 with the phase switched off) are solved as in the oracle, every result carries a valid certificate;
+    results of instances whose first pass succeeds do not change under the recovery flags"""
+    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM | _abi.INIT_NORESTO)
+    prm, _, _ = common.recovery_cases(_abi.INIT_WARM)
 
     def gpu(p):
         s = obca_mod.BatchSolver(p, a["edge_ptr"], a["x0"].shape[0])
@@ -323,11 +323,11 @@ def test_recovery_rules_raise_the_success_rate():
     from oracle import c_oracle
     g0 = gpu(prm0); g = gpu(prm)
     c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], Ts=Ts)
-    assert (g0["status"] < 0).sum() >= 5
+    assert (g0["status"] == -4).all()
     assert (g["status"] >= 0).all() and (c["status"] >= 0).all()
-    assert (g["iters"][g0["status"] < 0] > g0["iters"][g0["status"] < 0]).all()
+    assert (g["iters"] > g0["iters"]).all()
     same = np.abs(g["obj"] - c["obj"]) <= 1e-6 * np.maximum(1.0, np.abs(c["obj"]))
-    assert same.mean() >= 0.5                                               # non-convex: restarts may end elsewhere
+    assert same.mean() >= 0.8, (g["obj"], c["obj"])                         # non-convex: a restart may end elsewhere
     # certificate of every recovered result (per-instance obstacle rows)
     ego = np.array(list(prm.ego)); L = ego[0] + ego[2]; W = ego[1] + ego[3]
     gv = np.array([L / 2, W / 2, L / 2, W / 2]); off = L / 2 - ego[2]

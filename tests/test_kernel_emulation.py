@@ -107,7 +107,8 @@ def test_stall_at_acceptable_level():
     c = _oracle(prm, sub); e = common.emu_solve(prm, sub)
     # on the noise floor the two implementations take different (chaotic) paths; both must end soon after their best
     # acceptable point, with the same answer to well within the parity tolerances
-    assert (c["status"] == 1).all() and (e["status"] == 1).all()
+    # (1: stored point within acceptable_tol; 2: the looser noise-floor level, reported under its own code)
+    assert np.isin(c["status"], (1, 2)).all() and np.isin(e["status"], (1, 2)).all()
     assert c["iters"].max() <= 55 and e["iters"].max() <= 55
     assert np.abs(c["x"] - e["x"]).max() <= 1e-6 and (np.abs(c["obj"] - e["obj"]) <= 1e-8 * np.abs(c["obj"])).all()
 
@@ -129,28 +130,32 @@ def test_size_limits_and_ragged_polygons(name, sides, N, moving):
     assert (np.abs(e["obj"][ok] - c["obj"][ok]) / np.abs(c["obj"][ok])).max() <= 1e-7
 
 
-def test_recovery_rules_soft_restart_and_other_start_points():
-    """OBCA_INIT_SOFT / OBCA_INIT_RETRY (stand-ins for IPOPT's restoration phase): closed-loop solves whose line search
-    fails from the warm start are solved after a soft restart or from another start point, in the kernel code as in
-    the oracle; instances that succeed at once are untouched by the flags"""
-    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM)
+def test_restoration_phase_and_recovery_rules():
+    """Closed-loop solves whose line search fails from the warm start (tests/golden/recovery_cases.npz).  With the
+    feasibility-restoration phase switched off they fail; with it (the default) every one is solved, in the kernel code
+    as in the oracle, at the same local solution; the older rules (soft restarts, other start points) still work
+    without it; instances that succeed at once are untouched by the flags"""
+    prm0, a, Ts = common.recovery_cases(_abi.INIT_WARM | _abi.INIT_NORESTO)
     solve = lambda prm: c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], Ts=Ts)
     c0 = solve(prm0); e0 = common.emu_solve(prm0, a, Ts=Ts)
-    assert (c0["status"] < 0).all() and (e0["status"] < 0).sum() >= 5
-    prm_r, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.RECOVER)
-    assert prm_r.init == 2 | 16 | (3 << 8)
+    assert (c0["status"] == -4).all() and (e0["status"] == -4).all()
+    prm_r, _, _ = common.recovery_cases(_abi.INIT_WARM)
     c = solve(prm_r); e = common.emu_solve(prm_r, a, Ts=Ts)
-    assert (c["status"] >= 0).all() and (e["status"] >= 0).all()
-    assert (c["iters"] > c0["iters"]).all()                                # totals over the attempts
-    # recovered instances end at a local solution; most at the same one in both implementations
-    same = np.abs(c["obj"] - e["obj"]) <= 1e-6 * np.maximum(1.0, np.abs(c["obj"]))
-    assert same.mean() >= 0.5
-    prm_s, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.init_soft(3))
+    assert (c["status"] == 0).all() and (e["status"] == 0).all()
+    assert (c["iters"] > c0["iters"]).all()                                # totals over the passes
+    assert (np.abs(c["obj"] - e["obj"]) <= 1e-8 * np.maximum(1.0, np.abs(c["obj"]))).all()
+    assert np.abs(c["x"] - e["x"]).max() <= 1e-6
+    prm_o, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.INIT_NORESTO | _abi.INIT_RETRY | _abi.init_soft(3))
+    assert prm_o.init == 2 | 32 | 16 | (3 << 8)
+    co = solve(prm_o); eo = common.emu_solve(prm_o, a, Ts=Ts)
+    assert (co["status"] >= 0).all() and (eo["status"] >= 0).all()
+    assert (np.abs(co["obj"] - eo["obj"]) <= 1e-6 * np.maximum(1.0, np.abs(co["obj"]))).mean() >= 0.5
+    prm_s, _, _ = common.recovery_cases(_abi.INIT_WARM | _abi.INIT_NORESTO | _abi.init_soft(3))
     assert (solve(prm_s)["status"] >= 0).sum() >= 2
     # first attempt succeeds: nothing changes
     b = sc.make_batch(2, 6)
     p0, a2 = common.batch_arrays(b); p1, _ = common.batch_arrays(b, soft_restarts=3, retry=True)
-    assert p1.init == prm_r.init
+    assert p1.init == 2 | 16 | (3 << 8)
     r0 = _oracle(p0, a2); r1 = _oracle(p1, a2); e1 = common.emu_solve(p1, a2)
     assert (r0["status"] >= 0).all() and np.array_equal(r0["iters"], r1["iters"]) and np.array_equal(r0["x"], r1["x"])
     assert np.array_equal(e1["iters"], r0["iters"])

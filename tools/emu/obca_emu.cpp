@@ -15,8 +15,8 @@ using namespace obca;
 template <int EMAX>
 struct HostExec {
   std::vector<BlockRegs<EMAX>> brs;
-  std::vector<std::array<double, NPART>> parts;
-  double red[NPART];
+  std::vector<std::array<double, NPART_X>> parts;
+  double red[NPART_X];
   int T;
   explicit HostExec(int T_) : brs(T_), parts(T_), T(T_) {
     for (auto& p : parts) p.fill(0.0);
@@ -57,17 +57,9 @@ static void run(const KParams& kp, int nwarps, int has_uref) {
     for (int t = 0; t < ex.T; ++t) S.load(t, (size_t)b, true);
     int iters = 0;
     double obj = 0;
-    std::vector<double> wd(Solver<EMAX>::wd_doubles(ex.T, P.N + 1), 0.0);
-    int st;
-    for (int seq = 0;;) {
-      int it_a = 0;
-      st = solve_instance(S, ex, (size_t)b, wd.data(), it_a, obj);
-      iters += it_a;
-      if (!(P.init >> 4) || !retry_status(st) || iters >= OBCA_RECOVERY_BUDGET) break;
-      const int next = next_attempt(P.init, seq);
-      if (next < 0) break;
-      sm.G->init = next;
-    }
+    const int wdn = Solver<EMAX>::wd_doubles(ex.T, P.N + 1);
+    std::vector<double> wd(2 * (size_t)wdn, 0.0);   // watchdog reference | point of failure
+    const int st = solve_with_recovery(S, ex, (size_t)b, wd.data(), wd.data() + wdn, iters, obj);
     if (st != OBCA_ST_STORED)
       for (int t = 0; t < ex.T; ++t) S.store(t, ex.brs[t], (size_t)b, st, iters, obj);
     else { kp.obj[b] = obj; kp.iters[b] = iters; }

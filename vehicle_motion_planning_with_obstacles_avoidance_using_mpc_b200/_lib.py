@@ -15,9 +15,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("OBCA_B200_LIB") or os.path.join(CSRC, "libobca_b200.so")   # env override: developer builds
 SOURCES = ["obca_b200.cu", "obca_loop.cu", "obca_planner.cpp"]
-HEADERS = ["obca_cta.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-pthread"]
+HEADERS = ["obca_cta.cuh", "obca_kernel.cuh", os.path.join("..", "..", "include", "obca_b200.h")]
+# Kernel variants (obca_variant.cu compiled once per row, one translation unit each so that they build in parallel):
+# symbol, max edges per obstacle, threads per block, blocks per SM, then horizon / obstacles / rows compiled in (0 = generic)
+VARIANTS = [("obca_kv_cfg3", 4, 128, 3, 20, 4, 16), ("obca_kv_cfg5", 4, 192, 2, 20, 6, 24), ("obca_kv_cfg2", 4, 128, 3, 10, 2, 8),
+            ("obca_kv_cfg4d", 4, 128, 3, 5, 6, 18), ("obca_kv_cfg4f", 4, 128, 3, 5, 5, 14),
+            ("obca_kv_g4_128", 4, 128, 3, 0, 0, 0), ("obca_kv_g4_192", 4, 192, 2, 0, 0, 0), ("obca_kv_g4_416", 4, 416, 1, 0, 0, 0),
+            ("obca_kv_g8_128", 8, 128, 2, 0, 0, 0), ("obca_kv_g8_416", 8, 416, 1, 0, 0, 0)]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread"]
+
+
+def _mtime(f):
+    f = os.path.join(CSRC, f)
+    return os.path.getmtime(f) if os.path.exists(f) else 0.0
 
 
 def _stale():
@@ -26,18 +36,47 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.exists(os.path.join(CSRC, f)) and os.path.getmtime(os.path.join(CSRC, f)) > t
-               for f in SOURCES + HEADERS)
+    return any(_mtime(f) > t for f in SOURCES + HEADERS + ["obca_variant.cu"])
 
 
-def build(force=False, verbose=False):
-    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> csrc/libobca_b200.so (cross-compiles without a GPU)."""
-    if not force and not _stale():
+def build(force=False, verbose=False, extra_flags=(), out=None, objdir=None):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> csrc/libobca_b200.so (cross-compiles without a GPU).
+
+    Every kernel variant and every source file is its own object (csrc/_obj/), compiled in parallel on the host's
+    cores and re-compiled only when a file it includes is newer; the objects are then linked into the library."""
+    out = out or LIB
+    if not force and out == LIB and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    objdir = objdir or os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    newest_hdr = max(_mtime(f) for f in HEADERS)
+    jobs = []   # (object, source, extra defines, needs the kernel headers)
+    for sym, e, t, b, n, o, r in VARIANTS:
+        jobs.append((os.path.join(objdir, sym + ".o"), "obca_variant.cu",
+                     ["-DKV_SYM=%s" % sym, "-DKV_E=%d" % e, "-DKV_T=%d" % t, "-DKV_B=%d" % b, "-DKV_N=%d" % n, "-DKV_O=%d" % o,
+                      "-DKV_R=%d" % r]))
+    for src in SOURCES:
+        jobs.append((os.path.join(objdir, os.path.splitext(src)[0] + ".o"), src, []))
+
+    def compile_one(job):
+        obj, src, defs = job
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(newest_hdr, _mtime(src)):
+            return ""
+        r = subprocess.run([nvcc] + flags + defs + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s %s:\n%s" % (src, " ".join(defs), r.stderr[-4000:]))
+        return r.stderr
+
+    workers = int(os.environ.get("OBCA_BUILD_JOBS", "0")) or max(1, (os.cpu_count() or 1))
+    with ThreadPoolExecutor(workers) as pool:
+        logs = list(pool.map(compile_one, jobs))
+    if verbose:
+        print("\n".join(l for l in logs if l))
+    subprocess.check_call([nvcc, "-shared", "-o", out] + [j[0] for j in jobs] + ["-lpthread"], cwd=CSRC)
+    return out
 
 
 _lib = None

@@ -11,200 +11,24 @@
 
 #include "obca_cta.cuh"
 
-namespace obca {
-
-// Optional in-kernel phase timing (-DOBCA_PROFILE; tools/phase_profile.py): cycles per phase summed over blocks.
-#if defined(OBCA_PROFILE) || defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
-__device__ unsigned long long g_prof[48];   // phase cycles (16) | par-body cycles of warp 0 (16) | of the stage warp (16)
-#endif
-
-// Block reduction, two stages through shared memory.  `buf` holds nt rows (one per slot) of one value per thread
-// (row stride T).  Stage A: 8 threads per
-// slot each fold T/8 consecutive values; stage B: one thread per slot folds the 8 partials into RED[slot].
-// Slots [0, ns) are sums, [ns, ns+nm) maxima, the rest minima.  (Inlined: as a real call it cost ~5 k cycles per
-// reduction in caller-saved register traffic - the block threads carry their iterate in registers.)
-__device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt) {
-  const int L = T >> 3;
-  double* P2 = RED + NPART;
-  for (int j = tid; j < nt * 8; j += T) {
-    const int q = j >> 3, seg = j & 7;
-    const double* row = buf + q * T + seg * L;
-    // the 8 segments of a slot start a multiple of 32 words apart: start each at a different offset (rotation) so
-    // that the lanes of a warp hit different banks
-    double a = row[seg];              // seg < 8 <= L
-    for (int i = 1; i < L; ++i) {
-      int idx = seg + i;
-      if (idx >= L) idx -= L;
-      const double b = row[idx];
-      a = (q < ns) ? a + b : (q < ns + nm) ? fmax(a, b) : fmin(a, b);
-    }
-    P2[j] = a;
-  }
-  __syncthreads();
-  if (tid < nt) {
-    double a = P2[tid * 8];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      const double b = P2[tid * 8 + i];
-      a = (tid < ns) ? a + b : (tid < ns + nm) ? fmax(a, b) : fmin(a, b);
-    }
-    RED[tid] = a;
-  }
-  __syncthreads();
-}
-
-// Execution model of solve_instance() on the device: one CTA, registers for the per-thread state
-template <int EMAX>
-struct DevExec {
-  BlockRegs<EMAX> br;
-  double part[NPART];
-  double* red;   // block-reduced values (shared memory), valid after reduce()
-  int tid, lane, warp, nwarps;
-  bool stage_warp;
-#ifdef OBCA_PROFILE
-#define OBCA_P_TICK
-#define OBCA_P_PAR
-#define OBCA_P_SWEEP
-#endif
-#if defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
-  long long prof[16], prof_t;
-  long long work[16];   // cycles this warp spent inside par() bodies of the current phase group (before the barrier)
-  int phase;
-#endif
-#ifdef OBCA_P_PAR
-  template <class F> __device__ __forceinline__ void par(F&& f) {
-    const long long t0 = clock64();
-    f(tid, br, part);
-    work[phase] += clock64() - t0;
-    __syncthreads();
-  }
-#else
-  // Home of the per-thread state.  A dynamically indexed member makes this object addressable, so ptxas keeps it in
-  // (L1-resident) local memory and loads what a phase needs at its start instead of holding the block registers (80)
-  // live across phases that do not touch them - the sweep, the control code, the reductions - and spilling at random
-  // inside the hot loops: 1.0 KB of spill stores per thread instead of 2.3 KB, 15-20 % more throughput.  (Found by
-  // accident: the -DOBCA_PROFILE build, whose phase timers are such a member, was the faster one.)
-  int phase_hits[4];
-  int phase_id;
-  template <class F> __device__ __forceinline__ void par(F&& f) {
-    f(tid, br, part);
-    phase_hits[phase_id & 3] += 1;
-    __syncthreads();
-  }
-#endif
-  template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
-  SweepRegs sr;
-  template <class F> __device__ __forceinline__ void sweep(F&& f) {
-#ifdef OBCA_P_SWEEP
-    if (stage_warp) { const long long t0 = clock64(); f(lane, sr); __syncwarp(); work[15] += clock64() - t0; work[14] += 1; }
-#else
-    if (stage_warp) { f(lane, sr); __syncwarp(); }
-#endif
-  }
-  template <class F> __device__ __forceinline__ void stage(F&& f) {
-    if (stage_warp) { f(lane); __syncwarp(); }
-  }
-  __device__ __forceinline__ void stage_end() { __syncthreads(); }
-  template <class F> __device__ __forceinline__ void once(F&& f) { if (tid == 0) f(); }
-  __device__ __forceinline__ void trace(int, double, double, double, double, double, double) {}
-  __device__ __forceinline__ void tick(int i) {
-#ifdef OBCA_P_TICK
-    long long t = clock64(); prof[i] += t - prof_t; prof_t = t;
-    phase = (i + 1) & 15;
-#else
-    (void)i;
-#endif
-  }
-  // one block reduction: sums of part[S0..], maxima of part[M0..], minima of part[N0..] -> red[] (same slots).
-  // Slot ranges must be laid out S | M | N consecutively in part[] (they are: see the PS_/PM_/PN_ enums).
-  template <int S0, int NS, int M0, int NM, int N0, int NN> __device__ __forceinline__ void reduce(double* scratch) {
-    const int T = 32 * nwarps, rs = T, pos = tid;
-#pragma unroll
-    for (int q = 0; q < NS; ++q) scratch[q * rs + pos] = part[S0 + q];
-#pragma unroll
-    for (int q = 0; q < NM; ++q) scratch[(NS + q) * rs + pos] = part[M0 + q];
-#pragma unroll
-    for (int q = 0; q < NN; ++q) scratch[(NS + NM + q) * rs + pos] = part[N0 + q];
-    __syncthreads();
-    // results land at red[slot] = RED[slot]: shift the base so that RED[0] is slot S0 (or M0 / N0 when NS == 0)
-    constexpr int first = (NS > 0) ? S0 : ((NM > 0) ? M0 : N0);
-    cta_reduce(scratch, red + first, T, tid, NS, NM, NS + NM + NN);
-  }
-};
-
-extern __shared__ double obca_smem[];
-
-// NT/NOT/RT > 0: kernel specialised for horizon NT, NOT obstacles, RT half-space rows (sizes are literals);
-// 0: generic kernel, sizes read from the parameter block
-template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0>
-__global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
-  __shared__ unsigned int s_inst;
-  Sm sm;
-  constexpr bool fixed = NT > 0;
-  const int nwarps = fixed ? (NOT * (NT + 1) + 31) / 32 + 1 : nwarps_rt;
-  if (fixed) sm_carve(sm, obca_smem, NT, NOT, RT, (NOT * (NT + 1) + 31) / 32 + 1, has_uref);
-  else sm_carve(sm, obca_smem, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps_rt, has_uref);
-  const Solver<EMAX> S(kp, sm);
-  DevExec<EMAX> ex;
-  ex.red = sm.RED;
-  ex.tid = threadIdx.x; ex.lane = threadIdx.x & 31; ex.warp = threadIdx.x >> 5; ex.nwarps = nwarps;
-  ex.stage_warp = (ex.warp == nwarps - 1);
-  bool first = true;
-  const unsigned int n_items = kp.count_dev ? (unsigned)*kp.count_dev : (unsigned)kp.batch;
-  for (;;) {
-    if (threadIdx.x == 0) {
-      const unsigned int w = atomicAdd(kp.counter, 1u);
-      s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
-    }
-    __syncthreads();
-    const unsigned int inst = s_inst;
-    if (inst == 0xffffffffu) break;
-#if defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
-    for (int i = 0; i < 16; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
-    ex.prof_t = clock64(); ex.phase = 0;
-#endif
-    S.load(ex.tid, inst, first || !kp.shared_obs);
-    first = false;
-    __syncthreads();
-#if !defined(OBCA_P_PAR)
-    ex.phase_id = (int)(inst & 3u);
-    for (int i = 0; i < 4; ++i) ex.phase_hits[i] = 0;
-#endif
-    int iters = 0;
-    double obj = 0.0;
-    int status;
-    for (int seq = 0;;) {   // one pass unless a recovery rule is set and the attempt failed (cold path)
-      int it_a = 0;
-      status = solve_instance(S, ex, (size_t)inst, kp.wd_buf + (size_t)blockIdx.x * kp.wd_stride, it_a, obj);
-      iters += it_a;
-      if (!(kp.P.init >> 4) || !retry_status(status) || iters >= OBCA_RECOVERY_BUDGET) break;
-      const int next = next_attempt(kp.P.init, seq);
-      if (next < 0) break;
-      __syncthreads();
-      if (ex.tid == 0) sm.G->init = next;
-      __syncthreads();
-    }
-    if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
-    else if (ex.tid == 0) { kp.obj[inst] = obj; kp.iters[inst] = iters; }
-#if !defined(OBCA_P_PAR)
-    if (ex.phase_hits[ex.phase_id & 3] < 0) kp.iters[inst] = -1;   // never true: keeps the member alive
-#endif
-#if defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
-    if (ex.tid == 0)
-      for (int i = 0; i < 16; ++i) { atomicAdd(&g_prof[i], (unsigned long long)ex.prof[i]); atomicAdd(&g_prof[16 + i], (unsigned long long)ex.work[i]); }
-    if (ex.stage_warp && ex.lane == 0)
-      for (int i = 0; i < 16; ++i) atomicAdd(&g_prof[32 + i], (unsigned long long)ex.work[i]);
-#endif
-    __syncthreads();
-  }
-}
-
-}  // namespace obca
-
 // ======================================================================================================
 // C-ABI
 // ======================================================================================================
-typedef void (*kernel_fn)(const obca::KParams, int, int);
+// Kernel variants: one translation unit each (obca_variant.cu compiled with -DKV_*; _lib.py lists them), so that they
+// build in parallel.  A variant exports the host-side handle of its kernel.
+typedef const void* kernel_fn;
+extern "C" {
+const void* obca_kv_cfg3(void);    // <4,128,3, N=20, 4 obstacles, 16 rows>   headline
+const void* obca_kv_cfg5(void);    // <4,192,2, N=20, 6, 24>
+const void* obca_kv_cfg2(void);    // <4,128,3, N=10, 2, 8>
+const void* obca_kv_cfg4d(void);   // <4,128,3, N=5, 6, 18>   closed loop, obstacle detected
+const void* obca_kv_cfg4f(void);   // <4,128,3, N=5, 5, 14>   closed loop, free phase
+const void* obca_kv_g4_128(void);  // generic: sizes read from the parameter block
+const void* obca_kv_g4_192(void);
+const void* obca_kv_g4_416(void);
+const void* obca_kv_g8_128(void);
+const void* obca_kv_g8_416(void);
+}
 
 #define OBCA_HOST_CHUNKS 4
 
@@ -240,18 +64,18 @@ static int sm_count_of(int device) {
 // kernel variant for (max edges per obstacle, threads per block); the BASELINE configurations have kernels with
 // compile-time sizes
 static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
-  if (emax <= 4 && N == 20 && no == 4 && R == 16) return obca::obca_solve_kernel<4, 128, 3, 20, 4, 16>;   // cfg 3 (headline)
-  if (emax <= 4 && N == 20 && no == 6 && R == 24) return obca::obca_solve_kernel<4, 192, 2, 20, 6, 24>;   // cfg 5
-  if (emax <= 4 && N == 10 && no == 2 && R == 8) return obca::obca_solve_kernel<4, 128, 3, 10, 2, 8>;     // cfg 2
-  if (emax <= 4 && N == 5 && no == 6 && R == 18) return obca::obca_solve_kernel<4, 128, 3, 5, 6, 18>;     // cfg 4, detected obstacle
-  if (emax <= 4 && N == 5 && no == 5 && R == 14) return obca::obca_solve_kernel<4, 128, 3, 5, 5, 14>;     // cfg 4, free phase
+  if (emax <= 4 && N == 20 && no == 4 && R == 16) return obca_kv_cfg3();
+  if (emax <= 4 && N == 20 && no == 6 && R == 24) return obca_kv_cfg5();
+  if (emax <= 4 && N == 10 && no == 2 && R == 8) return obca_kv_cfg2();
+  if (emax <= 4 && N == 5 && no == 6 && R == 18) return obca_kv_cfg4d();
+  if (emax <= 4 && N == 5 && no == 5 && R == 14) return obca_kv_cfg4f();
   if (emax <= 4) {
-    if (threads <= 128) return obca::obca_solve_kernel<4, 128, 3>;
-    if (threads <= 192) return obca::obca_solve_kernel<4, 192, 2>;
-    return obca::obca_solve_kernel<4, 416, 1>;
+    if (threads <= 128) return obca_kv_g4_128();
+    if (threads <= 192) return obca_kv_g4_192();
+    return obca_kv_g4_416();
   }
-  if (threads <= 128) return obca::obca_solve_kernel<8, 128, 2>;
-  return obca::obca_solve_kernel<8, 416, 1>;
+  if (threads <= 128) return obca_kv_g8_128();
+  return obca_kv_g8_416();
 }
 
 static int configure(obca_ctx* c, int emax, int has_uref) {
@@ -277,7 +101,7 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
   c->grid = sm_count_of(c->device) * per_sm;
   c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
-  const size_t need = (size_t)c->slots * c->grid * c->wd_stride * sizeof(double);
+  const size_t need = (size_t)c->slots * c->grid * 2 * c->wd_stride * sizeof(double);   // two checkpoints per resident block
   if (need > c->wd_bytes) {
     if (c->wd_buf) cudaFree(c->wd_buf);
     c->wd_buf = nullptr; c->wd_bytes = 0;
@@ -341,12 +165,16 @@ int obca_b200_destroy(obca_ctx* c) {
 #ifdef OBCA_PROFILE
 // phase cycle counters (tick i closes phase i): 0 start 1 assemble 2 combine 3 reduce 4 control 5 riccati 6 roll-out
 // 7 steps 8 reduce 9 line-search setup 10 trial 11 reduce+test 12 update 13 exit
+static unsigned long long* g_prof_dev = nullptr;
+static unsigned long long* prof_buffer() {
+  if (!g_prof_dev && (cudaMalloc(&g_prof_dev, 48 * sizeof(unsigned long long)) != cudaSuccess ||
+                      cudaMemset(g_prof_dev, 0, 48 * sizeof(unsigned long long)) != cudaSuccess)) g_prof_dev = nullptr;
+  return g_prof_dev;
+}
 int obca_b200_prof_read(unsigned long long* out, int reset) {
-  if (cudaMemcpyFromSymbol(out, obca::g_prof, 48 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
-  if (reset) {
-    unsigned long long z[48] = {0};
-    if (cudaMemcpyToSymbol(obca::g_prof, z, sizeof(z)) != cudaSuccess) return OBCA_E_CUDA;
-  }
+  if (!prof_buffer()) return OBCA_E_CUDA;
+  if (cudaMemcpy(out, g_prof_dev, 48 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return OBCA_E_CUDA;
+  if (reset && cudaMemset(g_prof_dev, 0, 48 * sizeof(unsigned long long)) != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;
 }
 #endif
@@ -399,16 +227,21 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   kp.x0 = x0; kp.u0 = u0; kp.xref = xref; kp.uref = uref; kp.Tmax = T_max; kp.term = term; kp.Ts_inst = Ts_inst;
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
-  kp.counter = c->counter + slot; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * c->wd_stride; kp.wd_stride = c->wd_stride;
+  kp.counter = c->counter + slot; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * 2 * c->wd_stride; kp.wd_stride = c->wd_stride;
   kp.index = index_dev; kp.count_dev = count_dev;
+#ifdef OBCA_PROFILE
+  kp.prof = prof_buffer();
+#endif
   if (cudaMemsetAsync(c->counter + slot, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
   if (slot == 0) cudaEventRecord(c->ev0, st);
-  c->fn<<<grid, c->threads, c->smem_bytes, st>>>(kp, c->nwarps, uref != nullptr);
+  int nwarps = c->nwarps, has_uref = uref != nullptr;
+  void* args[3] = {&kp, &nwarps, &has_uref};
+  const cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->threads), args, c->smem_bytes, st);
   if (slot == 0) cudaEventRecord(c->ev1, st);
   c->timed = true;
   c->launches += 1;
-  if (cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
+  if (lerr != cudaSuccess || cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;
 }
 

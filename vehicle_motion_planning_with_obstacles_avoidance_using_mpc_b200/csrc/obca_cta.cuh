@@ -35,8 +35,13 @@ namespace obca {
 
 constexpr int FILT_MAX = 32;
 constexpr double SIG_MIN = 1e-8;  // primal regularisation of the OBCA duals (curvature floor of a sign row)
-constexpr int NPART = 12;
-constexpr int OBCA_ST_STORED = 100;  // internal: the result arrays already hold the (acceptable) answer         // per-thread partial results handed to the block reductions
+constexpr int NPART = 12;            // per-thread partial results handed to the block reductions
+constexpr int NPART_X = NPART + 1;   // + one slot that only the restoration pass uses (reduced separately)
+constexpr int OBCA_ST_STORED = 100;  // internal: the result arrays already hold the (acceptable) answer
+// feasibility-restoration phase (IPOPT's remedy for a failed line search; Waechter & Biegler 2006, sec. 3.3): see
+// solve_with_recovery.  kappa: reduction of the violation a call has to reach; rho: l1 penalty (IPOPT: 1000)
+constexpr double RESTO_KAPPA = 0.1, RESTO_RHO = 1000.0, RESTO_FEAS_TOL = 1e-6, RESTO_TOL = 1e-8;
+constexpr int RESTO_ROUNDS = 4, RESTO_STALL = 15, RESTO_MAXITER = 200;
 
 struct KParams {
   obca_params P;
@@ -48,8 +53,9 @@ struct KParams {
   unsigned int* counter;  // persistent-block work queue
   const int32_t* index;     // work item w solves instance index[w] (NULL: w itself)
   const int32_t* count_dev; // number of work items read on the device (NULL: batch)
-  double* wd_buf;         // watchdog checkpoints in HBM: one slot of wd_stride doubles per resident block
+  double* wd_buf;         // checkpoints in HBM: two slots of wd_stride doubles per resident block
   int64_t wd_stride;
+  unsigned long long* prof;   // phase cycle counters (48 words) of the -DOBCA_PROFILE build, else NULL
 };
 
 // block-uniform scalar state of one instance (shared memory)
@@ -62,9 +68,17 @@ struct Glob {
   // loop-carried control state that is read rarely: kept here instead of in every thread's registers (the iteration
   // body is register-bound).  Written by one thread, read by all after a block barrier.
   double c_best_E0, c_best_f, c_thmax, c_thmin, c_dw_last;
-  double c_wd_th, c_wd_ph, c_wd_dphi, c_wd_alpha, c_wd_pw_th, c_wd_pw_dphi;
+  double c_wd_th, c_wd_ph, c_wd_dphi, c_wd_alpha, c_wd_pw_th, c_wd_pw_dphi, c_wd_cmax;
   int bad;
   int init;   // start point of the current attempt (OBCA_INIT_*; set by load, changed by the retry rule)
+  // what a pass leaves for the recovery sequence: violation (1-norm, max-norm) and barrier parameter at its last point
+  double c_th_end, c_cmax_end, c_mu_end;
+  // restoration pass only.  Relaxed rows  d + n - S = 0, n >= 0 (cost rho n, bound multiplier V): state box NXY/VXY
+  // and OBCA distance ND/VD live in the shared arrays, the terminal set here; terminal equality z_N - r_N - pt + nt = 0
+  double ntm[3], Vtm[3], dntm[3];
+  double pt[3], nt[3], Vpt[3], Vnt[3], dpt[3], dnt[3];
+  double tdc[3], tcta[3], tctb[3];   // eliminated terminal equality: dz_N - tdc dy = -(mu tcta + tctb)
+  double TR, zeta, th_ref, mu0;      // reference time scale, proximity weight, violation to get below, first mu
 };
 
 // shared-memory map of one instance; stage arrays are [element][stage], block arrays [element][block]
@@ -76,6 +90,7 @@ struct Sm {
   double *K, *KAP, *PM, *PV, *XI;
   double *ETA, *DLAM, *DMU, *DYE, *DSN, *DSD, *EX;
   double *A, *B0, *DB, *XREF, *UREF;
+  double *NXY, *VXY, *DNXY, *ZR, *UR, *ND, *VD, *DND;   // restoration pass (ZR also carries the caller's guess, OBCA_INIT_GUESS)
   double *RIC, *RED, *SCR_D, *SCR_H;
   uint32_t* TAB;
   Glob* G;
@@ -130,6 +145,8 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   s.GL = s.K;       // Lagrangian gradient of assemble: dead before the sweep writes the feedback gains
   s.ETA = take(25 * (size_t)nb);
   s.A = take(2 * R); s.B0 = take(R); s.DB = take(R); s.XREF = take(3 * S1); s.UREF = take(has_uref ? 2 * N : 0);
+  s.NXY = take(4 * S1); s.VXY = take(4 * S1); s.DNXY = take(4 * S1); s.ZR = take(3 * S1); s.UR = take(2 * S1);
+  s.ND = take(nb); s.VD = take(nb); s.DND = take(nb);
   s.RIC = s.SCR_D;   // scratch of the sweep: the step arrays are dead while the sweep runs
   s.RED = take(NPART + 8 * NPART);
   s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
@@ -292,10 +309,35 @@ struct IneqAcc {
     th += fabs(rd); cmax = fmax(cmax, fabs(rd)); lg.add(S); sumz += Z;
     double sz = S * Z; szmax = fmax(szmax, sz); szmin = fmin(szmin, sz);
   }
+  // restoration pass: row relaxed to  d + n - S = 0, n >= 0 with cost rho n and bound multiplier V (stationarity in n:
+  // rho - Z - V = 0).  Eliminating dS, dn, dV from the Newton equations leaves  dZ = t - sigma (grad d . dX)  with
+  //   sigma = 1 / (S/Z + n/V),   t = mu ta + tb = -sigma [(d + n - S) + (mu - n (rho - Z))/V - (mu - S Z)/Z]
+  // which tends to the ordinary row as n -> 0.  e1: dual infeasibility of the n-row; tho: what the row adds to the
+  // violation of the ORIGINAL problem beyond its own residual (|d - S| - |d + n - S|).
+  double e1 = 0, tho = 0;
+  OB_HD void add_relaxed(double S, double Z, double n, double V, double d, double rho, double& sig, double& ta, double& tb) {
+    const double r = d + n - S, iZ = ob_rcp(Z), iV = ob_rcp(V);
+    sig = ob_rcp(S * iZ + n * iV);
+    ta = sig * (iZ - iV);
+    tb = -sig * (r - n * (rho - Z) * iV + S);
+    th += fabs(r); cmax = fmax(cmax, fabs(r)); lg.add(S); lg.add(n); sumz += Z + V;
+    const double sz = S * Z, nv = n * V;
+    szmax = fmax(szmax, fmax(sz, nv)); szmin = fmin(szmin, fmin(sz, nv));
+    e1 = fmax(e1, fabs(rho - Z - V));
+    tho += fabs(d - S) - fabs(r);
+  }
 };
+// steps of slack and relaxation of a relaxed row from the step dZ of its multiplier
+OB_HD void relaxed_steps(double S, double Z, double n, double V, double mu, double rho, double dZ, double& dS, double& dn) {
+  dS = (mu - S * Z - S * dZ) / Z;
+  const double dV = (rho - Z - V) - dZ;
+  dn = (mu - n * V - n * dV) / V;
+}
+// weight of the proximity term: D_R^2 = min(1, 1/ref^2)
+OB_HD double dr2(double ref) { const double a = fabs(ref); return a > 1.0 ? 1.0 / (a * a) : 1.0; }
 
 // partial-result slots (sum / max / min groups are reduced separately)
-enum { PS_F = 0, PS_TH, PS_LG, PS_SUMY, PS_SUMZ, PS_GT, PM_E1, PM_E2, PM_SZMAX, PM_CT, PM_BAD, PN_SZMIN };  // assemble
+enum { PS_F = 0, PS_TH, PS_LG, PS_SUMY, PS_SUMZ, PS_GT, PM_E1, PM_E2, PM_SZMAX, PM_CT, PM_BAD, PN_SZMIN, PS_THO };  // assemble (PS_THO: restoration)
 enum { QS_DPHI = 0, QN_AMAX = 1, QN_AZ = 2 };                                                                 // backsub
 
 struct StageVals {
@@ -376,6 +418,8 @@ struct Solver {
     Glob& G = *sm.G;
     const int T = sm.T, R = sm.R;
     for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = kp.xref[b * 3 * S1 + i];
+    if ((P.init & 15) == OBCA_INIT_GUESS)   // the caller's poses, read from the output array before it is written
+      for (int i = tid; i < 3 * S1; i += T) sm.ZR[(i % 3) * S1 + i / 3] = kp.x[b * 3 * S1 + i];
     if (sm.has_uref)
       for (int i = tid; i < 2 * N; i += T) sm.UREF[i] = kp.uref[b * 2 * N + i];
     if (load_obs) {
@@ -391,7 +435,7 @@ struct Solver {
       for (int j = 0; j < 2; ++j) G.u0[j] = kp.u0[2 * b + j];
       G.Tmax = (free_ && kp.Tmax) ? kp.Tmax[b] : 1.0;
       G.Ts = kp.Ts_inst ? kp.Ts_inst[b] : P.Ts;
-      G.init = (P.init & 15) % 3;
+      G.init = ((P.init & 15) == OBCA_INIT_GUESS) ? OBCA_INIT_GUESS : (P.init & 15) % 3;
       G.T = 1.0; G.dT = 0.0;
       for (int j = 0; j < 3; ++j) {
         G.term[j] = (has_term && kp.term) ? kp.term[3 * b + j] : 0.0;
@@ -409,8 +453,9 @@ struct Solver {
   OB_HD void pp_of(int k, double pp[3]) const {
     const Glob& G = *sm.G;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) pp[j] = (k == 0) ? G.x0[j] : xref(k)[j];
+    for (int j = 0; j < 3; ++j) pp[j] = (k == 0) ? G.x0[j] : (G.init == OBCA_INIT_GUESS ? sm.st(sm.ZR, j, k) : xref(k)[j]);
   }
+  OB_HD static bool warm_like(int init) { return init == OBCA_INIT_WARM || init == OBCA_INIT_GUESS; }
 
   // ------------------------------------------------------------------------------------------------
   // start point (oracle/obca_nlp.py start_point): init 0 = reference (all zero, T = 1: obca.py:856),
@@ -427,7 +472,7 @@ struct Solver {
       if (sm.G->init != OBCA_INIT_KEEP) sm.st(sm.Z, j, k) = (k == 0) ? pp[j] : (sm.G->init >= OBCA_INIT_XREF ? pp[j] : 0.0);
       sm.st(sm.YD, j, k) = 0.0;
     }
-    if (sm.G->init == OBCA_INIT_WARM && k < N) {
+    if (warm_like(sm.G->init) && k < N) {
       double pn[3];
       pp_of(k + 1, pn);
       part[0] = sqrt((pn[0] - pp[0]) * (pn[0] - pp[0]) + (pn[1] - pp[1]) * (pn[1] - pp[1]));
@@ -436,7 +481,7 @@ struct Solver {
   OB_HD double start_T(double len) const {
     const Glob& G = *sm.G;
     if (G.init == OBCA_INIT_KEEP) return free_ ? G.T : 1.0;
-    if (G.init != OBCA_INIT_WARM || !free_) return 1.0;
+    if (!warm_like(G.init) || !free_) return 1.0;
     double T0 = len / (N * P.uU[0] * G.Ts);
     return fmin(fmax(T0, 1.0), fmax(G.Tmax, P.T_min));
   }
@@ -446,7 +491,7 @@ struct Solver {
     if (is_stage(tid)) {
       const int k = stage_lane(tid);
       double u[2] = {0, 0};
-      if (sm.G->init == OBCA_INIT_WARM && k < N) {
+      if (warm_like(sm.G->init) && k < N) {
         const double h = (free_ ? T0 : 1.0) * G.Ts;
         double pp[3], pn[3];
         pp_of(k, pp); pp_of(k + 1, pn);
@@ -467,7 +512,7 @@ struct Solver {
       for (int j = 0; j < EMAX; ++j) br.lam[j] = 0.0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) br.mu[q] = 0.0;
-      if (sm.G->init == OBCA_INIT_WARM) {
+      if (warm_like(sm.G->init)) {
         double pp[3];
         pp_of(k, pp);
         const double ct = cos(pp[2]), st = sin(pp[2]);
@@ -614,12 +659,118 @@ struct Solver {
   }
 
   // ------------------------------------------------------------------------------------------------
+  // restoration pass, start: the point where the ordinary pass failed becomes the reference of the proximity term;
+  // it is then projected onto the rows the restoration problem keeps hard, so that the pass starts feasible for its
+  // own constraints - poses by rolling the inputs out through the dynamics, OBCA duals pushed inside their sign
+  // bounds, mu_1..4 so that the two OBCA equalities hold - and the relaxation variables absorb what remains.
+  // ------------------------------------------------------------------------------------------------
+  OB_HD void resto_ref(int tid) const {
+    Glob& G = *sm.G;
+    if (!is_stage(tid)) return;
+    const int k = stage_lane(tid);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sm.st(sm.ZR, j, k) = sm.st(sm.Z, j, k);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) sm.st(sm.UR, j, k) = sm.st(sm.U, j, k);
+    if (k == 0) G.TR = free_ ? G.T : 1.0;
+  }
+  OB_HD void resto_rollout() const {   // one thread: sequential in the stage
+    const Glob& G = *sm.G;
+    const double h = (free_ ? G.T : 1.0) * G.Ts;
+    for (int k = 0; k < N; ++k) {
+      const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
+      sm.st(sm.Z, 0, k + 1) = z0 + h * sm.st(sm.U, 0, k) * cos(z2);
+      sm.st(sm.Z, 1, k + 1) = z1 + h * sm.st(sm.U, 0, k) * sin(z2);
+      sm.st(sm.Z, 2, k + 1) = z2 + h * sm.st(sm.U, 1, k);
+    }
+  }
+  // relaxation variable of a row with residual c = d - S: c - p + n = 0 with p n on the central path (IPOPT's
+  // initialisation); the slack absorbs p (it carries no cost), so the row starts satisfied
+  OB_HD static void relax_start(double d, double bp, double mu, double& S, double& Z, double& n, double& V) {
+    S = fmax(d, bp); Z = 1.0;
+    const double c = d - S, hh = (mu - RESTO_RHO * c) / (2 * RESTO_RHO);
+    n = hh + sqrt(hh * hh + mu * c / (2 * RESTO_RHO));
+    S += c + n;
+    V = mu / n;
+  }
+  OB_HD void resto_init(int tid, BlockRegs<EMAX>& br, double mu) const {
+    Glob& G = *sm.G;
+    const double bp = P.bound_push;
+    const double T = free_ ? G.T : 1.0;
+    if (is_stage(tid)) {
+      const int k = stage_lane(tid);
+      double z[3], u[2], up[2], zn[3];
+      stage_point(k, 0.0, z, u, up, zn);
+      StageVals sv;
+      stage_vals(k, z, u, up, zn, T, sv);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sm.st(sm.YD, j, k) = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k >= 1) relax_start(sv.dxy[j], bp, mu, sm.st(sm.SXY, j, k), sm.st(sm.ZXY, j, k), sm.st(sm.NXY, j, k), sm.st(sm.VXY, j, k));
+        else { sm.st(sm.SXY, j, k) = fmax(sv.dxy[j], bp); sm.st(sm.ZXY, j, k) = 1.0; sm.st(sm.NXY, j, k) = 1.0; sm.st(sm.VXY, j, k) = 1.0; }
+        sm.st(sm.DNXY, j, k) = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm.st(sm.SUB, j, k) = (k < N) ? fmax(sv.dub[j], bp) : 1.0; sm.st(sm.ZUB, j, k) = 1.0; }
+      if (k == 0 && free_) {
+        G.STb[0] = fmax(T - P.T_min, bp); G.STb[1] = fmax(G.Tmax - T, bp);
+        G.ZTb[0] = G.ZTb[1] = 1.0;
+      }
+      if (k == N) {
+        const double dtm[3] = {z[0] - G.term[0], z[1] - G.term[1], G.term[2] - z[1]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (has_term) relax_start(dtm[j], bp, mu, G.Stm[j], G.Ztm[j], G.ntm[j], G.Vtm[j]);
+          G.dntm[j] = 0.0; G.yt[j] = 0.0; G.dpt[j] = G.dnt[j] = 0.0;
+          if (free_) {
+            const double c = z[j] - xref(N)[j], hh = (mu - RESTO_RHO * c) / (2 * RESTO_RHO);
+            G.nt[j] = hh + sqrt(hh * hh + mu * c / (2 * RESTO_RHO));
+            G.pt[j] = c + G.nt[j];
+            G.Vpt[j] = mu / G.pt[j]; G.Vnt[j] = mu / G.nt[j];
+          }
+        }
+      }
+    }
+    if (is_block(tid)) {
+      const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
+      const double z0 = sm.st(sm.Z, 0, k), z1 = sm.st(sm.Z, 1, k), z2 = sm.st(sm.Z, 2, k);
+      double st, ct;
+      ob_sincos(z2, &st, &ct);
+      const double tx = z0 + G.off * ct, ty = z1 + G.off * st;
+      double a1 = 0, a2 = 0, bl = 0;
+#pragma unroll
+      for (int j = 0; j < EMAX; ++j) {
+        if (j < E) {
+          const int r = r0 + j;
+          const double l = fmax(br.lam[j], bp);
+          br.lam[j] = l;
+          a1 += sm.A[2 * r] * l; a2 += sm.A[2 * r + 1] * l; bl += bk(k, r) * l;
+          br.Sl[j] = l; br.Zl[j] = 1.0;
+        } else { br.Sl[j] = 1.0; br.Zl[j] = 1.0; }
+      }
+      const double c1 = ct * a1 + st * a2, c2 = -st * a1 + ct * a2;
+      const double b1 = fmax(fmin(br.mu[0], br.mu[2]), bp), b2 = fmax(fmin(br.mu[1], br.mu[3]), bp);
+      br.mu[0] = b1 + fmax(-c1, 0.0); br.mu[2] = b1 + fmax(c1, 0.0);
+      br.mu[1] = b2 + fmax(-c2, 0.0); br.mu[3] = b2 + fmax(c2, 0.0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { br.Sm_[q] = br.mu[q]; br.Zm[q] = 1.0; }
+      br.ye[0] = br.ye[1] = 0.0;
+      br.Sn = fmax(1.0 - a1 * a1 - a2 * a2, bp); br.Zn = 1.0;
+      const double dd = -(G.g[0] * br.mu[0] + G.g[1] * br.mu[1] + G.g[2] * br.mu[2] + G.g[3] * br.mu[3]) + tx * a1 + ty * a2 - bl - P.dmin;
+      relax_start(dd, bp, mu, br.Sd, br.Zd, sm.bl(sm.ND, 0, tid), sm.bl(sm.VD, 0, tid));
+      sm.bl(sm.DND, 0, tid) = 0.0;
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
   // assemble, stage part (lane k): everything that does not depend on the barrier parameter; right-hand
   // sides are split as  mu * (a part) + (b part)  so that mu can be chosen from this pass's own error.
   // Leaves H, RA, RB (without the Lagrangian gradient), GL, GF, CD, DYN in shared memory.
   // ------------------------------------------------------------------------------------------------
+  template <bool RESTO>
   OB_HD void assemble_stage(int k, BlockRegs<EMAX>& br, double* part) const {
-    const Glob& G = *sm.G;
+    Glob& G = *sm.G;
     double z[3], u[2], up[2], zn[3], yd[3], ydm[3];
     stage_point(k, 0.0, z, u, up, zn);
 #pragma unroll
@@ -637,8 +788,17 @@ struct Solver {
     stage_vals(k, z, u, up, zn, T, sv);
     IneqAcc acc;
     double sumy = 0, ceq_th = 0, ceq_max = 0, ctmax = 0;
-    // (1) tracking cost
-    {
+    // (1) tracking cost; restoration: proximity to the reference point instead of the objective
+    double fR = 0.0;   // restoration objective of this stage: zeta/2 |D_R (. - ref)|^2 + rho (relaxation variables)
+    if constexpr (RESTO) {
+      if (k >= 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double ref = sm.st(sm.ZR, a, k), w = G.zeta * dr2(ref), e = z[a] - ref;
+          gf[a] += w * e; HH(a, a) += w; fR += 0.5 * w * e * e;
+        }
+      }
+    } else {
       const double* M = (k < N) ? P.Q : P.P;
       double e[3];
 #pragma unroll
@@ -660,6 +820,13 @@ struct Solver {
       // (2) input cost
       double uu[2] = {u[0], u[1]};
       if (sm.has_uref) { uu[0] -= sm.UREF[2 * k]; uu[1] -= sm.UREF[2 * k + 1]; }
+      if constexpr (RESTO) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const double ref = sm.st(sm.UR, a, k), w = G.zeta * dr2(ref), e = u[a] - ref;
+          gf[6 + a] += w * e; HH(6 + a, 6 + a) += w; fR += 0.5 * w * e * e;
+        }
+      } else {
 #pragma unroll
       for (int a = 0; a < 2; ++a) {
         double s = 0;
@@ -671,8 +838,9 @@ struct Solver {
         }
         gf[6 + a] += s;
       }
+      }
       // (3) acceleration cost between u_{k-1} (state 3,4) and u_k, k >= 1 (the t == 0 term is identically 0)
-      if (k >= 1) {
+      if (k >= 1 && !RESTO) {
         double du[2] = {u[0] - up[0], u[1] - up[1]}, qv[2], Aacc = 0;
         const double ih2 = 1.0 / (h * h);
 #pragma unroll
@@ -758,16 +926,29 @@ struct Solver {
       for (int j = 0; j < 2; ++j) {
         double sg, ta, tb;
         const double Z0 = sm.st(sm.ZXY, j, k), Z2 = sm.st(sm.ZXY, 2 + j, k);
-        acc.add(sm.st(sm.SXY, j, k), Z0, sv.dxy[j], sg, ta, tb);
+        if constexpr (RESTO) {
+          acc.add_relaxed(sm.st(sm.SXY, j, k), Z0, sm.st(sm.NXY, j, k), sm.st(sm.VXY, j, k), sv.dxy[j], RESTO_RHO, sg, ta, tb);
+          fR += RESTO_RHO * sm.st(sm.NXY, j, k);
+        } else
+          acc.add(sm.st(sm.SXY, j, k), Z0, sv.dxy[j], sg, ta, tb);
         HH(j, j) += sg; ra[j] += ta; rb[j] += tb; gL[j] -= Z0;
-        acc.add(sm.st(sm.SXY, 2 + j, k), Z2, sv.dxy[2 + j], sg, ta, tb);
+        if constexpr (RESTO) {
+          acc.add_relaxed(sm.st(sm.SXY, 2 + j, k), Z2, sm.st(sm.NXY, 2 + j, k), sm.st(sm.VXY, 2 + j, k), sv.dxy[2 + j], RESTO_RHO, sg, ta, tb);
+          fR += RESTO_RHO * sm.st(sm.NXY, 2 + j, k);
+        } else
+          acc.add(sm.st(sm.SXY, 2 + j, k), Z2, sv.dxy[2 + j], sg, ta, tb);
         HH(j, j) += sg; ra[j] -= ta; rb[j] -= tb; gL[j] += Z2;
       }
     }
     if (k == 0 && free_) {
       // (4) time cost and (8) T bounds live in stage 0
-      gf[5] += (N + 1) * (P.time_cost[0] + 2 * P.time_cost[1] * T);
-      HH(5, 5) += 2 * (N + 1) * P.time_cost[1];
+      if constexpr (RESTO) {
+        const double w = G.zeta * dr2(G.TR), e = T - G.TR;
+        gf[5] += w * e; HH(5, 5) += w; fR += 0.5 * w * e * e;
+      } else {
+        gf[5] += (N + 1) * (P.time_cost[0] + 2 * P.time_cost[1] * T);
+        HH(5, 5) += 2 * (N + 1) * P.time_cost[1];
+      }
       double sg, ta, tb;
       acc.add(G.STb[0], G.ZTb[0], T - P.T_min, sg, ta, tb);
       HH(5, 5) += sg; ra[5] += ta; rb[5] += tb; gL[5] -= G.ZTb[0];
@@ -776,18 +957,43 @@ struct Solver {
     }
     if (k == N && has_term) {
       double sg, ta, tb;
-      acc.add(G.Stm[0], G.Ztm[0], z[0] - G.term[0], sg, ta, tb);
-      HH(0, 0) += sg; ra[0] += ta; rb[0] += tb; gL[0] -= G.Ztm[0];
-      acc.add(G.Stm[1], G.Ztm[1], z[1] - G.term[1], sg, ta, tb);
-      HH(1, 1) += sg; ra[1] += ta; rb[1] += tb; gL[1] -= G.Ztm[1];
-      acc.add(G.Stm[2], G.Ztm[2], G.term[2] - z[1], sg, ta, tb);
-      HH(1, 1) += sg; ra[1] -= ta; rb[1] -= tb; gL[1] += G.Ztm[2];
+      const double dtm[3] = {z[0] - G.term[0], z[1] - G.term[1], G.term[2] - z[1]};
+      const int ix[3] = {0, 1, 1};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if constexpr (RESTO) {
+          acc.add_relaxed(G.Stm[j], G.Ztm[j], G.ntm[j], G.Vtm[j], dtm[j], RESTO_RHO, sg, ta, tb);
+          fR += RESTO_RHO * G.ntm[j];
+        } else
+          acc.add(G.Stm[j], G.Ztm[j], dtm[j], sg, ta, tb);
+        HH(ix[j], ix[j]) += sg;
+        if (j < 2) { ra[ix[j]] += ta; rb[ix[j]] += tb; gL[ix[j]] -= G.Ztm[j]; }
+        else { ra[ix[j]] -= ta; rb[ix[j]] -= tb; gL[ix[j]] += G.Ztm[j]; }
+      }
     }
+    double tho_eq = 0.0;
     if (k == N && free_) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         gL[j] += G.yt[j];
         double c = z[j] - xref(N)[j];
+        if constexpr (RESTO) {
+          // terminal equality relaxed to  z_N - r_N - pt + nt = 0,  pt, nt >= 0 with cost rho each; eliminating pt, nt
+          // and their multipliers leaves  dz_N - tdc dy = -(mu tcta + tctb)
+          const double pp = G.pt[j], nn = G.nt[j], Vp = G.Vpt[j], Vn = G.Vnt[j], y = G.yt[j];
+          tho_eq += fabs(c);
+          c += -pp + nn;
+          tho_eq -= fabs(c);
+          const double iVp = ob_rcp(Vp), iVn = ob_rcp(Vn);
+          G.tdc[j] = pp * iVp + nn * iVn;
+          G.tcta[j] = iVn - iVp;
+          G.tctb[j] = c + pp * (RESTO_RHO - y) * iVp - nn * (RESTO_RHO + y) * iVn;
+          acc.lg.add(pp); acc.lg.add(nn); acc.sumz += Vp + Vn;
+          const double sp = pp * Vp, sn_ = nn * Vn;
+          acc.szmax = fmax(acc.szmax, fmax(sp, sn_)); acc.szmin = fmin(acc.szmin, fmin(sp, sn_));
+          acc.e1 = fmax(acc.e1, fmax(fabs(RESTO_RHO - y - Vp), fabs(RESTO_RHO + y - Vn)));
+          fR += RESTO_RHO * (pp + nn);
+        }
         ceq_th += fabs(c); ceq_max = fmax(ceq_max, fabs(c)); ctmax = fmax(ctmax, fabs(c));
         sumy += fabs(G.yt[j]);
       }
@@ -803,15 +1009,17 @@ struct Solver {
     sm.st(sm.DYN, 8, k) = dyn[8]; sm.st(sm.DYN, 9, k) = dyn[9];
 #pragma unroll
     for (int j = 0; j < 3; ++j) sm.st(sm.CD, j, k) = (k < N) ? sv.cd[j] : 0.0;
-    part[PS_F] = sv.f; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg.value(); part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
+    part[PS_F] = RESTO ? fR : sv.f; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg.value(); part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
     part[PS_GT] = 0.0; part[PM_E1] = 0.0; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
     part[PM_CT] = ctmax; part[PM_BAD] = 0.0; part[PN_SZMIN] = acc.szmin;
+    if constexpr (RESTO) { part[PS_THO] = acc.tho + tho_eq; part[PM_CT] = acc.e1; }   // PM_CT carries the n-rows' dual infeasibility
   }
 
   // ------------------------------------------------------------------------------------------------
   // assemble, block part (thread = one (obstacle, stage) pair): square-root factorisation of the 5x5 block
   // system, solves for the mu-split right-hand side and the three pose columns, Schur complement onto the pose
   // ------------------------------------------------------------------------------------------------
+  template <bool RESTO>
   OB_HD void assemble_block(int tid, const BlockRegs<EMAX>& br, double* part) const {
     const Glob& G = *sm.G;
     const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
@@ -841,8 +1049,16 @@ struct Solver {
     const double sumy = fabs(y1) + fabs(y2);
     double sn, tna, tnb, sd, tda, tdb;
     acc.add(Sn, Zn, dn, sn, tna, tnb);
-    acc.add(Sd, Zd, dd, sd, tda, tdb);
-    (void)tda; (void)tdb;
+    // right-hand side of the distance row divided by its sigma, split in mu:  (t - Z)/sd = mu rda + rdb
+    double rda, rdb;
+    if constexpr (RESTO) {
+      acc.add_relaxed(Sd, Zd, sm.bl(sm.ND, 0, tid), sm.bl(sm.VD, 0, tid), dd, RESTO_RHO, sd, tda, tdb);
+      const double isd = ob_rcp(sd);
+      rda = tda * isd; rdb = tdb * isd;
+    } else {
+      acc.add(Sd, Zd, dd, sd, tda, tdb);
+      rda = ob_rcp(Zd); rdb = -dd;
+    }
     Tri5 Lf;
     Lf.zero();
     double g0a[5] = {0, 0, 0, 0, 0}, g0b[5] = {0, 0, 0, 0, 0};
@@ -894,9 +1110,9 @@ struct Solver {
     const double ydv = -Zd, c1 = y1 + ydv * G.off;
     const double hc[3][2] = {{ydv, 0.0}, {0.0, ydv}, {-c1 * st - y2 * ct, c1 * ct - y2 * st}};
     double bc[3][5];
-    sm.bl(sm.ETA, 0, tid) = g0a[0] - cha[0]; sm.bl(sm.ETA, 1, tid) = g0a[1] - cha[1]; sm.bl(sm.ETA, 2, tid) = g0a[2] - ob_rcp(Zd);
+    sm.bl(sm.ETA, 0, tid) = g0a[0] - cha[0]; sm.bl(sm.ETA, 1, tid) = g0a[1] - cha[1]; sm.bl(sm.ETA, 2, tid) = g0a[2] - rda;
     sm.bl(sm.ETA, 3, tid) = g0a[3]; sm.bl(sm.ETA, 4, tid) = g0a[4];
-    sm.bl(sm.ETA, 5, tid) = g0b[0] - chb[0]; sm.bl(sm.ETA, 6, tid) = g0b[1] - chb[1]; sm.bl(sm.ETA, 7, tid) = g0b[2] + dd;
+    sm.bl(sm.ETA, 5, tid) = g0b[0] - chb[0]; sm.bl(sm.ETA, 6, tid) = g0b[1] - chb[1]; sm.bl(sm.ETA, 7, tid) = g0b[2] - rdb;
     sm.bl(sm.ETA, 8, tid) = g0b[3] + ce1; sm.bl(sm.ETA, 9, tid) = g0b[4] + ce2;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -948,6 +1164,7 @@ struct Solver {
     part[PS_F] = 0.0; part[PS_TH] = acc.th + ceq_th; part[PS_LG] = acc.lg.value(); part[PS_SUMY] = sumy; part[PS_SUMZ] = acc.sumz;
     part[PS_GT] = 0.0; part[PM_E1] = e1; part[PM_E2] = fmax(acc.cmax, ceq_max); part[PM_SZMAX] = acc.szmax;
     part[PM_CT] = 0.0; part[PM_BAD] = ok ? 0.0 : 1.0; part[PN_SZMIN] = acc.szmin;
+    if constexpr (RESTO) { part[PS_F] = RESTO_RHO * sm.bl(sm.ND, 0, tid); part[PS_THO] = acc.tho; part[PM_CT] = acc.e1; }
   }
 
   // fold the block contributions into the stage QP (lane k), finish the step-form right-hand side and the
@@ -1086,17 +1303,26 @@ struct Solver {
   }
   // The sweep is the longest dependent chain of an iteration (3 sub-steps x N stages).  Each sub-step has <= 32 tasks
   // and runs on the stage warp alone, separated by warp barriers; the other warps wait at one block barrier.
+  template <bool RESTO>
   OB_HD void ric_terminal(int t, double mu, double dw, double dc) const {
-    // stage N: cost-to-go = its own 6x6 block (terminal equality folded in Levenberg-Marquardt style)
+    // stage N: cost-to-go = its own 6x6 block (terminal equality folded in Levenberg-Marquardt style; in the restoration
+    // pass the fold is the elimination of pt, nt: per-component regularisation tdc and residual mu tcta + tctb)
     const int s = N;
+    const Glob& G = *sm.G;
     if (t < 21) {
       double v = sm.st(sm.H, t, s);
-      if (t == 0 || t == 2 || t == 5) { v += dw; if (free_) v += 1.0 / dc; }   // (0,0) (1,1) (2,2)
+      if (t == 0 || t == 2 || t == 5) {   // (0,0) (1,1) (2,2)
+        v += dw;
+        if (free_) v += RESTO ? 1.0 / G.tdc[t == 0 ? 0 : (t == 2 ? 1 : 2)] : 1.0 / dc;
+      }
       sm.st(sm.PM, t, s) = v;
     } else if (t < 27) {
       const int a = t - 21;
       double r = mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
-      if (a < 3 && free_) r -= (sm.st(sm.Z, a, s) - xref(N)[a]) / dc;
+      if (a < 3 && free_) {
+        if constexpr (RESTO) r -= (mu * G.tcta[a] + G.tctb[a]) / G.tdc[a];
+        else r -= (sm.st(sm.Z, a, s) - xref(N)[a]) / dc;
+      }
       sm.st(sm.PV, a, s) = r;
     }
   }
@@ -1237,7 +1463,8 @@ struct Solver {
       sm.st(sm.XI, lane, s + 1) = v;
     }
   }
-  OB_HD void fwd_post(int k, double dc) const {
+  template <bool RESTO>
+  OB_HD void fwd_post(int k, double dc, double mu) const {
     Glob& G = *sm.G;
     double xi[6];
 #pragma unroll
@@ -1265,7 +1492,10 @@ struct Solver {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         sm.st(sm.DYD, a, N) = 0.0;
-        if (free_) G.dyt[a] = (xi[a] + (sm.st(sm.Z, a, N) - xref(N)[a])) / dc;
+        if (free_) {
+          if constexpr (RESTO) G.dyt[a] = (xi[a] + (mu * G.tcta[a] + G.tctb[a])) / G.tdc[a];
+          else G.dyt[a] = (xi[a] + (sm.st(sm.Z, a, N) - xref(N)[a])) / dc;
+        }
       }
     }
   }
@@ -1279,9 +1509,29 @@ struct Solver {
     sls += dS * iS;
   }
 
+  // the same for a relaxation variable n >= 0 with bound multiplier V and steps dn, dV
+  OB_HD static void ftb_n(double n, double V, double dn, double dV, double tau, double& amax, double& az, double& sls) {
+    if (dn < 0 && tau * n < amax * -dn) amax = -tau * n / dn;
+    if (dV < 0 && tau * V < az * -dV) az = -tau * V / dV;
+    sls += dn / n;
+  }
+  // restoration pass: steps of a relaxed row from g = grad d . dX; returns dn (dS through the reference)
+  OB_HD static double relaxed_row_steps(double S, double Z, double n, double V, double d, double g, double mu, double tau,
+                                        double& dS, double& amax, double& az, double& sls) {
+    const double iZ = ob_rcp(Z), iV = ob_rcp(V), sig = ob_rcp(S * iZ + n * iV);
+    const double t = -sig * ((d + n - S) + (mu - n * (RESTO_RHO - Z)) * iV - (mu - S * Z) * iZ);
+    const double dZ = t - sig * g;
+    double dn;
+    relaxed_steps(S, Z, n, V, mu, RESTO_RHO, dZ, dS, dn);
+    ftb(S, Z, dS, mu, tau, amax, az, sls);
+    ftb_n(n, V, dn, (RESTO_RHO - Z - V) - dZ, tau, amax, az, sls);
+    return dn;
+  }
+
   // ------------------------------------------------------------------------------------------------
   // steps of the slacks, fraction to the boundary, directional derivative - stage part (lane k)
   // ------------------------------------------------------------------------------------------------
+  template <bool RESTO>
   OB_HD void backsub_stage(int k, const BlockRegs<EMAX>& br, double mu, double tau, double* part) const {
     Glob& G = *sm.G;
     double z[3], u[2], up[2], zn[3], dz[3], du[2], dup[2];
@@ -1305,10 +1555,19 @@ struct Solver {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         double S0 = sm.st(sm.SXY, j, k), S1_ = sm.st(sm.SXY, 2 + j, k);
+        if constexpr (RESTO) {
+          double d0, d1;
+          const double n0 = relaxed_row_steps(S0, sm.st(sm.ZXY, j, k), sm.st(sm.NXY, j, k), sm.st(sm.VXY, j, k), sv.dxy[j], dz[j], mu, tau, d0, amax, az, sls);
+          const double n1 = relaxed_row_steps(S1_, sm.st(sm.ZXY, 2 + j, k), sm.st(sm.NXY, 2 + j, k), sm.st(sm.VXY, 2 + j, k), sv.dxy[2 + j], -dz[j], mu, tau, d1, amax, az, sls);
+          sm.st(sm.DSXY, j, k) = d0; sm.st(sm.DSXY, 2 + j, k) = d1;
+          sm.st(sm.DNXY, j, k) = n0; sm.st(sm.DNXY, 2 + j, k) = n1;
+          dphi += RESTO_RHO * (n0 + n1);
+        } else {
         double d0 = dz[j] + (sv.dxy[j] - S0), d1 = -dz[j] + (sv.dxy[2 + j] - S1_);
         sm.st(sm.DSXY, j, k) = d0; sm.st(sm.DSXY, 2 + j, k) = d1;
         ftb(S0, sm.st(sm.ZXY, j, k), d0, mu, tau, amax, az, sls);
         ftb(S1_, sm.st(sm.ZXY, 2 + j, k), d1, mu, tau, amax, az, sls);
+        }
       }
     }
     if (k < N) {
@@ -1332,16 +1591,40 @@ struct Solver {
       ftb(G.STb[1], G.ZTb[1], G.dSTb[1], mu, tau, amax, az, sls);
     }
     if (k == N && has_term) {
+      if constexpr (RESTO) {
+        const double dtm[3] = {z[0] - G.term[0], z[1] - G.term[1], G.term[2] - z[1]}, gtm[3] = {dz[0], dz[1], -dz[1]};
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          G.dntm[j] = relaxed_row_steps(G.Stm[j], G.Ztm[j], G.ntm[j], G.Vtm[j], dtm[j], gtm[j], mu, tau, G.dStm[j], amax, az, sls);
+          dphi += RESTO_RHO * G.dntm[j];
+        }
+      } else {
       G.dStm[0] = dz[0] + ((z[0] - G.term[0]) - G.Stm[0]);
       G.dStm[1] = dz[1] + ((z[1] - G.term[1]) - G.Stm[1]);
       G.dStm[2] = -dz[1] + ((G.term[2] - z[1]) - G.Stm[2]);
 #pragma unroll
       for (int j = 0; j < 3; ++j) ftb(G.Stm[j], G.Ztm[j], G.dStm[j], mu, tau, amax, az, sls);
+      }
+    }
+    if constexpr (RESTO) {
+      if (k == N && free_) {   // pt, nt of the relaxed terminal equality from the step of its multiplier
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double dy = G.dyt[j], y = G.yt[j];
+          const double dVp = (RESTO_RHO - y - G.Vpt[j]) - dy, dVn = (RESTO_RHO + y - G.Vnt[j]) + dy;
+          G.dpt[j] = (mu - G.pt[j] * G.Vpt[j] - G.pt[j] * dVp) / G.Vpt[j];
+          G.dnt[j] = (mu - G.nt[j] * G.Vnt[j] - G.nt[j] * dVn) / G.Vnt[j];
+          ftb_n(G.pt[j], G.Vpt[j], G.dpt[j], dVp, tau, amax, az, sls);
+          ftb_n(G.nt[j], G.Vnt[j], G.dnt[j], dVn, tau, amax, az, sls);
+          dphi += RESTO_RHO * (G.dpt[j] + G.dnt[j]);
+        }
+      }
     }
     part[QS_DPHI] = dphi - mu * sls; part[QN_AMAX] = amax; part[QN_AZ] = az;
   }
 
   // block part: back-substitution of the dual block
+  template <bool RESTO>
   OB_HD void backsub_block(int tid, const BlockRegs<EMAX>& br, double mu, double tau, double* part) const {
     const Glob& G = *sm.G;
     const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
@@ -1403,18 +1686,33 @@ struct Solver {
     double ada = a1 * da1 + a2 * da2;
     if (sn >= 1.0) ada = (a1 * (et[0] + ht[0]) + a2 * (et[1] + ht[1])) / (2 * Zn + 4 * sn * (a1 * a1 + a2 * a2));
     const double dSn = -2 * ada + (dn - Sn);
-    double dSd;
-    if (sd >= 1.0) dSd = (mu - Sd * Zd + Sd * et[2]) / Zd;
-    else dSd = qdw + (dd - Sd) + dpose[0] * dp[0] + dpose[1] * dp[1] + dpose[2] * dp[2];
+    double dSd, rdn = 0.0;
+    if constexpr (RESTO) {
+      // relaxed distance row: multiplier step from the solve when the row is active, from the primal direction otherwise
+      const double nd = sm.bl(sm.ND, 0, tid), Vd = sm.bl(sm.VD, 0, tid);
+      const double iZ = ob_rcp(Zd), iV = ob_rcp(Vd), sde = ob_rcp(Sd * iZ + nd * iV);
+      const double tds = -((dd + nd - Sd) + (mu - nd * (RESTO_RHO - Zd)) * iV - (mu - Sd * Zd) * iZ);
+      const double gd = qdw + dpose[0] * dp[0] + dpose[1] * dp[1] + dpose[2] * dp[2];
+      const double dZ = (sde >= 1.0) ? -et[2] : sde * (tds - gd);
+      double dnd;
+      relaxed_steps(Sd, Zd, nd, Vd, mu, RESTO_RHO, dZ, dSd, dnd);
+      sm.bl(sm.DND, 0, tid) = dnd;
+      ftb_n(nd, Vd, dnd, (RESTO_RHO - Zd - Vd) - dZ, tau, amax, az, sls);
+      rdn = RESTO_RHO * dnd;
+    } else {
+      if (sd >= 1.0) dSd = (mu - Sd * Zd + Sd * et[2]) / Zd;
+      else dSd = qdw + (dd - Sd) + dpose[0] * dp[0] + dpose[1] * dp[1] + dpose[2] * dp[2];
+    }
     sm.bl(sm.DSN, 0, tid) = dSn; sm.bl(sm.DSD, 0, tid) = dSd;
     ftb(Sn, Zn, dSn, mu, tau, amax, az, sls);
     ftb(Sd, Zd, dSd, mu, tau, amax, az, sls);
-    part[QS_DPHI] = -mu * sls; part[QN_AMAX] = amax; part[QN_AZ] = az;
+    part[QS_DPHI] = rdn - mu * sls; part[QN_AMAX] = amax; part[QN_AZ] = az;
   }
 
   // ------------------------------------------------------------------------------------------------
   // trial point X + a dX, S + a dS: partial objective, constraint violation theta, sum log S
   // ------------------------------------------------------------------------------------------------
+  template <bool RESTO>
   OB_HD void trial_stage(int k, double a, double* part) const {
     const Glob& G = *sm.G;
     double z[3], u[2], up[2], zn[3];
@@ -1430,9 +1728,27 @@ struct Solver {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { double S = sm.st(sm.SUB, j, k) + a * sm.st(sm.DSUB, j, k); th += fabs(sv.dub[j] - S); lg.add(S); }
     }
+    double fR = 0.0;
+    if constexpr (RESTO) {
+      if (k >= 1) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { const double ref = sm.st(sm.ZR, j, k), e = z[j] - ref; fR += 0.5 * G.zeta * dr2(ref) * e * e; }
+      }
+      if (k < N) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { const double ref = sm.st(sm.UR, j, k), e = u[j] - ref; fR += 0.5 * G.zeta * dr2(ref) * e * e; }
+      }
+      if (k == 0 && free_) { const double e = T - G.TR; fR += 0.5 * G.zeta * dr2(G.TR) * e * e; }
+    }
     if (k >= 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { double S = sm.st(sm.SXY, j, k) + a * sm.st(sm.DSXY, j, k); th += fabs(sv.dxy[j] - S); lg.add(S); }
+      for (int j = 0; j < 4; ++j) {
+        double S = sm.st(sm.SXY, j, k) + a * sm.st(sm.DSXY, j, k);
+        if constexpr (RESTO) {
+          const double n = sm.st(sm.NXY, j, k) + a * sm.st(sm.DNXY, j, k);
+          th += fabs(sv.dxy[j] + n - S); lg.add(S); lg.add(n); fR += RESTO_RHO * n;
+        } else { th += fabs(sv.dxy[j] - S); lg.add(S); }
+      }
     }
     if (k == 0 && free_) {
       double S = G.STb[0] + a * G.dSTb[0]; th += fabs(T - P.T_min - S); lg.add(S);
@@ -1440,15 +1756,27 @@ struct Solver {
     }
     if (k == N && free_) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) th += fabs(z[j] - xref(N)[j]);
+      for (int j = 0; j < 3; ++j) {
+        if constexpr (RESTO) {
+          const double pp = G.pt[j] + a * G.dpt[j], nn = G.nt[j] + a * G.dnt[j];
+          th += fabs(z[j] - xref(N)[j] - pp + nn); lg.add(pp); lg.add(nn); fR += RESTO_RHO * (pp + nn);
+        } else th += fabs(z[j] - xref(N)[j]);
+      }
     }
     if (k == N && has_term) {
-      double S = G.Stm[0] + a * G.dStm[0]; th += fabs(z[0] - G.term[0] - S); lg.add(S);
-      S = G.Stm[1] + a * G.dStm[1]; th += fabs(z[1] - G.term[1] - S); lg.add(S);
-      S = G.Stm[2] + a * G.dStm[2]; th += fabs(G.term[2] - z[1] - S); lg.add(S);
+      const double dtm[3] = {z[0] - G.term[0], z[1] - G.term[1], G.term[2] - z[1]};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double S = G.Stm[j] + a * G.dStm[j];
+        if constexpr (RESTO) {
+          const double n = G.ntm[j] + a * G.dntm[j];
+          th += fabs(dtm[j] + n - S); lg.add(S); lg.add(n); fR += RESTO_RHO * n;
+        } else { th += fabs(dtm[j] - S); lg.add(S); }
+      }
     }
-    part[0] = sv.f; part[1] = th; part[2] = lg.value();
+    part[0] = RESTO ? fR : sv.f; part[1] = th; part[2] = lg.value();
   }
+  template <bool RESTO>
   OB_HD void trial_block(int tid, const BlockRegs<EMAX>& br, double a, double* part) const {
     const Glob& G = *sm.G;
     const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
@@ -1486,9 +1814,13 @@ struct Solver {
     {
       const double S = br.Sd + a * sm.bl(sm.DSD, 0, tid);
       const double d = -(G.g[0] * m[0] + G.g[1] * m[1] + G.g[2] * m[2] + G.g[3] * m[3]) + tx * a1 + ty * a2 - bl - P.dmin;
-      th += fabs(d - S); lg.add(S);
+      if constexpr (RESTO) {
+        const double n = sm.bl(sm.ND, 0, tid) + a * sm.bl(sm.DND, 0, tid);
+        th += fabs(d + n - S); lg.add(S); lg.add(n);
+        part[0] = RESTO_RHO * n;
+      } else { th += fabs(d - S); lg.add(S); part[0] = 0.0; }
     }
-    part[0] = 0.0; part[1] = th; part[2] = lg.value();
+    part[1] = th; part[2] = lg.value();
   }
 
   // ------------------------------------------------------------------------------------------------
@@ -1503,7 +1835,19 @@ struct Solver {
     Zn = fmin(fmax(Zn, mS * 1e-10), ks * mS);
     S = Sn; Z = Zn;
   }
+  // relaxation variable and its bound multiplier (restoration pass; before upd of the row: the step of V needs the
+  // row's current S and Z)
+  OB_HD static void upd_n(double S, double Z, double dS, double& n, double& V, double dn, double a, double az, double mu) {
+    const double ks = 1e10;
+    const double dZ = (mu - Z * dS) * ob_rcp(S) - Z;
+    const double nn = n + a * dn;
+    double Vn = V + az * ((RESTO_RHO - Z - V) - dZ);
+    const double mN = mu * ob_rcp(nn);
+    V = fmin(fmax(Vn, mN * 1e-10), ks * mN);
+    n = nn;
+  }
   // NOTE: reads neighbours' DZ/DU only through its own column, so no barrier is needed inside
+  template <bool RESTO>
   OB_HD void update(int tid, BlockRegs<EMAX>& br, double a, double az, double mu) const {
     Glob& G = *sm.G;
     if (is_stage(tid)) {
@@ -1512,7 +1856,10 @@ struct Solver {
 #pragma unroll
         for (int j = 0; j < 3; ++j) sm.st(sm.Z, j, k) += a * sm.st(sm.DZ, j, k);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) upd(sm.st(sm.SXY, j, k), sm.st(sm.ZXY, j, k), sm.st(sm.DSXY, j, k), a, az, mu);
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (RESTO) upd_n(sm.st(sm.SXY, j, k), sm.st(sm.ZXY, j, k), sm.st(sm.DSXY, j, k), sm.st(sm.NXY, j, k), sm.st(sm.VXY, j, k), sm.st(sm.DNXY, j, k), a, az, mu);
+          upd(sm.st(sm.SXY, j, k), sm.st(sm.ZXY, j, k), sm.st(sm.DSXY, j, k), a, az, mu);
+        }
       }
       if (k < N) {
 #pragma unroll
@@ -1522,16 +1869,34 @@ struct Solver {
 #pragma unroll
         for (int j = 0; j < 3; ++j) sm.st(sm.YD, j, k) += a * sm.st(sm.DYD, j, k);
       }
+      if constexpr (RESTO) {
+        if (k == N && free_) {   // needs the current yt: the same lane moves yt below
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const double ks = 1e10, dy = G.dyt[j], y = G.yt[j];
+            const double pn = G.pt[j] + a * G.dpt[j], nn = G.nt[j] + a * G.dnt[j];
+            const double Vp = G.Vpt[j] + az * ((RESTO_RHO - y - G.Vpt[j]) - dy), Vn = G.Vnt[j] + az * ((RESTO_RHO + y - G.Vnt[j]) + dy);
+            G.Vpt[j] = fmin(fmax(Vp, mu / (ks * pn)), ks * mu / pn);
+            G.Vnt[j] = fmin(fmax(Vn, mu / (ks * nn)), ks * mu / nn);
+            G.pt[j] = pn; G.nt[j] = nn;
+          }
+        }
+      }
+      if (k == N && free_) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) G.yt[j] += a * G.dyt[j];
+      }
       if (k == 0 && free_) {
         G.T += a * G.dT;
         upd(G.STb[0], G.ZTb[0], G.dSTb[0], a, az, mu);
         upd(G.STb[1], G.ZTb[1], G.dSTb[1], a, az, mu);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) G.yt[j] += a * G.dyt[j];
       }
       if (k == N && has_term) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) upd(G.Stm[j], G.Ztm[j], G.dStm[j], a, az, mu);
+        for (int j = 0; j < 3; ++j) {
+          if constexpr (RESTO) upd_n(G.Stm[j], G.Ztm[j], G.dStm[j], G.ntm[j], G.Vtm[j], G.dntm[j], a, az, mu);
+          upd(G.Stm[j], G.Ztm[j], G.dStm[j], a, az, mu);
+        }
       }
     }
     if (is_block(tid)) {
@@ -1551,6 +1916,7 @@ struct Solver {
         br.mu[q] = m0 + a * dm;
       }
       upd(br.Sn, br.Zn, sm.bl(sm.DSN, 0, tid), a, az, mu);
+      if constexpr (RESTO) upd_n(br.Sd, br.Zd, sm.bl(sm.DSD, 0, tid), sm.bl(sm.ND, 0, tid), sm.bl(sm.VD, 0, tid), sm.bl(sm.DND, 0, tid), a, az, mu);
       upd(br.Sd, br.Zd, sm.bl(sm.DSD, 0, tid), a, az, mu);
       br.ye[0] += a * sm.bl(sm.DYE, 0, tid);
       br.ye[1] += a * sm.bl(sm.DYE, 1, tid);
@@ -1647,24 +2013,36 @@ struct Solver {
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
 //   once(f)           run f() on one thread (block-uniform shared state), visible after the next barrier
 // ======================================================================================================
-// start point of attempt a (0, 1, 2) for a context whose first choice is `base` (OBCA_INIT_RETRY, include/obca_b200.h)
+// start point of attempt a for a context whose first choice is `base` (OBCA_INIT_RETRY, include/obca_b200.h):
+// ZERO -> WARM -> XREF, XREF -> WARM -> ZERO, WARM -> XREF -> ZERO, GUESS -> WARM -> XREF -> ZERO; -1 = no more
 OB_HD int retry_init(int base, int a) {
+  if (base == OBCA_INIT_GUESS) return a == 0 ? OBCA_INIT_GUESS : (a == 1 ? OBCA_INIT_WARM : (a == 2 ? OBCA_INIT_XREF : (a == 3 ? OBCA_INIT_ZERO : -1)));
+  if (a > 2) return -1;
   return a == 0 ? base : (a == 1 ? (base == OBCA_INIT_WARM ? OBCA_INIT_XREF : OBCA_INIT_WARM)
                                  : (base == OBCA_INIT_ZERO ? OBCA_INIT_XREF : OBCA_INIT_ZERO));
 }
-OB_HD bool retry_status(int st) { return st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL; }
+OB_HD bool failed_search(int st) { return st == OBCA_ST_LSFAIL || st == OBCA_ST_REGFAIL || st == OBCA_ST_STALL; }
+// outcomes after which another start point may still succeed (the problems are non-convex)
+OB_HD bool failed_attempt(int st) { return failed_search(st) || st == OBCA_ST_INFEASIBLE || st == OBCA_ST_RESTOFAIL; }
 // Recovery sequence after a failed attempt (include/obca_b200.h, OBCA_INIT_SOFT / OBCA_INIT_RETRY): up to n soft
 // restarts from the point reached (multipliers, slacks, barrier parameter and filter start afresh), then the next
 // start point.  `seq` packs (start point index << 4 | soft restarts used); returns the next start code or -1.
 OB_HD int next_attempt(int init_word, int& seq) {
   const int nsoft = OBCA_SOFT_RESTARTS(init_word), soft = seq & 15, a = seq >> 4;
   if (soft < nsoft) { seq += 1; return OBCA_INIT_KEEP; }
-  if ((init_word & OBCA_INIT_RETRY) && a < 2) { seq = (a + 1) << 4; return retry_init((init_word & 15) % 3, a + 1); }
+  if (init_word & OBCA_INIT_RETRY) {
+    const int base = ((init_word & 15) == OBCA_INIT_GUESS) ? OBCA_INIT_GUESS : (init_word & 15) % 3;
+    const int nx = retry_init(base, a + 1);
+    if (nx >= 0) { seq = (a + 1) << 4; return nx; }
+  }
   return -1;
 }
 
-template <int EMAX, class Exec>
-OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, int& iters_out, double& obj_out) {
+// One pass of the interior-point method.  RESTO = false: the NLP itself, from the start point G.init.  RESTO = true: the
+// feasibility-restoration problem at the point the previous pass reached (see solve_with_recovery), a separate
+// instantiation so that the ordinary pass - the hot loop - carries none of its code or state.
+template <int EMAX, bool RESTO, class Exec>
+OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, int& iters_out, double& obj_out) {
   const obca_params& P = S.P;
   Glob& G = *S.sm.G;
   const double s_max = 100.0, kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
@@ -1677,9 +2055,19 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   (void)theta_mu;
   const bool free_ = S.free_, has_term = S.has_term;
   const int m_eq = 3 * N + (free_ ? 3 : 0) + 2 * no * (N + 1);
-  const int q_in = 12 * N + (free_ ? 2 : 0) + (has_term ? 3 : 0) + (S.sm.R + 6 * no) * (N + 1);
+  // the bounds n >= 0 (and pt, nt >= 0) count as inequalities of the restoration problem
+  const int q_in = 12 * N + (free_ ? 2 : 0) + (has_term ? 3 : 0) + (S.sm.R + 6 * no) * (N + 1) +
+                   (RESTO ? 4 * N + (has_term ? 3 : 0) + S.nb + (free_ ? 6 : 0) : 0);
   typedef BlockRegs<EMAX> BR;
 
+  double mu = P.mu_init;
+  if constexpr (RESTO) {
+    mu = G.mu0;
+    ex.par([&](int tid, BR& br, double* part) { (void)br; (void)part; S.resto_ref(tid); });
+    ex.once([&]() { S.resto_rollout(); G.zeta = sqrt(mu); });
+    ex.stage_end();
+    ex.par([&](int tid, BR& br, double* part) { (void)part; S.resto_init(tid, br, mu); });
+  } else {
   ex.par([&](int tid, BR& br, double* part) {
     br.i = (tid < S.nb) ? tid / S.S1 : 0; br.k = (tid < S.nb) ? tid % S.S1 : 0;
     br.r0 = S.kp.eptr[br.i]; br.E = S.kp.eptr[br.i + 1] - br.r0;
@@ -1689,8 +2077,8 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   const double T0 = S.start_T(ex.red[0]);
   ex.par([&](int tid, BR& br, double* part) { (void)part; S.start_b(tid, br, T0); });
   ex.par([&](int tid, BR& br, double* part) { (void)part; S.init_slacks(tid, br); });
+  }
 
-  double mu = P.mu_init;
   int f_n = 0, f_wr = 0;
   bool f_active = false;
   int nstall = 0, acc_count = 0, iter = 0, status = OBCA_ST_MAXITER;
@@ -1703,16 +2091,19 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   const int WD_TRIGGER = 10, WD_MAX = 3, ACC_STALL = 10;
   bool have_best = false;
   double e_min = 1e300;
-  int e_min_iter = 0;
+  int e_min_iter = 0, best_lvl = 0;
   int in_wd = 0, wd_count = 0, wd_block = 0, n_short = 0;
+  double rs_best = 1e300;   // restoration: lowest violation of the original problem so far, and when it was reached
+  int rs_iter = 0;
+  double th_last = 0.0, cmax_last = 0.0;
 
   ex.tick(0);
   for (;;) {
     // ---- assemble
     ex.par([&](int tid, BR& br, double* part) {
-      if (S.is_block(tid)) S.assemble_block(tid, br, part);
-      else if (S.is_stage(tid)) S.assemble_stage(S.stage_lane(tid), br, part);
-      else for (int q = 0; q < NPART; ++q) part[q] = (q == PN_SZMIN) ? 1e300 : 0.0;
+      if (S.is_block(tid)) S.template assemble_block<RESTO>(tid, br, part);
+      else if (S.is_stage(tid)) S.template assemble_stage<RESTO>(S.stage_lane(tid), br, part);
+      else { for (int q = 0; q < NPART; ++q) part[q] = (q == PN_SZMIN) ? 1e300 : 0.0; if constexpr (RESTO) part[PS_THO] = 0.0; }
     });
     ex.tick(1);
     ex.par([&](int tid, BR& br, double* part) { (void)br; if (S.is_stage(tid)) S.assemble_combine(S.stage_lane(tid), part); });
@@ -1722,17 +2113,38 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     const double Ef = ex.red[PS_F], Eth = ex.red[PS_TH], ElgS = ex.red[PS_LG], Esumy = ex.red[PS_SUMY], Esumz = ex.red[PS_SUMZ];
     double Ee1 = ex.red[PM_E1];
     if (free_) Ee1 = fmax(Ee1, fabs(ex.red[PS_GT]));
+    double th_orig = 0.0;
+    if constexpr (RESTO) {
+      Ee1 = fmax(Ee1, ex.red[PM_CT]);   // dual infeasibility of the relaxation variables (PM_CT is theirs in this pass)
+      const double Eth_ = Eth;
+      ex.template reduce<PS_THO, 1, 0, 0, 0, 0>(S.sm.SCR_D);   // (SCR_H is the live Hessian here)
+      th_orig = Eth_ + ex.red[PS_THO];
+    }
+    th_last = Eth; cmax_last = ex.red[PM_E2];
     const double Ee2 = ex.red[PM_E2], Eszmax = ex.red[PM_SZMAX], Ectmax = ex.red[PM_CT], Eszmin = ex.red[PN_SZMIN];
     const bool Eok = !(ex.red[PM_BAD] > 0.0);
     fcur = Ef;
     if (!Eok) { status = OBCA_ST_REGFAIL; break; }
     const double sd = fmax(s_max, (Esumy + Esumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, Esumz / q_in) / s_max;
     E0 = fmax(fmax(Ee1 / sd, Ee2), Eszmax / sc);
+    if constexpr (RESTO) {
+      // the restoration pass ends as soon as the violation of the original problem is below kappa times what it has to
+      // beat (IPOPT: 0.9 plus acceptance by the original filter - here that filter starts afresh, so more is asked);
+      // if instead its own problem converges, or the violation stops decreasing (1 % in RESTO_STALL iterations) while
+      // its own constraints hold, the point is a local minimiser of the violation (the dual error of the regularised
+      // steps sits on a noise floor and would never reach tol)
+      if (th_orig <= fmax(RESTO_KAPPA * G.th_ref, RESTO_FEAS_TOL)) { status = OBCA_ST_OK; break; }
+      if (E0 <= fmax(tol, RESTO_TOL)) { status = OBCA_ST_INFEASIBLE; break; }
+      if (th_orig < 0.99 * rs_best) { rs_best = th_orig; rs_iter = iter; }
+      if (iter - rs_iter >= RESTO_STALL && Eth <= 1e-6 * fmax(1.0, th_orig)) { status = OBCA_ST_INFEASIBLE; break; }
+      if (iter >= RESTO_MAXITER) { status = OBCA_ST_RESTOFAIL; break; }
+    } else {
     if (E0 <= tol) { status = OBCA_ST_OK; break; }
     if (E0 <= P.acceptable_tol) {
       if (++acc_count >= P.acceptable_iter) { status = OBCA_ST_ACCEPTABLE; break; }
     } else
       acc_count = 0;
+    }
     // stall at the acceptable level: an acceptable point is stored, the barrier parameter is final and the error has not
     // halved for ACC_STALL iterations - the iterate wanders on the noise floor (objective constant to 10 digits).  End
     // like IPOPT does when it cannot progress from an acceptable point: with the stored point.  This, with the
@@ -1754,14 +2166,14 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     // complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of the
     // OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the iteration that lowers
     // mu to its final value already counts (otherwise a point that is left again one noisy step later is never stored)
-    const bool acc_lvl = (E0 <= P.acceptable_tol) || (mu <= tol / 10 * (1 + 1e-12) && Eth <= 1e-6 && E0 <= 1e-3);
+    const int acc_lvl = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && Eth <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
     if (acc_lvl) {
       // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails later
       // on.  The store goes straight to the result arrays: no on-chip copy is kept.
       if (E0 < 0.1 * G.c_best_E0) {   // a store per decade of improvement keeps the HBM writes near the algorithmic figure
-        ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, OBCA_ST_ACCEPTABLE, iter, Ef); });
+        ex.par([&](int tid, BR& br, double* part) { (void)part; S.store(tid, br, inst, acc_lvl, iter, Ef); });
         ex.once([&]() { G.c_best_E0 = E0; G.c_best_f = Ef; });   // after the barrier: everyone has evaluated the test
-        have_best = true;
+        have_best = true; best_lvl = acc_lvl;
       }
       if (E0 < 0.5 * e_min) { e_min = E0; e_min_iter = iter; }
     }
@@ -1778,7 +2190,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     for (;;) {
       ex.once([&]() { G.bad = 0; });
       ex.stage_end();
-      ex.sweep([&](int t, SweepRegs& sr) { S.sweep_load(t, sr); S.ric_terminal(t, mu, dw, dc); });
+      ex.sweep([&](int t, SweepRegs& sr) { S.sweep_load(t, sr); S.template ric_terminal<RESTO>(t, mu, dw, dc); });
       for (int s = N - 1; s >= 0; --s) {
         ex.sweep([&](int t, SweepRegs& sr) { S.ric_w(t, s, sr); });
         ex.sweep([&](int t, SweepRegs& sr) { S.ric_f(t, s, mu, dw, sr); });
@@ -1798,13 +2210,13 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     // ---- roll-out
     ex.stage([&](int lane) { if (lane <= N) S.fwd_prep(lane); });
     for (int s = 0; s < N; ++s) ex.stage([&](int lane) { S.fwd_step(lane, s); });
-    ex.stage([&](int lane) { if (lane <= N) S.fwd_post(lane, dc); });
+    ex.stage([&](int lane) { if (lane <= N) S.template fwd_post<RESTO>(lane, dc, mu); });
     ex.stage_end();
     ex.tick(6);
     // ---- steps of the duals / slacks, fraction to the boundary
     ex.par([&](int tid, BR& br, double* part) {
-      if (S.is_block(tid)) S.backsub_block(tid, br, mu, tau, part);
-      else if (S.is_stage(tid)) S.backsub_stage(S.stage_lane(tid), br, mu, tau, part);
+      if (S.is_block(tid)) S.template backsub_block<RESTO>(tid, br, mu, tau, part);
+      else if (S.is_stage(tid)) S.template backsub_stage<RESTO>(S.stage_lane(tid), br, mu, tau, part);
       else { part[QS_DPHI] = 0.0; part[QN_AMAX] = 1.0; part[QN_AZ] = 1.0; }
     });
     ex.tick(7);
@@ -1843,8 +2255,8 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     ex.tick(9);
     while (a >= a_min * (1 - 1e-12)) {
       ex.par([&](int tid, BR& br, double* part) {
-        if (S.is_block(tid)) S.trial_block(tid, br, a, part);
-        else if (S.is_stage(tid)) S.trial_stage(S.stage_lane(tid), a, part);
+        if (S.is_block(tid)) S.template trial_block<RESTO>(tid, br, a, part);
+        else if (S.is_stage(tid)) S.template trial_stage<RESTO>(S.stage_lane(tid), a, part);
         else { part[0] = part[1] = part[2] = 0.0; }
       });
       ex.tick(10);
@@ -1871,9 +2283,9 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       }
       accepted = accept_test(tht, pht, th, ph0, Dphi, a, pw_th, pw_dphi);
       if (accepted) break;
-      if (first && !wd_block && n_short >= WD_TRIGGER && isfinite(pht)) {
+      if (!RESTO && first && !wd_block && n_short >= WD_TRIGGER && isfinite(pht)) {   // (no watchdog in the restoration pass)
         ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_save(tid, br, wd_buf); });
-        ex.once([&]() { G.c_wd_th = th; G.c_wd_ph = ph0; G.c_wd_dphi = Dphi; G.c_wd_alpha = a; G.c_wd_pw_th = pw_th; G.c_wd_pw_dphi = pw_dphi; });
+        ex.once([&]() { G.c_wd_th = th; G.c_wd_ph = ph0; G.c_wd_dphi = Dphi; G.c_wd_alpha = a; G.c_wd_pw_th = pw_th; G.c_wd_pw_dphi = pw_dphi; G.c_wd_cmax = Ee2; });
         in_wd = 1; wd_count = 0; accepted = 3;
         break;
       }
@@ -1885,12 +2297,12 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
     // clause is the rounding-noise floor of a degenerate vertex of the OBCA dual polytope: barrier parameter at most
     // 1e-6, primal feasible to 1e-6, only the dual infeasibility (non-unique multipliers, block elimination in fp64)
     // above tol.  Every cfg-3 instance that ends here has its objective constant to 11 digits over the last ten steps.
-    const bool at_floor = (E0 <= P.acceptable_tol) || (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3);
+    const int at_floor = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
     ex.tick(11);
-    ex.trace(iter, Ef, th, E0, mu, dw, accepted ? a : -1.0);
-    if (!accepted) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_LSFAIL; break; }
+    ex.trace(iter, RESTO ? th_orig : Ef, th, E0, mu, dw, accepted ? a : -1.0);
+    if (!accepted) { status = at_floor ? at_floor : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;
-    if (nstall >= stall_iters) { status = at_floor ? OBCA_ST_ACCEPTABLE : OBCA_ST_STALL; break; }
+    if (nstall >= stall_iters) { status = at_floor ? at_floor : OBCA_ST_STALL; break; }
     if (accepted != 3) { wd_block = 0; n_short = (a < a_max) ? n_short + 1 : 0; }
     else if (!in_wd) n_short = 0;   // watchdog succeeded
     if (accepted == 1) {
@@ -1898,7 +2310,7 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
       ex.once([&]() { G.fth[slot] = (1 - g_th) * th; G.fph[slot] = ph0 - g_ph * th; });
       f_wr++;
     }
-    ex.par([&](int tid, BR& br, double* part) { (void)part; S.update(tid, br, a, a_z, mu); });
+    ex.par([&](int tid, BR& br, double* part) { (void)part; S.template update<RESTO>(tid, br, a, a_z, mu); });
     ex.tick(12);
     iter++;
   }
@@ -1906,11 +2318,84 @@ OB_HD int solve_instance(const Solver<EMAX>& S, Exec& ex, size_t inst, double* w
   iters_out = iter;
   if (status < 0 && G.c_best_E0 < 1e300) {
     // x, u, lam, mu, T of the stored acceptable point are already in the result arrays
-    ex.once([&]() { S.kp.status[inst] = OBCA_ST_ACCEPTABLE; });   // obj and iters: the caller (totals over the attempts)
+    ex.once([&]() { S.kp.status[inst] = best_lvl; });   // obj and iters: the caller (totals over the attempts)
     obj_out = G.c_best_f;
     return OBCA_ST_STORED;
   }
+  if (!RESTO && status < 0 && in_wd) {
+    // failed on a step taken on trust: the point reached is the watchdog's reference
+    ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_restore(tid, br, wd_buf); });
+    th_last = G.c_wd_th; cmax_last = G.c_wd_cmax;
+  }
+  ex.once([&]() { G.c_th_end = th_last; G.c_cmax_end = cmax_last; G.c_mu_end = mu; });
+  ex.stage_end();
   obj_out = fcur;
+  return status;
+}
+
+// One attempt = the interior-point pass and, where its line search / regularisation / progress fails, IPOPT's remedy:
+// the feasibility-restoration phase from the point reached - the same algorithm on
+//     min  rho sum(n) + rho sum(pt + nt) + zeta/2 |D_R ((z,u,T) - (z,u,T)_R)|^2
+//     s.t. dynamics, OBCA equalities, sign / norm / input / acceleration / T rows as they are,
+//          d_i(X) + n_i - S_i = 0, n_i >= 0 for the state box, the terminal set and the OBCA distance rows,
+//          z_N - r_N - pt + nt = 0, pt, nt >= 0 (free-time modes)
+// (IPOPT's restoration problem with the rows that can always be satisfied kept hard, so that the structure of the
+// linear algebra is that of the NLP) - then the NLP again from the restored point with multipliers, slacks, barrier
+// parameter and filter afresh.  Where the restoration phase cannot reduce the violation (a local minimiser of the
+// violation - e.g. a predicted pose inside an obstacle, where the OBCA distance has no gradient - or its own line
+// search fails) the fresh start is taken from the point of failure instead.  At most RESTO_ROUNDS rounds, within the
+// iteration budget; every call has to get below RESTO_KAPPA times the lowest violation seen so far.
+template <int EMAX, class Exec>
+OB_HD int solve_attempt(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, double* fail_buf, int& iters, double& obj) {
+  typedef BlockRegs<EMAX> BR;
+  Glob& G = *S.sm.G;
+  int it_a = 0;
+  int st = solve_pass<EMAX, false>(S, ex, inst, wd_buf, it_a, obj);
+  iters += it_a;
+  const bool use_resto = !(S.P.init & OBCA_INIT_NORESTO);
+  double th_goal = 1e300;
+  bool infeasible = false;
+  for (int nres = 0; use_resto && failed_search(st) && nres < RESTO_ROUNDS && iters < OBCA_RECOVERY_BUDGET; ++nres) {
+    // (block-uniform: written before the last barrier of the pass)
+    const double th_orig = G.c_th_end, cmax = G.c_cmax_end, mu_end = G.c_mu_end;
+    // called at an almost feasible point (IPOPT aborts there): nothing to restore, only the fresh start below
+    if (th_orig > RESTO_FEAS_TOL) {
+      ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_save(tid, br, fail_buf); });
+      th_goal = fmin(th_goal, th_orig);
+      ex.once([&]() { G.th_ref = th_goal; G.mu0 = fmax(mu_end, cmax); });
+      ex.stage_end();
+      double obj_r = 0.0;
+      const int st_r = solve_pass<EMAX, true>(S, ex, inst, wd_buf, it_a, obj_r);
+      iters += it_a;
+      if (st_r < 0) ex.par([&](int tid, BR& br, double* part) { (void)part; S.wd_restore(tid, br, fail_buf); });
+      else th_goal *= RESTO_KAPPA;
+      infeasible = (st_r == OBCA_ST_INFEASIBLE);
+    }
+    ex.once([&]() { G.init = OBCA_INIT_KEEP; });
+    ex.stage_end();
+    st = solve_pass<EMAX, false>(S, ex, inst, wd_buf, it_a, obj);
+    iters += it_a;
+  }
+  if (failed_search(st) && infeasible) st = OBCA_ST_INFEASIBLE;
+  return st;
+}
+
+// The instance: attempts from the start points / soft restarts the caller's flags allow (cold path: one attempt
+// unless it failed).  Returns the final status (OBCA_ST_STORED: the result arrays already hold the answer).
+template <int EMAX, class Exec>
+OB_HD int solve_with_recovery(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, double* fail_buf, int& iters, double& obj) {
+  Glob& G = *S.sm.G;
+  int status;
+  iters = 0;
+  for (int seq = 0;;) {
+    status = solve_attempt(S, ex, inst, wd_buf, fail_buf, iters, obj);
+    if (!failed_attempt(status) || iters >= OBCA_RECOVERY_BUDGET) break;
+    const int next = next_attempt(S.P.init, seq);
+    if (next < 0) break;
+    ex.stage_end();
+    ex.once([&]() { G.init = next; });
+    ex.stage_end();
+  }
   return status;
 }
 
