@@ -11,7 +11,7 @@
  *                    mode 3  FREE_STACKED  obca.obca2 fixtime=0  src/obca.py:338-629 (closed_loop.py:170,263)
  *                    mode 4  FIXED_OBCA2   obca.obca2 fixtime=1  (terminal set optional, obca.py:518-521)
  *
- * One call solves `batch` independent NLPs (one warp each).  All arrays are float64, C-contiguous,
+ * One call solves `batch` independent NLPs (one thread block each).  All arrays are float64, C-contiguous,
  * batch-major; the caller owns every buffer, the library owns only the context.  Functions return 0 on
  * success and a negative code on argument / CUDA errors (obca_b200_strerror); they never throw and never
  * exit.  The per-instance solver outcome is in `status` (>= 0  <=>  the reference's feas == True).
@@ -38,19 +38,26 @@ enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
  * start and goal - closed_loop.py:113-120 -, or the previous plan shifted by one step).  With OBCA_INIT_RETRY the
  * other start points follow as for WARM. */
 #define OBCA_INIT_GUESS 4
-/* OR-ed into `init`: an instance whose line search, regularisation or progress fails (status -4, -2, -5: where IPOPT
- * would enter its restoration phase, which this solver does not have) is restarted from the other start points
- * (WARM -> XREF -> ZERO, XREF -> WARM -> ZERO, ZERO -> WARM -> XREF) before the failure is reported; `iters` is the
- * total over the attempts.  The problems are non-convex: a restart may end in a different local solution. */
+/* An instance whose line search, regularisation or progress fails (status -4, -2, -5) enters the feasibility-
+ * restoration phase, as in IPOPT (up to two rounds of: minimise the violation of the state box, terminal and OBCA
+ * distance rows from the point reached, then the NLP again from the restored point).
+ * OR-ed into `init`: if the attempt still fails (or ends at a local minimiser of the violation, -6 / -7) the instance
+ * is restarted from the other start points (WARM -> XREF -> ZERO, XREF -> WARM -> ZERO, ZERO -> WARM -> XREF) before the
+ * failure is reported; `iters` is the total over the attempts.  The problems are non-convex: a restart may end in a
+ * different local solution. */
 #define OBCA_INIT_RETRY 16
 /* OR-ed into `init`: OBCA_INIT_SOFT(n), n <= 15.  After a failure of the same kind the solver first keeps the primal
  * point it reached and starts again from there with fresh multipliers (y = 0, z = 1), slacks (max(d(x), bound_push)),
- * barrier parameter and filter - at most n times per start point.  This stands in for IPOPT's restoration phase.
+ * barrier parameter and filter - at most n times per start point.  (Round 1's stand-in for the restoration phase;
+ * kept for callers that switch the phase off.)
  * OBCA_INIT_KEEP is that start code (internal: contexts are created with ZERO, XREF or WARM). */
 #define OBCA_INIT_KEEP 3
 /* OR-ed into `init`: switch the feasibility-restoration phase off (a failed line search is then reported at once, or
  * handed to the restart rules above) */
 #define OBCA_INIT_NORESTO 32
+/* OR-ed into `init`: the iteration budget below counts per start point instead of per instance (single solves, where
+ * a long tail does not hold a batch) */
+#define OBCA_INIT_PATIENT 64
 #define OBCA_INIT_SOFT(n) (((n) & 15) << 8)
 /* no further pass is started once the passes of an instance add up to this many iterations (recovered instances of the
  * closed-loop workload need 80 at the median and 216 at most; an instance that fails all twelve passes would run 350-800) */

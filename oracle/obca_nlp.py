@@ -504,6 +504,46 @@ def unpack(p: Problem, lay: Layout, X):
     return x, u, T, lam, mu
 
 
+def pack(p: Problem, lay: Layout, x, u, T, lam, mu):
+    """inverse of unpack with the ABI layouts of ONE instance: x (N+1,3), u (N,2), T, lam (N+1,R), mu (N+1,4*nobs) -> X"""
+    N = p.N
+    X = np.zeros(lay.n)
+    x = np.asarray(x, float).reshape(N + 1, 3); u = np.asarray(u, float).reshape(N, 2)
+    for k in range(1, N + 1):
+        X[lay.iz(k):lay.iz(k) + 3] = x[k]
+    X[lay.u:lay.u + 2 * N] = u.reshape(-1)
+    if p.free:
+        X[lay.T] = float(T)
+    for k in range(N + 1):
+        for i in range(p.nobs):
+            E = int(p.edges[i]); o = lay.eoff[i]
+            X[lay.lam[k, i]:lay.lam[k, i] + E] = lam[k, o:o + E]
+            X[lay.mu[k, i]:lay.mu[k, i] + 4] = mu[k, 4 * i:4 * i + 4]
+    return X
+
+
+def kkt_certificate(p: Problem, lay: Layout, X, act_tol=1e-5):
+    """First-order optimality certificate of a point X, from this restatement alone (no solver state): primal
+    infeasibility (max |c|, max violation of d >= 0), and the stationarity residual of the best multipliers the
+    active set admits - bounded least squares  min |grad f + J^T y - Jd_A^T z|  s.t. z >= 0  (y free).
+    -> dict(f, c_max, d_min, stat = max |residual| / max(1, max |grad f|), z_min, n_active)"""
+    from scipy.optimize import lsq_linear
+    ev = evaluate(p, lay, X, want=("f", "g", "c", "J", "d", "Jd"))
+    act = ev["d"] <= act_tol
+    J = ev["J"]; JdA = ev["Jd"][act]
+    J = J.toarray() if hasattr(J, "toarray") else np.asarray(J)
+    JdA = JdA.toarray() if hasattr(JdA, "toarray") else np.asarray(JdA)
+    M = np.hstack([J.T, -JdA.T])
+    lb = np.concatenate([np.full(J.shape[0], -np.inf), np.zeros(JdA.shape[0])])
+    r = lsq_linear(M, -ev["g"], bounds=(lb, np.full(M.shape[1], np.inf)), method="bvls" if M.shape[1] < 400 else "trf",
+                   tol=1e-13, max_iter=400)
+    res = M @ r.x + ev["g"]
+    z = r.x[J.shape[0]:]
+    return dict(f=float(ev["f"]), c_max=float(np.abs(ev["c"]).max()) if len(ev["c"]) else 0.0, d_min=float(ev["d"].min()),
+                stat=float(np.abs(res).max() / max(1.0, np.abs(ev["g"]).max())), z_min=float(z.min()) if len(z) else 0.0,
+                n_active=int(act.sum()))
+
+
 def objective_of(p: Problem, x, u, T):
     """Objective exactly as the reference's obj_rule writes it (obca.py:859-895), from (x,u,T) arrays."""
     N = p.N

@@ -889,7 +889,7 @@ static trace_fn g_trace = 0;
  * difference on the BASELINE batches and the T bounds must stay hard - measured), rounds per attempt.
  * The setter is a developer hook for exactly those measurements. */
 static double g_kappa_resto = 0.1, g_resto_tol = 1e-8, g_feas_tol = 1e-6, g_rho = 1000.0;
-static int g_rmask = CLS_XY | CLS_TM | CLS_DIST, g_max_resto = 4, g_post_mode = 4;
+static int g_rmask = CLS_XY | CLS_TM | CLS_DIST, g_max_resto = 2, g_post_mode = 4;
 void obca_oracle_set_resto(double kappa, double rtol, double rho, int rmask, int max_resto, int post_mode) {
   g_kappa_resto = kappa; g_resto_tol = rtol; g_rho = rho; g_rmask = rmask; g_max_resto = max_resto; g_post_mode = post_mode;
 }
@@ -1447,7 +1447,7 @@ static int failed_attempt(int st) { return failed_search(st) || st == OBCA_ST_IN
  * predicted pose inside an obstacle, where the OBCA distance has no gradient - or its own line search fails) the fresh
  * start is taken from the point of failure instead.  At most g_max_resto rounds, within the iteration budget; every
  * call of the restoration phase has to get below kappa_resto times the lowest violation seen so far. */
-static int solve_attempt(const prob_t* p, work_t* w, int* iters_io, int use_resto) {
+static int solve_attempt(const prob_t* p, work_t* w, int* iters_io, int use_resto, int budget) {
   int it_a = 0;
   double mu_end = 0;
   int st = solve_one(p, w, &it_a, 0, &mu_end);
@@ -1455,7 +1455,7 @@ static int solve_attempt(const prob_t* p, work_t* w, int* iters_io, int use_rest
   if (g_verbose) fprintf(stderr, "  pass init=%d: status %d iters %d mu %.1e\n", p->init, st, it_a, mu_end);
   double th_goal = 1e300;
   int infeasible = 0;
-  for (int nres = 0; use_resto && failed_search(st) && nres < g_max_resto && *iters_io < g_budget; ++nres) {
+  for (int nres = 0; use_resto && failed_search(st) && nres < g_max_resto && *iters_io < budget; ++nres) {
     prob_t pr = *p;
     eval_values(p, &w->it, &w->v);
     double th, ph, cmax, th_orig;
@@ -1543,13 +1543,15 @@ static void* worker(void* arg) {
     if (has_guess) { memcpy(guess, J->x + (size_t)b * 3 * (N + 1), sizeof(double) * 3 * (N + 1)); p.guess = guess; }
     int iters = 0, st = OBCA_ST_MAXITER;
     const int use_resto = (P->init & OBCA_INIT_NORESTO) == 0;
+    int budget = g_budget;
     for (int a = 0; a < 4 && order[base][a] >= 0; ++a) {
+      if (P->init & OBCA_INIT_PATIENT) budget = iters + g_budget;   /* the iteration budget counts per start point */
       for (int s_ = 0; s_ <= nsoft; ++s_) {
         p.init = s_ == 0 ? order[base][a] : OBCA_INIT_KEEP;
-        st = solve_attempt(&p, w, &iters, use_resto);
-        if (!failed_attempt(st) || iters >= g_budget) break;
+        st = solve_attempt(&p, w, &iters, use_resto, budget);
+        if (!failed_attempt(st) || iters >= budget) break;
       }
-      if (!retry || !failed_attempt(st) || iters >= g_budget) break;
+      if (!retry || !failed_attempt(st) || iters >= budget) break;
     }
     const iter_t* it = &w->it;
     for (int k = 0; k <= N; ++k) {

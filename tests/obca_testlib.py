@@ -51,6 +51,48 @@ def rel(a, b):
     return np.abs(a - b).max() / max(1.0, np.abs(b).max())
 
 
+# ---- certificates from the NumPy restatement of the NLP (oracle/obca_nlp.py), independent of any solver state ------
+def nlp_problem(prm, a, i=0, Ts=None):
+    """oracle/obca_nlp Problem + Layout of instance i of ABI-level arrays"""
+    from oracle import obca_nlp as nlp
+    shared = a["A"].ndim == 2
+    pick = lambda v: None if v is None else v[i]
+    p = nlp.problem_from_abi(prm, a["edge_ptr"], a["x0"][i], a["u0"][i], a["xref"][i], a["A"] if shared else a["A"][i],
+                             a["b0"] if shared else a["b0"][i], None if a["db"] is None else (a["db"] if shared else a["db"][i]),
+                             Ts=None if Ts is None else float(Ts[i]), T_max=pick(a.get("T_max")), term=pick(a.get("term")),
+                             uref=pick(a.get("uref")))
+    return p, nlp.Layout(p)
+
+
+def kkt_of(prm, a, out, i=0, Ts=None):
+    """First-order optimality certificate (oracle/obca_nlp.kkt_certificate) of result i of a solver output dict"""
+    from oracle import obca_nlp as nlp
+    p, lay = nlp_problem(prm, a, i, Ts)
+    X = nlp.pack(p, lay, out["x"][i], out["u"][i], out["T"][i], out["lam"][i], out["mu"][i])
+    return nlp.kkt_certificate(p, lay, X)
+
+
+def slsqp_polish(prm, a, out, i=0, perturb=1e-3, maxiter=300, start=None):
+    """SciPy SLSQP (an independent SQP code) on the NumPy restatement, started from result i (trajectory perturbed) or
+    from one of obca_nlp.start_point's named starts -> (objective, T, max |c|, min d)"""
+    from scipy.optimize import minimize
+    from oracle import obca_nlp as nlp
+    p, lay = nlp_problem(prm, a, i)
+    if start is None:
+        X0 = nlp.pack(p, lay, out["x"][i], out["u"][i], out["T"][i], out["lam"][i], out["mu"][i])
+        X0[:lay.ntraj] += perturb * np.random.default_rng(0).standard_normal(lay.ntraj)
+    else:
+        X0 = nlp.start_point(p, lay, start)
+    den = lambda M: M.toarray() if hasattr(M, "toarray") else np.asarray(M)
+    ev = lambda X, w: nlp.evaluate(p, lay, X, want=w)
+    cons = [dict(type="eq", fun=lambda X: ev(X, ("c", "J"))["c"], jac=lambda X: den(ev(X, ("c", "J"))["J"])),
+            dict(type="ineq", fun=lambda X: ev(X, ("d", "Jd"))["d"], jac=lambda X: den(ev(X, ("d", "Jd"))["Jd"]))]
+    s = minimize(lambda X: ev(X, ("f", "g"))["f"], X0, jac=lambda X: ev(X, ("f", "g"))["g"], constraints=cons,
+                 method="SLSQP", options=dict(maxiter=maxiter, ftol=1e-12))
+    e = ev(s.x, ("c", "d"))
+    return float(s.fun), (float(s.x[lay.T]) if p.free else 1.0), float(np.abs(e["c"]).max()), float(e["d"].min())
+
+
 # ---- oracle-backed stand-ins (CPU tests only): same interfaces as BatchSolver / obca, C oracle underneath ----------
 class OracleSolver:
     """BatchSolver look-alike (``solve_host`` / ``params`` / ``close``) that runs the C oracle.  Lets the host-side

@@ -18,7 +18,10 @@ def _demo9_setting(dyn_row=None):
 
 def _single(dyn_row, steps):
     s = _demo9_setting(dyn_row)
-    c = cl.closedLoop(s, solver=common.oracle_obca())
+    solver = common.oracle_obca()
+    # the solver settings of the lock-step drivers (the `obca` class defaults to IPOPT's mu_init / bound_push)
+    solver.mu_init, solver.bound_push, solver.recover = 10.0, 0.1, _abi.RECOVER
+    c = cl.closedLoop(s, solver=solver)
     c.N_free = c.N_fix = 5
     c.Q_free = 0.5 * np.eye(3); c.P_free = c.Q_free            # simulation.py:68-70
     c.max_steps = steps
@@ -26,14 +29,43 @@ def _single(dyn_row, steps):
     return c, logs
 
 
-def test_open_loop_two_stage_demo1():
-    """simulation.run: free-time solve from start/goal reference, then the fixed-time solve on its result"""
+def test_open_loop_two_stage_demo9_reference_benchmark():
+    """simulation.calc_time (the reference's only timed datapoint, 3.69 s for N = 10; simulation.py:225-231): demo9,
+    N_free = 10, free-time solve from the start/goal-only reference (closed_loop.py:113-120, 535-544), then
+    simulation.run's second stage - the fixed-time solve on its result.  Real start, real goal."""
+    s = ds.problemSetting("demo9")
+    c = cl.closedLoop(s, solver=common.oracle_obca())
+    c.N_free = 10
+    c.mpc_openLoop_freeTime()
+    assert c.xref.shape == (3, 11) and np.array_equal(c.xref[:, 1], c.xref[:, 10])      # start, then the goal ten times
+    assert c.feas and c.xOpt.shape == (3, 11) and c.uOpt.shape == (2, 10)
+    assert np.allclose(c.xOpt[:, -1], s.goalPose, atol=1e-6)      # terminal equality (obca.py:951)
+    T = c.Ts_opt / c.Ts
+    Tmax = ((s.goalPose[0] - s.startPose[0]) + (s.goalPose[1] - s.startPose[1])) / (10 * 0.6 * c.Ts) + 1     # obca.py:961-962
+    assert 1e-4 <= T <= Tmax + 1e-6 and abs(T - 133.959) < 0.01
+    # every pose of the plan keeps the car outside every obstacle by d_min (certificate through the duals)
+    lam, mu = c.obca_solver.lam, c.obca_solver.mu
+    assert lam.min() >= -1e-9 and mu.min() >= -1e-9
+    c.N_fix = 10
+    c.mpc_openLoop_fixTime()
+    assert c.feas and c.Ts == c.Ts_opt
+
+
+def test_open_loop_demo1():
+    """demo1 with its real goal is infeasible as an open-loop problem: T_max (obca.py:961-962) allows 0.6 m more than the
+    straight line and the box [10,15]x[1,5] lies on it - the solver must say so (IPOPT: restoration converges to a
+    point of local infeasibility; the reference prints 'MPC1 -- Failed', simulation.py:48).  With a goal before the box
+    the two stages run and reach the optimum of the A*-window fixture."""
+    c = cl.closedLoop(ds.problemSetting("demo1"), solver=common.oracle_obca())
+    c.N_free = 10
+    c.mpc_openLoop_freeTime()
+    assert not c.feas and c.obca_solver.status in (-4, -6)
     c = cl.closedLoop(ds.problemSetting("demo1"), solver=common.oracle_obca())
     c.x0 = [3, 4, 0]
     c.xF = [10, 6, 0]
     c.mpc_openLoop_freeTime()
     assert c.feas and c.xOpt.shape == (3, 7) and c.uOpt.shape == (2, 6)
-    assert np.allclose(c.xOpt[:, -1], [10, 6, 0], atol=1e-6)      # terminal equality (obca.py:951)
+    assert np.allclose(c.xOpt[:, -1], [10, 6, 0], atol=1e-6)
     T1 = c.Ts_opt
     assert abs(T1 - 2.0378865) < 1e-5            # same optimum as from the A* window (tests/golden demo1_N6)
     c.terminal_set = None

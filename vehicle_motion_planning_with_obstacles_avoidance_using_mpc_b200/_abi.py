@@ -20,7 +20,8 @@ INIT_ZERO, INIT_XREF, INIT_WARM = 0, 1, 2
 INIT_GUESS = 4                        # OBCA_INIT_GUESS: poses of the start point are read from the output array x
 INIT_RETRY = 16                       # OBCA_INIT_RETRY: failed attempts restart from the other start points
 INIT_NORESTO = 32                     # OBCA_INIT_NORESTO: no feasibility-restoration phase
-RECOVER = INIT_RETRY | (3 << 8)       # + OBCA_INIT_SOFT(3): what the receding-horizon drivers and `obca` use
+INIT_PATIENT = 64                     # OBCA_INIT_PATIENT: the iteration budget counts per start point
+RECOVER = INIT_RETRY                  # what the receding-horizon drivers use: restoration phase, then the other start points
 
 
 def init_soft(n):

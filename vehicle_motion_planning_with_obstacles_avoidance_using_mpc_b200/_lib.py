@@ -21,7 +21,10 @@ HEADERS = ["obca_cta.cuh", "obca_kernel.cuh", os.path.join("..", "..", "include"
 VARIANTS = [("obca_kv_cfg3", 4, 128, 3, 20, 4, 16), ("obca_kv_cfg5", 4, 192, 2, 20, 6, 24), ("obca_kv_cfg2", 4, 128, 3, 10, 2, 8),
             ("obca_kv_cfg4d", 4, 128, 3, 5, 6, 18), ("obca_kv_cfg4f", 4, 128, 3, 5, 5, 14),
             ("obca_kv_g4_128", 4, 128, 3, 0, 0, 0), ("obca_kv_g4_192", 4, 192, 2, 0, 0, 0), ("obca_kv_g4_416", 4, 416, 1, 0, 0, 0),
-            ("obca_kv_g8_128", 8, 128, 2, 0, 0, 0), ("obca_kv_g8_416", 8, 416, 1, 0, 0, 0)]
+            ("obca_kv_g8_128", 8, 128, 2, 0, 0, 0), ("obca_kv_g8_416", 8, 416, 1, 0, 0, 0),
+            # recovery kernels (the complete sequence: pass, restoration phase, fresh starts, other start points)
+            ("obca_kv_r4_128", 4, 128, 3, 0, 0, 0), ("obca_kv_r4_192", 4, 192, 2, 0, 0, 0), ("obca_kv_r4_416", 4, 416, 1, 0, 0, 0),
+            ("obca_kv_r8_128", 8, 128, 2, 0, 0, 0), ("obca_kv_r8_416", 8, 416, 1, 0, 0, 0)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-pthread"]
 
 
@@ -53,11 +56,11 @@ def build(force=False, verbose=False, extra_flags=(), out=None, objdir=None):
     os.makedirs(objdir, exist_ok=True)
     flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
     newest_hdr = max(_mtime(f) for f in HEADERS)
-    jobs = []   # (object, source, extra defines, needs the kernel headers)
+    jobs = []   # (object, source, extra defines)
     for sym, e, t, b, n, o, r in VARIANTS:
         jobs.append((os.path.join(objdir, sym + ".o"), "obca_variant.cu",
                      ["-DKV_SYM=%s" % sym, "-DKV_E=%d" % e, "-DKV_T=%d" % t, "-DKV_B=%d" % b, "-DKV_N=%d" % n, "-DKV_O=%d" % o,
-                      "-DKV_R=%d" % r]))
+                      "-DKV_R=%d" % r, "-DKV_FULL=%d" % int(sym.startswith("obca_kv_r"))]))
     for src in SOURCES:
         jobs.append((os.path.join(objdir, os.path.splitext(src)[0] + ".o"), src, []))
 
@@ -70,6 +73,7 @@ def build(force=False, verbose=False, extra_flags=(), out=None, objdir=None):
             raise RuntimeError("nvcc failed on %s %s:\n%s" % (src, " ".join(defs), r.stderr[-4000:]))
         return r.stderr
 
+    jobs.sort(key=lambda j: 0 if "KV_FULL=1" in " ".join(j[2]) else 1)   # the recovery kernels take longest: start them first
     workers = int(os.environ.get("OBCA_BUILD_JOBS", "0")) or max(1, (os.cpu_count() or 1))
     with ThreadPoolExecutor(workers) as pool:
         logs = list(pool.map(compile_one, jobs))

@@ -28,6 +28,11 @@ const void* obca_kv_g4_192(void);
 const void* obca_kv_g4_416(void);
 const void* obca_kv_g8_128(void);
 const void* obca_kv_g8_416(void);
+const void* obca_kv_r4_128(void);  // recovery kernels (generic sizes): the complete sequence over the failed instances
+const void* obca_kv_r4_192(void);
+const void* obca_kv_r4_416(void);
+const void* obca_kv_r8_128(void);
+const void* obca_kv_r8_416(void);
 }
 
 #define OBCA_HOST_CHUNKS 4
@@ -39,7 +44,9 @@ struct obca_ctx {
   int emax;               // largest edge count seen at the last solve (selects the kernel variant)
   int nwarps, threads, grid;
   size_t smem_bytes;
-  kernel_fn fn;
+  kernel_fn fn, fn_rec;   // first-pass kernel, recovery kernel
+  int grid_rec;
+  int32_t* fail_list;     // per launch slot: instances whose first pass failed (max_batch entries each)
   int cfg_emax, cfg_uref; // configuration the launch geometry was computed for
   unsigned int* counter;
   double* wd_buf;         // watchdog checkpoints, one slot per resident block
@@ -77,6 +84,10 @@ static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
   if (threads <= 128) return obca_kv_g8_128();
   return obca_kv_g8_416();
 }
+static kernel_fn pick_recovery_kernel(int emax, int threads) {
+  if (emax <= 4) return threads <= 128 ? obca_kv_r4_128() : (threads <= 192 ? obca_kv_r4_192() : obca_kv_r4_416());
+  return threads <= 128 ? obca_kv_r8_128() : obca_kv_r8_416();
+}
 
 static int configure(obca_ctx* c, int emax, int has_uref) {
   if (c->fn && c->cfg_emax == emax && c->cfg_uref == has_uref && c->cfg_slots == c->slots) return OBCA_OK;
@@ -100,6 +111,15 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   const char* env = getenv("OBCA_CTAS_PER_SM");
   if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
   c->grid = sm_count_of(c->device) * per_sm;
+  c->fn_rec = pick_recovery_kernel(emax, c->threads);
+  int per_sm_rec = 0;
+  if (cudaFuncSetAttribute(c->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rec, c->fn_rec, c->threads, c->smem_bytes) != cudaSuccess || per_sm_rec < 1) {
+    cudaGetLastError();
+    return OBCA_E_CUDA;
+  }
+  c->grid_rec = sm_count_of(c->device) * per_sm_rec;
+  if (c->grid_rec > c->grid) c->grid_rec = c->grid;   // (the checkpoint slots are sized for c->grid blocks)
   c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
   const size_t need = (size_t)c->slots * c->grid * 2 * c->wd_stride * sizeof(double);   // two checkpoints per resident block
   if (need > c->wd_bytes) {
@@ -142,7 +162,11 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   obca_ctx* c = (obca_ctx*)calloc(1, sizeof(obca_ctx));
   if (!c) return OBCA_E_NOMEM;
   c->device = device; c->max_batch = max_batch; c->P = *p;
-  if (cudaMalloc(&c->counter, OBCA_HOST_CHUNKS * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
+  // per launch slot: work counters of the two kernels and the length of the list of failed instances
+  if (cudaMalloc(&c->counter, 3 * OBCA_HOST_CHUNKS * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
+  if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(c->counter); free(c); return OBCA_E_NOMEM;
+  }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
   cudaEventCreateWithFlags(&c->ev_shared, cudaEventDisableTiming);
   c->slots = 1;
@@ -154,6 +178,7 @@ int obca_b200_destroy(obca_ctx* c) {
   if (!c) return OBCA_E_ARG;
   cudaSetDevice(c->device);
   cudaFree(c->counter);
+  cudaFree(c->fail_list);
   if (c->stage) cudaFree(c->stage);
   if (c->wd_buf) cudaFree(c->wd_buf);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_shared);
@@ -181,7 +206,10 @@ int obca_b200_prof_read(unsigned long long* out, int reset) {
 
 // device bytes held by the context: the solver keeps its whole working set on-chip, so this is only the work-queue
 // counter, the watchdog checkpoint slots (one per resident block) and the staging buffer of the host entry point
-int64_t obca_b200_scratch_bytes(const obca_ctx* c) { return c ? (int64_t)(sizeof(unsigned int) + c->stage_bytes + c->wd_bytes) : 0; }
+int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
+  return c ? (int64_t)(3 * OBCA_HOST_CHUNKS * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * sizeof(int32_t) +
+                       c->stage_bytes + c->wd_bytes) : 0;
+}
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
 
 float obca_b200_last_kernel_ms(obca_ctx* c) {
@@ -227,17 +255,31 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   kp.x0 = x0; kp.u0 = u0; kp.xref = xref; kp.uref = uref; kp.Tmax = T_max; kp.term = term; kp.Ts_inst = Ts_inst;
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
-  kp.counter = c->counter + slot; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * 2 * c->wd_stride; kp.wd_stride = c->wd_stride;
+  unsigned int* const cnt = c->counter + 3 * slot;   // work counter of the first pass | of the recovery kernel | failures
+  kp.counter = cnt; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * 2 * c->wd_stride; kp.wd_stride = c->wd_stride;
   kp.index = index_dev; kp.count_dev = count_dev;
+  const bool recover = obca::recovery_follows(P.init, OBCA_ST_LSFAIL);   // do the flags allow anything after a failed pass?
+  if (recover) { kp.fail_list = c->fail_list + (size_t)slot * c->max_batch; kp.fail_count = cnt + 2; }
 #ifdef OBCA_PROFILE
   kp.prof = prof_buffer();
 #endif
-  if (cudaMemsetAsync(c->counter + slot, 0, sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
+  if (cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
   if (slot == 0) cudaEventRecord(c->ev0, st);
   int nwarps = c->nwarps, has_uref = uref != nullptr;
   void* args[3] = {&kp, &nwarps, &has_uref};
-  const cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->threads), args, c->smem_bytes, st);
+  cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->threads), args, c->smem_bytes, st);
+  // the recovery kernel over the instances whose first pass failed (restoration phase, fresh starts, other start
+  // points).  Their number is only known on the device: the blocks of an empty list exit at once.
+  if (lerr == cudaSuccess && recover) {
+    obca::KParams kr = kp;
+    kr.counter = cnt + 1; kr.index = kp.fail_list; kr.count_dev = (const int32_t*)kp.fail_count;
+    kr.fail_list = nullptr; kr.fail_count = nullptr;
+    void* args_r[3] = {&kr, &nwarps, &has_uref};
+    const int grid_r = c->grid_rec < batch ? c->grid_rec : batch;
+    lerr = cudaLaunchKernel(c->fn_rec, dim3(grid_r), dim3(c->threads), args_r, c->smem_bytes, st);
+    c->launches += 1;
+  }
   if (slot == 0) cudaEventRecord(c->ev1, st);
   c->timed = true;
   c->launches += 1;

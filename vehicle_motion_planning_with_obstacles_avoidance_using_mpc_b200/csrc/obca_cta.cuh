@@ -41,7 +41,7 @@ constexpr int OBCA_ST_STORED = 100;  // internal: the result arrays already hold
 // feasibility-restoration phase (IPOPT's remedy for a failed line search; Waechter & Biegler 2006, sec. 3.3): see
 // solve_with_recovery.  kappa: reduction of the violation a call has to reach; rho: l1 penalty (IPOPT: 1000)
 constexpr double RESTO_KAPPA = 0.1, RESTO_RHO = 1000.0, RESTO_FEAS_TOL = 1e-6, RESTO_TOL = 1e-8;
-constexpr int RESTO_ROUNDS = 4, RESTO_STALL = 15, RESTO_MAXITER = 200;
+constexpr int RESTO_ROUNDS = 2, RESTO_STALL = 15, RESTO_MAXITER = 200;
 
 struct KParams {
   obca_params P;
@@ -56,6 +56,10 @@ struct KParams {
   double* wd_buf;         // checkpoints in HBM: two slots of wd_stride doubles per resident block
   int64_t wd_stride;
   unsigned long long* prof;   // phase cycle counters (48 words) of the -DOBCA_PROFILE build, else NULL
+  // first-pass kernel: instances whose pass fails and that the flags allow to recover are appended here (the recovery
+  // kernel then solves exactly this work list); NULL: report the failure
+  int32_t* fail_list;
+  unsigned int* fail_count;
 };
 
 // block-uniform scalar state of one instance (shared memory)
@@ -2343,10 +2347,10 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
 // linear algebra is that of the NLP) - then the NLP again from the restored point with multipliers, slacks, barrier
 // parameter and filter afresh.  Where the restoration phase cannot reduce the violation (a local minimiser of the
 // violation - e.g. a predicted pose inside an obstacle, where the OBCA distance has no gradient - or its own line
-// search fails) the fresh start is taken from the point of failure instead.  At most RESTO_ROUNDS rounds, within the
+// search fails) the fresh start is taken from the point of failure instead.  At most RESTO_ROUNDS (2) rounds, within the
 // iteration budget; every call has to get below RESTO_KAPPA times the lowest violation seen so far.
 template <int EMAX, class Exec>
-OB_HD int solve_attempt(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, double* fail_buf, int& iters, double& obj) {
+OB_HD int solve_attempt(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_buf, double* fail_buf, int& iters, double& obj, int budget) {
   typedef BlockRegs<EMAX> BR;
   Glob& G = *S.sm.G;
   int it_a = 0;
@@ -2355,7 +2359,7 @@ OB_HD int solve_attempt(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd
   const bool use_resto = !(S.P.init & OBCA_INIT_NORESTO);
   double th_goal = 1e300;
   bool infeasible = false;
-  for (int nres = 0; use_resto && failed_search(st) && nres < RESTO_ROUNDS && iters < OBCA_RECOVERY_BUDGET; ++nres) {
+  for (int nres = 0; use_resto && failed_search(st) && nres < RESTO_ROUNDS && iters < budget; ++nres) {
     // (block-uniform: written before the last barrier of the pass)
     const double th_orig = G.c_th_end, cmax = G.c_cmax_end, mu_end = G.c_mu_end;
     // called at an almost feasible point (IPOPT aborts there): nothing to restore, only the fresh start below
@@ -2387,16 +2391,24 @@ OB_HD int solve_with_recovery(const Solver<EMAX>& S, Exec& ex, size_t inst, doub
   Glob& G = *S.sm.G;
   int status;
   iters = 0;
+  int budget = OBCA_RECOVERY_BUDGET;
   for (int seq = 0;;) {
-    status = solve_attempt(S, ex, inst, wd_buf, fail_buf, iters, obj);
-    if (!failed_attempt(status) || iters >= OBCA_RECOVERY_BUDGET) break;
+    status = solve_attempt(S, ex, inst, wd_buf, fail_buf, iters, obj, budget);
+    if (!failed_attempt(status) || iters >= budget) break;
     const int next = next_attempt(S.P.init, seq);
     if (next < 0) break;
+    if ((S.P.init & OBCA_INIT_PATIENT) && next != OBCA_INIT_KEEP) budget = iters + OBCA_RECOVERY_BUDGET;   // per start point
     ex.stage_end();
     ex.once([&]() { G.init = next; });
     ex.stage_end();
   }
   return status;
+}
+
+// does a failed first pass have anything to follow (restoration phase, soft restart, another start point)?
+OB_HD bool recovery_follows(int init_word, int st) {
+  int seq = 0;
+  return failed_search(st) && (!(init_word & OBCA_INIT_NORESTO) || next_attempt(init_word, seq) >= 0);
 }
 
 }  // namespace obca

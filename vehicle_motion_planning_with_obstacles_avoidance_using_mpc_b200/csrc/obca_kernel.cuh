@@ -128,8 +128,15 @@ struct DevExec {
 extern __shared__ double obca_smem[];
 
 // NT/NOT/RT > 0: kernel specialised for horizon NT, NOT obstacles, RT half-space rows (sizes are literals);
-// 0: generic kernel, sizes read from the parameter block
-template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0>
+// 0: generic kernel, sizes read from the parameter block.
+// FULL = false: the first-pass kernel - one interior-point pass per instance, nothing else, so that the hot loop is the
+// whole kernel (with the restoration pass compiled into the same kernel the hot loop lost 10 % to a 50 % larger stack
+// frame); an instance whose pass fails and that may recover is appended to kp.fail_list instead of being stored.
+// FULL = true: the recovery kernel - the complete sequence (pass, restoration phase, fresh starts, other start points)
+// over that list, started from scratch per instance (the first pass is deterministic, so the sequence is the one a
+// single kernel would run; failures are rare, and the list spreads them over all blocks instead of leaving them as the
+// tail of the block that met them).
+template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0, bool FULL = false>
 __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
   __shared__ unsigned int s_inst;
   Sm sm;
@@ -166,8 +173,12 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     int iters = 0;
     double obj = 0.0;
     double* const ckpt = kp.wd_buf + (size_t)blockIdx.x * 2 * kp.wd_stride;   // watchdog reference | point of failure
-    const int status = solve_with_recovery(S, ex, (size_t)inst, ckpt, ckpt + kp.wd_stride, iters, obj);
-    if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
+    int status;
+    if constexpr (FULL) status = solve_with_recovery(S, ex, (size_t)inst, ckpt, ckpt + kp.wd_stride, iters, obj);
+    else status = solve_pass<EMAX, false>(S, ex, (size_t)inst, ckpt, iters, obj);
+    if (!FULL && kp.fail_list && recovery_follows(kp.P.init, status)) {   // (block-uniform)
+      if (ex.tid == 0) kp.fail_list[atomicAdd(kp.fail_count, 1u)] = (int32_t)inst;
+    } else if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
     else if (ex.tid == 0) { kp.obj[inst] = obj; kp.iters[inst] = iters; }
 #if !defined(OBCA_P_PAR)
     if (ex.phase_hits[ex.phase_id & 3] < 0) kp.iters[inst] = -1;   // never true: keeps the member alive

@@ -200,9 +200,14 @@ class obca:
     # closed_loop.py:535-544, whose poses are useless as an initial trajectory), or force INIT_ZERO / INIT_XREF / INIT_WARM
     init = None
     device = -1
-    # recovery rules standing in for IPOPT's restoration phase (soft restarts, then the other start points); OR-ed into
-    # the start point.  0 switches them off.
-    recover = _abi.RECOVER
+    # what follows a failed attempt (the solver's own feasibility-restoration phase comes first): the other start points,
+    # with the iteration budget counted per start point - a single solve has no batch to hold up.  OR-ed into the
+    # start point; 0 switches it off.
+    recover = _abi.INIT_RETRY | _abi.INIT_PATIENT
+    # IPOPT's defaults, which the reference runs with: a single solve takes ~30 % more iterations with
+    # them than with the batch defaults (10, 0.1) but the hard open-loop problems of closed_loop.py:113-120 need them
+    mu_init = 0.1
+    bound_push = 1e-2
 
     @staticmethod
     def _auto_init(xref, x0, N):
@@ -219,8 +224,7 @@ class obca:
                         np.asarray(xref, float).reshape(1, 3, int(N) + 1), int(nObs), vObs, AObs, bObs, dmin, ego,
                         np.asarray(u0, float).reshape(1, 2), terminal_set=terminal_set, uref=uref,
                         init=(self._auto_init(xref, x0, int(N)) if self.init is None else self.init) | self.recover,
-                        device=self.device,
-                        **opts)
+                        device=self.device, **dict(dict(mu_init=self.mu_init, bound_push=self.bound_push), **opts))
         self.lam, self.mu = r["lam"][0], r["mu"][0]
         self.obj, self.status, self.iters, self.T = float(r["obj"][0]), int(r["status"][0]), int(r["iters"][0]), float(r["T"][0])
         return r["x"][0], r["u"][0], bool(r["feas"][0]), float(r["Ts_opt"][0])
