@@ -67,8 +67,10 @@ enum { OBCA_INIT_ZERO = 0, OBCA_INIT_XREF = 1, OBCA_INIT_WARM = 2 };
 /* 0: optimality error <= tol.  1: IPOPT's "Solved To Acceptable Level" (error <= acceptable_tol for acceptable_iter
  * iterations, or the run could not progress from such a point).  2: the run ended on the rounding-noise floor of a
  * degenerate vertex of the OBCA dual polytope - primal infeasibility <= 1e-6, barrier parameter <= 1e-6, and only the
- * (scaled) dual infeasibility above acceptable_tol, at most 1e-3; the objective is constant to ~10 digits there, but
- * this is looser than anything IPOPT reports as success, hence its own code.  feas <=> status >= 0. */
+ * dual infeasibility (IPOPT's scaled AND the unscaled one) above acceptable_tol, at most 1e3 * acceptable_tol (1e-3 for
+ * mpc4, 1e-5 for mpc6/8); the objective is constant to ~10 digits there and a multiplier fit on the active set shows
+ * these points stationary to ~1e-7 (profiles/r2_parity_report.json), but the solver's own error estimate is looser
+ * than anything IPOPT reports as success, hence its own code.  feas <=> status >= 0. */
 enum { OBCA_ST_OK = 0, OBCA_ST_ACCEPTABLE = 1, OBCA_ST_FLOOR = 2, OBCA_ST_MAXITER = -1, OBCA_ST_REGFAIL = -2, OBCA_ST_EMPTYBOX = -3,
        OBCA_ST_LSFAIL = -4, OBCA_ST_STALL = -5,
        OBCA_ST_INFEASIBLE = -6,   /* the restoration phase converged to a local minimiser of the constraint violation
@@ -156,6 +158,9 @@ int64_t obca_b200_launch_count(const obca_ctx* ctx);
  * valid after the stream was synchronised */
 float obca_b200_last_kernel_ms(obca_ctx* ctx);
 const char* obca_b200_strerror(int rc);
+/* Measured fp64 throughput of the device (TFLOP/s): a kernel of independent DFMA chains, best of three.  The solver is
+ * bound by the fp64 pipe and its latencies, not by HBM; bench.py reports the solver's fp64 rate against this ceiling. */
+int  obca_b200_fp64_peak(int device, double* tflops);
 
 /* ---- host planner: the callers' side of the solve, batched on the host cores ----------------
  * obca_b200_astar_batch replaces a_star.solve + rebuild_path + create_reference_path (src/a_star.py:39-102, 137-147,

@@ -522,11 +522,13 @@ def pack(p: Problem, lay: Layout, x, u, T, lam, mu):
     return X
 
 
-def kkt_certificate(p: Problem, lay: Layout, X, act_tol=1e-5):
+def kkt_certificate(p: Problem, lay: Layout, X, act_tol=1e-3):
     """First-order optimality certificate of a point X, from this restatement alone (no solver state): primal
     infeasibility (max |c|, max violation of d >= 0), and the stationarity residual of the best multipliers the
     active set admits - bounded least squares  min |grad f + J^T y - Jd_A^T z|  s.t. z >= 0  (y free).
-    -> dict(f, c_max, d_min, stat = max |residual| / max(1, max |grad f|), z_min, n_active)"""
+    Rows with d <= act_tol enter the fit (generously: a row at distance 1e-4 may still carry a multiplier of 1e-5 at the
+    final barrier parameter); `compl` = max z_i d_i over them reports the complementarity of the fitted multipliers.
+    -> dict(f, c_max, d_min, stat = max |residual| / max(1, max |grad f|), z_min, compl, n_active)"""
     from scipy.optimize import lsq_linear
     ev = evaluate(p, lay, X, want=("f", "g", "c", "J", "d", "Jd"))
     act = ev["d"] <= act_tol
@@ -541,7 +543,7 @@ def kkt_certificate(p: Problem, lay: Layout, X, act_tol=1e-5):
     z = r.x[J.shape[0]:]
     return dict(f=float(ev["f"]), c_max=float(np.abs(ev["c"]).max()) if len(ev["c"]) else 0.0, d_min=float(ev["d"].min()),
                 stat=float(np.abs(res).max() / max(1.0, np.abs(ev["g"]).max())), z_min=float(z.min()) if len(z) else 0.0,
-                n_active=int(act.sum()))
+                compl=float((z * np.maximum(ev["d"][act], 0.0)).max()) if len(z) else 0.0, n_active=int(act.sum()))
 
 
 def objective_of(p: Problem, x, u, T):

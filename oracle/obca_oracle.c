@@ -1126,7 +1126,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
      * complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of
      * the OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the
      * iteration that lowers mu to its final value already counts */
-    const int acc_lvl = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    const int acc_lvl = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && fmax(E0, e1) <= 1e3 * P->acceptable_tol) ? OBCA_ST_FLOOR : 0;
     if (acc_lvl && !p->resto) {
       /* IPOPT stores the best acceptable iterate and falls back to it when the run ends in a failure
        * ("Solved To Acceptable Level"); a point that only meets the noise-floor level is reported as such */
@@ -1367,7 +1367,7 @@ static int solve_one(const prob_t* p, work_t* w, int* iters_out, double* err_out
      * above tol, so this is how such instances end
      * (second clause: barrier parameter at most 1e-6, primal feasible to 1e-6 and complementary, with only
      * the dual infeasibility sitting on the rounding-noise floor of the degenerate-vertex linear algebra) */
-    int at_floor = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    int at_floor = (E0 <= P->acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && fmax(E0, e1) <= 1e3 * P->acceptable_tol) ? OBCA_ST_FLOOR : 0;
     if (p->resto) at_floor = 0;
     if (!accepted) { status = at_floor ? at_floor : OBCA_ST_LSFAIL; break; }
     nstall = (a < stall_alpha) ? nstall + 1 : 0;

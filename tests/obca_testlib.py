@@ -34,17 +34,7 @@ def fixture_arrays(name, init=_abi.INIT_WARM, **opts):
 
 
 def batch_arrays(b, init=_abi.INIT_WARM, **opts):
-    ep, A, b0, db = _abi.pack_obstacles(b.mode, b.N, b.nObs, b.vObs, b.AObs, b.bObs)
-    prm = _abi.make_params(b.mode, b.N, b.nObs, int(ep[-1]), b.Ts, b.P, b.Q, b.R, b.xL, b.xU, b.uL, b.uU, b.dmin,
-                           b.ego, init=init, **opts)
-    xref = np.ascontiguousarray(b.xref.transpose(0, 2, 1))
-    Tm = None
-    if _abi.is_free(b.mode):
-        Tm = ((b.xref[:, 0, b.N] - b.x0[:, 0]) + (b.xref[:, 1, b.N] - b.x0[:, 1])) / (b.N * b.uU[0] * b.Ts) + 1.0
-    term = None
-    if b.terminal_set is not None:
-        term = np.stack([b.terminal_set[:, 0, 0], b.terminal_set[:, 1, 0], b.terminal_set[:, 1, 1]], axis=1)
-    return prm, dict(x0=b.x0, u0=b.u0, xref=xref, edge_ptr=ep, A=A, b0=b0, db=db, T_max=Tm, term=term)
+    return sc.batch_arrays(b, init=init, **opts)
 
 
 def rel(a, b):
@@ -91,6 +81,63 @@ def slsqp_polish(prm, a, out, i=0, perturb=1e-3, maxiter=300, start=None):
                  method="SLSQP", options=dict(maxiter=maxiter, ftol=1e-12))
     e = ev(s.x, ("c", "d"))
     return float(s.fun), (float(s.x[lay.T]) if p.free else 1.0), float(np.abs(e["c"]).max()), float(e["d"].min())
+
+
+# ---- parity protocol (GPU tests, tools/parity_report.py) ---------------------------------------------------------
+PRIMAL_RTOL, OBJ_RTOL = 1e-4, 1e-6    # north_star: 1e-4 relative on primal variables, 1e-6 relative on the objective
+
+
+def component_errors(g, c, sel):
+    """Per-instance relative errors of result dict g against c over the instances `sel`, every component against its
+    own scale: positions by the instance's largest coordinate, heading, speed, turn rate and T by max(1, max |.|) of
+    that component (so 1e-4 means 1e-4 rad, 1e-4 m/s ... - not 1e-4 of a 39 m coordinate), objective relative."""
+    n = int(sel.sum())
+    mx = lambda v: np.abs(v).reshape(n, -1).max(1)
+    e = lambda gv, cv: mx(gv - cv) / np.maximum(1.0, mx(cv))
+    gx, cx, gu, cu = g["x"][sel], c["x"][sel], g["u"][sel], c["u"][sel]
+    return dict(pos=e(gx[..., :2], cx[..., :2]), hdg=e(gx[..., 2], cx[..., 2]), v=e(gu[..., 0], cu[..., 0]),
+                w=e(gu[..., 1], cu[..., 1]), T=e(g["T"][sel], c["T"][sel]),
+                obj=np.abs(g["obj"][sel] - c["obj"][sel]) / np.maximum(1e-300, np.abs(c["obj"][sel])))
+
+
+def parity_summary(prm, a, g, c, kkt_sample=0, Ts=None):
+    """The numbers the parity tests assert on.  `within` = instances solved by both whose x, u, T agree to PRIMAL_RTOL
+    (component-wise, see component_errors) and whose objective agrees to OBJ_RTOL.  For the others (`outliers`) and for
+    a random sample of `kkt_sample` feasible GPU results the first-order optimality certificate of the NumPy
+    restatement is evaluated (kkt_of): an outlier with a valid certificate on both sides is a different local
+    solution of a non-convex problem, not an error."""
+    gs, cs = g["status"] >= 0, c["status"] >= 0
+    both = gs & cs
+    e = component_errors(g, c, both)
+    prim = np.maximum.reduce([e["pos"], e["hdg"], e["v"], e["w"], e["T"]])
+    bad = (prim > PRIMAL_RTOL) | (e["obj"] > OBJ_RTOL)
+    idx = np.flatnonzero(both)
+    out = dict(batch=int(len(gs)), gpu_feasible=int(gs.sum()), oracle_feasible=int(cs.sum()), both=int(both.sum()),
+               feasibility_agreement=float((gs == cs).mean()), within=int((~bad).sum()), outliers=int(bad.sum()),
+               primal_max=float(prim[~bad].max()) if (~bad).any() else 0.0, obj_max=float(e["obj"][~bad].max()) if (~bad).any() else 0.0,
+               primal_within_1e8=float((prim <= 1e-8).mean()) if len(prim) else 0.0,
+               iters_equal=float((g["iters"][both] == c["iters"][both]).mean()) if both.any() else 0.0,
+               status_gpu={int(k): int(v) for k, v in zip(*np.unique(g["status"], return_counts=True))},
+               status_oracle={int(k): int(v) for k, v in zip(*np.unique(c["status"], return_counts=True))},
+               iters_mean_gpu=float(g["iters"].mean()), iters_mean_oracle=float(c["iters"].mean()))
+    ok = lambda k: k["c_max"] <= 1e-6 and k["d_min"] >= -1e-6 and k["stat"] <= 1e-5 and k["z_min"] >= -1e-6 and k["compl"] <= 1e-4
+    out["outliers_certified"] = int(sum(ok(kkt_of(prm, a, g, i, Ts)) and ok(kkt_of(prm, a, c, i, Ts)) for i in idx[bad][:64]))
+    out["outliers_checked"] = int(min(64, bad.sum()))
+    out["outliers_gpu_better"] = int((g["obj"][idx[bad]] < c["obj"][idx[bad]]).sum())
+    if kkt_sample:
+        pick = np.random.default_rng(0).permutation(np.flatnonzero(gs))[:kkt_sample]
+        ks = [kkt_of(prm, a, g, i, Ts) for i in pick]
+        out["kkt"] = dict(sample=int(len(ks)), c_max=float(max(k["c_max"] for k in ks)), d_min=float(min(k["d_min"] for k in ks)),
+                          stat_max=float(max(k["stat"] for k in ks)), stat_p99=float(np.quantile([k["stat"] for k in ks], 0.99)),
+                          z_min=float(min(k["z_min"] for k in ks)), valid=int(sum(ok(k) for k in ks)))
+        # results that ended on the rounding-noise floor (status 2: the solver's own dual error <= 1e-3 only): how
+        # stationary are they when the multipliers are fitted instead of taken from the noisy iterate?
+        fl = np.flatnonzero(g["status"] == 2)[:kkt_sample]
+        kf = [kkt_of(prm, a, g, i, Ts) for i in fl]
+        if kf:
+            out["kkt_floor"] = dict(sample=int(len(kf)), stat_max=float(max(k["stat"] for k in kf)),
+                                    c_max=float(max(k["c_max"] for k in kf)), valid=int(sum(ok(k) for k in kf)))
+    return out
 
 
 # ---- oracle-backed stand-ins (CPU tests only): same interfaces as BatchSolver / obca, C oracle underneath ----------

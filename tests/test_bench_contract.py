@@ -27,6 +27,19 @@ def test_reference_arm_line():
     assert d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the CPU arm plans with the Python A* and runs the oracle: the product's CUDA library is never mapped
+    assert d["native_libraries_loaded"] == ["libobca_oracle.so"]
+    assert sum(d["status_histogram"].values()) == 64 and sum(d["iters_histogram"].values()) == 64
+    assert d["config"]["cfg"] == 3 and d["config"]["batch_per_gpu"] == 8192
+
+
+def test_reference_arm_other_configurations():
+    """--cfg selects the other single-launch BASELINE configurations; --start reference the reference's own start"""
+    d = _run(["--impl", "reference", "--cfg", "5", "--batch", "48", "--steps", "1", "--warmup", "0"])
+    assert d["config"]["cfg"] == 5 and d["config"]["mode"].startswith("FIXED_SET") and d["config"]["rows"] == 24
+    assert "cfg 5" in d["metric"] and sum(d["status_histogram"].values()) == 48
+    d = _run(["--impl", "reference", "--cfg", "2", "--batch", "48", "--steps", "1", "--warmup", "0", "--start", "reference"])
+    assert d["config"]["cfg"] == 2 and "zeros" in d["config"]["init"] and d["success_rate"] > 0.9
 
 
 def test_reference_arm_other_ranks_are_silent():
@@ -38,8 +51,11 @@ def test_reference_arm_other_ranks_are_silent():
 @pytest.mark.gpu
 def test_b200_arm_line_small_batch():
     d = _run(["--batch", "512", "--steps", "3", "--warmup", "3", "--cpu-sample", "128"])
-    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches"} <= set(d)
-    assert d["gpu_launches"] == 3 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert BASE_KEYS | {"roofline", "roofline_fp64", "clocks", "gpu_launches", "status_histogram", "iters_histogram"} <= set(d)
+    # two launches per step: the first-pass kernel and the recovery kernel over the instances it could not solve
+    assert d["gpu_launches"] == 6 and d["value"] > 0 and d["e2e"]["value"] > 0
+    assert d["roofline_fp64"]["peak"] > 10 and d["roofline_fp64"]["unit"] == "TFLOP/s"
+    assert sum(d["status_histogram"].values()) == 512
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12

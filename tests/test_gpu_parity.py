@@ -4,6 +4,8 @@ Tolerances are the north_star's: 1e-4 relative on primal variables (x, u, T), 1e
 lambda / mu are not unique where a distance constraint is inactive, so they are certificate-checked
 (non-negative, dual norm <= 1, signed distance >= dmin) rather than value-compared.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -31,18 +33,15 @@ def _cpu(prm, a, nthreads=8):
 
 
 def _compare(g, c, min_ok=0.9):
+    """small / odd-shaped batches: every instance solved by both within tolerance except a bounded few that took
+    another path (checked strictly, at full size and with certificates, by test_full_size_parity)"""
     both = (g["status"] >= 0) & (c["status"] >= 0)
     assert both.mean() >= min_ok, "only %.3f of the instances solved by both" % both.mean()
-    # the two implementations must agree on feasibility for (nearly) every instance
     assert ((g["status"] >= 0) == (c["status"] >= 0)).mean() >= 0.97
-    for key in ("x", "u"):
-        d = np.abs(g[key][both] - c[key][both]).reshape(both.sum(), -1).max(1)
-        s = np.maximum(1.0, np.abs(c[key][both]).reshape(both.sum(), -1).max(1))
-        assert (d / s <= PRIMAL_RTOL).mean() >= 0.98, (key, np.sort(d / s)[-5:])
-    dT = np.abs(g["T"][both] - c["T"][both]) / np.maximum(1.0, np.abs(c["T"][both]))
-    assert (dT <= PRIMAL_RTOL).mean() >= 0.98
-    dO = np.abs(g["obj"][both] - c["obj"][both]) / np.maximum(1.0, np.abs(c["obj"][both]))
-    assert (dO <= OBJ_RTOL).mean() >= 0.98, np.sort(dO)[-5:]
+    e = common.component_errors(g, c, both)
+    prim = np.maximum.reduce([e["pos"], e["hdg"], e["v"], e["w"], e["T"]])
+    assert (prim <= PRIMAL_RTOL).mean() >= 0.98, np.sort(prim)[-5:]
+    assert (e["obj"] <= OBJ_RTOL).mean() >= 0.98, np.sort(e["obj"])[-5:]
 
 
 def _certificate(prm, a, g, dmin, ego):
@@ -75,9 +74,10 @@ def test_reference_fixtures(name, init):
     prm, a, d = common.fixture_arrays(name, init=init)
     g = _gpu(prm, a); c = _cpu(prm, a, 1)
     if (name, init) == ("demo9_N5_fixed", _abi.INIT_ZERO):
-        # from the reference's all-zero start this one ends at an infeasible stationary point of the constraint
-        # violation in the dense spec solver too (IPOPT would enter restoration); both must report it
-        assert c["status"][0] < 0 and g["status"][0] < 0
+        # from the reference's all-zero start this one ends at a local minimiser of the constraint violation (the
+        # car drives straight at the wall it has to pass; IPOPT: "Converged to a point of local infeasibility"); both
+        # must report it.  With the retry rule it is solved: test_reference_benchmark_problem_on_the_gpu
+        assert c["status"][0] in (-6, -4) and g["status"][0] in (-6, -4)
         return
     assert c["status"][0] >= 0 and g["status"][0] >= 0
     assert common.rel(g["x"], c["x"]) <= PRIMAL_RTOL and common.rel(g["u"], c["u"]) <= PRIMAL_RTOL
@@ -93,30 +93,72 @@ def test_infeasible_reported():
     assert g["status"][0] < 0
 
 
-def test_cfg2_batch():
-    """SURVEY 8(d) cfg 2: 1024 start poses, 2 quads, N = 10, FREE"""
-    b = sc.make_batch(2, 1024)
-    prm, a = common.batch_arrays(b)
-    g = _gpu(prm, a); c = _cpu(prm, a)
-    _compare(g, c)
+# (cfg, batch, start, allowed fraction of outliers among the instances solved by both, feasibility agreement)
+# Free-time configurations: EVERY instance solved by both agrees (0 outliers at the full BASELINE sizes, from the warm
+# start and from the reference's own start with IPOPT's mu_init / bound_push).  Fixed-time cfg 5 has several local
+# solutions per instance (which side of a moving box to pass): paths that go through the restoration phase are
+# chaotic, a few end at a different local solution - each of those must carry a first-order optimality certificate
+# on both sides.
+FULL = [(2, 1024, "warm", 0.0, 0.997), (2, 1024, "reference", 0.0, 0.99), (3, 8192, "warm", 0.0, 0.999),
+        (3, 8192, "reference", 0.0, 0.998), (5, 4096, "warm", 0.03, 0.97)]
+
+
+@pytest.mark.parametrize("cfg,B,start,max_outliers,min_agree", FULL)
+def test_full_size_parity(cfg, B, start, max_outliers, min_agree):
+    """BASELINE configurations at their full batch sizes, default flags (restoration phase on), through the C-ABI,
+    against the C oracle: component-wise 1e-4 on x, u, T and 1e-6 on the objective for EVERY instance solved by both
+    (see FULL for cfg 5), feasibility agreement, and first-order optimality certificates (oracle/obca_nlp.py: primal
+    feasibility, stationarity with fitted multipliers >= 0, complementarity) of 256 GPU results"""
+    b = sc.make_batch(cfg, B)
+    opts = {} if start == "warm" else dict(mu_init=0.1, bound_push=1e-2)
+    prm, a = common.batch_arrays(b, init=_abi.INIT_WARM if start == "warm" else _abi.INIT_ZERO, **opts)
+    g = _gpu(prm, a); c = _cpu(prm, a, nthreads=os.cpu_count() or 8)
+    r = common.parity_summary(prm, a, g, c, kkt_sample=256)
+    print(r)
+    assert r["feasibility_agreement"] >= min_agree, r
+    assert r["both"] >= (0.95 if cfg != 5 else 0.6) * B, r
+    assert r["outliers"] <= max_outliers * r["both"], r
+    assert r["outliers_certified"] == r["outliers_checked"], r          # another local solution, not an error
+    assert r["kkt"]["valid"] >= 0.99 * r["kkt"]["sample"] and r["kkt"]["c_max"] <= 1e-6 and r["kkt"]["d_min"] >= -1e-6, r
     _certificate(prm, a, g, b.dmin, b.ego)
 
 
-def test_cfg3_batch_sample():
-    """cfg 3 (headline shape: 4 quads, N = 20) on 512 instances"""
-    b = sc.make_batch(3, 512)
-    prm, a = common.batch_arrays(b)
-    g = _gpu(prm, a); c = _cpu(prm, a)
-    _compare(g, c)
-    _certificate(prm, a, g, b.dmin, b.ego)
+@pytest.mark.parametrize("cfg,B", [(3, 2048), (5, 2048)])
+def test_interior_point_pass_alone(cfg, B):
+    """restoration phase off: kernel and oracle run the same interior-point pass, so every instance solved by both
+    agrees - also in the fixed-time configuration"""
+    b = sc.make_batch(cfg, B)
+    prm, a = common.batch_arrays(b, init=_abi.INIT_WARM | _abi.INIT_NORESTO)
+    g = _gpu(prm, a); c = _cpu(prm, a, nthreads=os.cpu_count() or 8)
+    r = common.parity_summary(prm, a, g, c)
+    print(r)
+    assert r["feasibility_agreement"] >= 0.99 and r["outliers"] <= 0.002 * r["both"], r
+    assert r["outliers_certified"] == r["outliers_checked"], r
 
 
-def test_cfg5_fixed_moving_obstacles():
-    """cfg 5 shape: 4 static + 2 moving quads, FIXED_SET, N = 20 (time-stacked rows b_k = b0 + k db)"""
-    b = sc.make_batch(5, 256)
-    prm, a = common.batch_arrays(b)
-    g = _gpu(prm, a); c = _cpu(prm, a)
-    _compare(g, c, min_ok=0.5)
+def test_reference_benchmark_problem_on_the_gpu():
+    """demo9, N = 10, start/goal-only reference (simulation.calc_time, the reference's only timed datapoint) through the
+    drop-in class: solved, same answer as the oracle, first-order optimality certificate; and demo9_N5_fixed from the
+    reference's start with the retry rule"""
+    from oracle import c_oracle
+    mode, d = common.load_fixture("demo9_N10_sg_free")
+    s = obca_mod.obca()
+    x, u, feas, Ts_opt = s.obca_mpc4(float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], int(d["N"]), d["x0"], d["xL"],
+                                     d["xU"], d["uL"], d["uU"], d["xref"], int(d["nObs"]), d["vObs"], d["AObs"],
+                                     d["bObs"], float(d["dmin"]), d["ego"], d["u0"])
+    assert feas is True and s.status >= 0
+    assert np.abs(x[:, -1] - d["xref"][:, -1]).max() <= 1e-6
+    init = _abi.INIT_ZERO | _abi.INIT_RETRY | _abi.INIT_PATIENT
+    prm, a, _ = common.fixture_arrays("demo9_N10_sg_free", init=init, mu_init=0.1, bound_push=1e-2)
+    c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], T_max=a["T_max"])
+    g = _gpu(prm, a)
+    assert g["status"][0] >= 0 and c["status"][0] >= 0
+    k = common.kkt_of(prm, a, g)
+    assert k["c_max"] <= 1e-6 and k["d_min"] >= -1e-6 and k["stat"] <= 1e-5, k
+    assert abs(g["obj"][0] - c["obj"][0]) <= 1e-6 * c["obj"][0] and abs(s.obj - c["obj"][0]) <= 1e-6 * c["obj"][0]
+    prm, a, _ = common.fixture_arrays("demo9_N5_fixed", init=_abi.INIT_ZERO | _abi.INIT_RETRY)
+    g = _gpu(prm, a)
+    assert g["status"][0] == 0 and abs(g["obj"][0] - 0.06455441) < 1e-7
 
 
 def test_reference_call_surface():
@@ -147,7 +189,7 @@ def test_device_path_matches_host_path():
     t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
     o = s.solve(t(a["x0"]), t(a["u0"]), t(a["xref"]), t(a["A"]), t(a["b0"]), None, T_max=t(a["T_max"]))
     torch.cuda.synchronize()
-    assert s.launches == 2 and s.last_kernel_ms() > 0
+    assert s.launches == 4 and s.last_kernel_ms() > 0      # per solve: first-pass kernel + recovery kernel
     for k in ("x", "u", "T", "obj", "lam", "mu"):
         assert np.array_equal(o[k].cpu().numpy(), h[k]), k      # same kernel, same inputs: bit-identical
     assert np.array_equal(o["status"].cpu().numpy(), h["status"])
@@ -281,7 +323,7 @@ def test_large_host_batch_goes_through_in_chunks():
     n0 = s.launches
     h = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"],
                      out=s.alloc_host_outputs(B, pinned=True))
-    assert s.launches - n0 == 4
+    assert s.launches - n0 == 8
     A_i = np.tile(a["A"][None], (B, 1, 1)); b_i = np.tile(a["b0"][None], (B, 1))
     h2 = s.solve_host(a["x0"], a["u0"], a["xref"], A_i, b_i, None, T_max=a["T_max"])
     for k in ("x", "u", "T", "obj", "lam", "mu", "status", "iters"):
@@ -301,7 +343,7 @@ def test_large_host_batch_goes_through_in_chunks():
     torch.cuda.synchronize()
     n0 = s.launches
     h = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], term=a["term"], Ts=Ts)
-    assert s.launches - n0 == 4
+    assert s.launches - n0 == 8
     for k in ("x", "u", "obj", "lam", "mu", "status", "iters"):
         assert np.array_equal(o[k].cpu().numpy(), h[k]), k
     s.close()

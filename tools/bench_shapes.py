@@ -26,7 +26,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     for name, sides, N, moving in SHAPES:
         b = sc.make_polygon_batch(sides, B, N, seed=1, moving=moving)
-        prm, a = common.batch_arrays(b)
+        prm, a = sc.batch_arrays(b)
         s = om.BatchSolver(prm, a["edge_ptr"], B)
         t = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
         dv = {k: t(a[k]) for k in ("x0", "u0", "xref", "A", "b0", "db", "T_max", "term")}

@@ -1,11 +1,10 @@
 import os, sys, time, numpy as np
 ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,ROOT); sys.path.insert(0,os.path.join(ROOT,'tests'))
-import obca_testlib as common
 from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om, scenario as sc
 import torch
 cfg=int(sys.argv[1]); B=int(sys.argv[2])
 b=sc.make_batch(cfg,B)
-prm,a=common.batch_arrays(b, init=int(os.environ.get('OBCA_QUICK_INIT', '2')))   # 786 = WARM | RECOVER
+prm,a=sc.batch_arrays(b, init=int(os.environ.get('OBCA_QUICK_INIT', '2')))   # 786 = WARM | RECOVER
 s=om.BatchSolver(prm,a['edge_ptr'],B)
 t=lambda v: None if v is None else torch.as_tensor(v,dtype=torch.float64,device='cuda').contiguous()
 dv={k:t(a[k]) for k in ('x0','u0','xref','A','b0','db','T_max','term')}

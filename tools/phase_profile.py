@@ -21,23 +21,23 @@ PROF = os.path.join(_lib.CSRC, "libobca_b200_prof.so")
 
 
 def build():
-    cmd = ["nvcc"] + _lib.NVCC_FLAGS + ["-DOBCA_PROFILE", "-o", PROF] + _lib.SOURCES
-    subprocess.check_call(cmd, cwd=_lib.CSRC)
+    _lib.build(force=True, extra_flags=["-DOBCA_PROFILE"], out=PROF, objdir=os.path.join(_lib.CSRC, "_obj_prof"))
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "build":      # (here, without a GPU: the library travels to the GPU box)
+        return build()
     cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     if not os.path.exists(PROF) or os.path.getmtime(PROF) < max(
-            os.path.getmtime(os.path.join(_lib.CSRC, f)) for f in _lib.SOURCES + _lib.HEADERS[:1]):
+            os.path.getmtime(os.path.join(_lib.CSRC, f)) for f in _lib.SOURCES + _lib.HEADERS[:2]):
         build()
     _lib.LIB = PROF
     _lib._stale = lambda: False
     import torch
-    import obca_testlib as common
     from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import obca as om, scenario as sc
     b = sc.make_batch(cfg, B)
-    prm, a = common.batch_arrays(b)
+    prm, a = sc.batch_arrays(b)
     s = om.BatchSolver(prm, a["edge_ptr"], B)
     L = _lib.lib()
     t = lambda v: None if v is None else torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()

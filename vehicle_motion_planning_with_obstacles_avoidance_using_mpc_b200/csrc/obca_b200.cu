@@ -53,8 +53,8 @@ struct obca_ctx {
   size_t wd_bytes;
   int64_t wd_stride;
   int64_t launches;
-  cudaEvent_t ev0, ev1;
-  bool timed;
+  cudaEvent_t ev0[OBCA_HOST_CHUNKS], ev1[OBCA_HOST_CHUNKS];   // around the launches of each slot
+  int timed_slots;        // slots used by the last solve call (0: nothing timed yet)
   void* stage;            // host-path staging
   size_t stage_bytes;
   int slots, cfg_slots;   // launches that may be in flight at once (own work counter and checkpoint slots each)
@@ -132,9 +132,49 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   return OBCA_OK;
 }
 
+// fp64 throughput probe: 8 independent DFMA chains per thread, nothing else in the loop.  The solver is bound by the
+// fp64 pipe and its latencies, not by HBM, so bench.py reports the solver's fp64 rate against THIS measured ceiling
+// beside the HBM roofline the metric asks for.
+__global__ void __launch_bounds__(256) obca_dfma_probe(double* out, int iters, double b, double c) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 extern "C" {
 
 int obca_b200_abi_version(void) { return OBCA_B200_ABI_VERSION; }
+
+int obca_b200_fp64_peak(int device, double* tflops) {
+  if (!tflops) return OBCA_E_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return OBCA_E_NODEVICE; }
+  if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return OBCA_E_CUDA;
+  if (device >= ndev || cudaSetDevice(device) != cudaSuccess) return OBCA_E_ARG;
+  const int blocks = sm_count_of(device) * 8, threads = 256, iters = 1 << 14;
+  double* buf = nullptr;
+  if (cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return OBCA_E_NOMEM; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; ++r) {   // first run warms up
+    cudaEventRecord(e0, 0);
+    obca_dfma_probe<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); cudaFree(buf); return OBCA_E_CUDA; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return OBCA_OK;
+}
 
 const char* obca_b200_strerror(int rc) {
   switch (rc) {
@@ -167,7 +207,7 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError(); cudaFree(c->counter); free(c); return OBCA_E_NOMEM;
   }
-  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventCreate(&c->ev0[j]); cudaEventCreate(&c->ev1[j]); }
   cudaEventCreateWithFlags(&c->ev_shared, cudaEventDisableTiming);
   c->slots = 1;
   *out = c;
@@ -181,7 +221,8 @@ int obca_b200_destroy(obca_ctx* c) {
   cudaFree(c->fail_list);
   if (c->stage) cudaFree(c->stage);
   if (c->wd_buf) cudaFree(c->wd_buf);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_shared);
+  for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventDestroy(c->ev0[j]); cudaEventDestroy(c->ev1[j]); }
+  cudaEventDestroy(c->ev_shared);
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) if (c->hs[j]) cudaStreamDestroy(c->hs[j]);
   free(c);
   return OBCA_OK;
@@ -212,11 +253,17 @@ int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
 }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
 
+// Kernel time of the last solve call.  A chunked host solve keeps several launches in flight on separate streams: its
+// kernel time is the span from the start of the first chunk's launch to the end of the last one to finish.
 float obca_b200_last_kernel_ms(obca_ctx* c) {
-  if (!c || !c->timed) return -1.0f;
-  float ms = -1.0f;
-  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
-  return ms;
+  if (!c || c->timed_slots < 1) return -1.0f;
+  float best = -1.0f;
+  for (int j = 0; j < c->timed_slots; ++j) {
+    float ms = -1.0f;
+    if (cudaEventElapsedTime(&ms, c->ev0[0], c->ev1[j]) != cudaSuccess) { cudaGetLastError(); return -1.0f; }
+    if (ms > best) best = ms;
+  }
+  return best;
 }
 
 static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev, const int32_t* index_dev,
@@ -265,7 +312,7 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
 #endif
   if (cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   const int grid = c->grid < batch ? c->grid : batch;
-  if (slot == 0) cudaEventRecord(c->ev0, st);
+  cudaEventRecord(c->ev0[slot], st);
   int nwarps = c->nwarps, has_uref = uref != nullptr;
   void* args[3] = {&kp, &nwarps, &has_uref};
   cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->threads), args, c->smem_bytes, st);
@@ -280,8 +327,8 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
     lerr = cudaLaunchKernel(c->fn_rec, dim3(grid_r), dim3(c->threads), args_r, c->smem_bytes, st);
     c->launches += 1;
   }
-  if (slot == 0) cudaEventRecord(c->ev1, st);
-  c->timed = true;
+  cudaEventRecord(c->ev1[slot], st);
+  c->timed_slots = slot + 1 > c->timed_slots || slot == 0 ? slot + 1 : c->timed_slots;
   c->launches += 1;
   if (lerr != cudaSuccess || cudaGetLastError() != cudaSuccess) return OBCA_E_CUDA;
   return OBCA_OK;

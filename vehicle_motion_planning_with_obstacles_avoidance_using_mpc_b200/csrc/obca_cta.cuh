@@ -2131,6 +2131,9 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
     if (!Eok) { status = OBCA_ST_REGFAIL; break; }
     const double sd = fmax(s_max, (Esumy + Esumz) / (m_eq + q_in)) / s_max, sc = fmax(s_max, Esumz / q_in) / s_max;
     E0 = fmax(fmax(Ee1 / sd, Ee2), Eszmax / sc);
+    // noise-floor level (status 2): IPOPT's scaled error AND the unscaled dual infeasibility within 1e3 acceptable_tol
+    // (diverging multipliers make the scaled error small at points that are not stationary)
+    const bool floor_err = fmax(E0, Ee1) <= 1e3 * P.acceptable_tol;
     if constexpr (RESTO) {
       // the restoration pass ends as soon as the violation of the original problem is below kappa times what it has to
       // beat (IPOPT: 0.9 plus acceptance by the original filter - here that filter starts afresh, so more is asked);
@@ -2170,7 +2173,7 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
     // complementary, with only the dual infeasibility above tol (the rounding-noise floor of a degenerate vertex of the
     // OBCA dual polytope; same condition as at_floor below).  Judged after the barrier update: the iteration that lowers
     // mu to its final value already counts (otherwise a point that is left again one noisy step later is never stored)
-    const int acc_lvl = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && Eth <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    const int acc_lvl = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && Eth <= 1e-6 && floor_err) ? OBCA_ST_FLOOR : 0;
     if (acc_lvl) {
       // IPOPT stores the best acceptable iterate and ends there ("Solved To Acceptable Level") if the run fails later
       // on.  The store goes straight to the result arrays: no on-chip copy is kept.
@@ -2301,7 +2304,7 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
     // clause is the rounding-noise floor of a degenerate vertex of the OBCA dual polytope: barrier parameter at most
     // 1e-6, primal feasible to 1e-6, only the dual infeasibility (non-unique multipliers, block elimination in fp64)
     // above tol.  Every cfg-3 instance that ends here has its objective constant to 11 digits over the last ten steps.
-    const int at_floor = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && E0 <= 1e-3) ? OBCA_ST_FLOOR : 0;
+    const int at_floor = RESTO ? 0 : (E0 <= P.acceptable_tol) ? OBCA_ST_ACCEPTABLE : (mu <= 1e-6 && th <= 1e-6 && floor_err) ? OBCA_ST_FLOOR : 0;
     ex.tick(11);
     ex.trace(iter, RESTO ? th_orig : Ef, th, E0, mu, dw, accepted ? a : -1.0);
     if (!accepted) { status = at_floor ? at_floor : OBCA_ST_LSFAIL; break; }

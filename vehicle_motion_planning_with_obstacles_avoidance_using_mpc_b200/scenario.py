@@ -116,14 +116,19 @@ def update_reference_trajectory(N, ref, x0):
     return ref[:, idx].copy()
 
 
-def sample_instances(rng, grid, static_polys, goal, N, B, free, x_cells=(1, 36), y_cells=(1, 10)):
+def sample_instances(rng, grid, static_polys, goal, N, B, free, x_cells=(1, 36), y_cells=(1, 10), native_planner=True):
     """B start poses on free grid cells (AABB clearance 2) with their A* reference windows; poses whose start or
-    terminal pose collides, or whose T_max (obca.py:961-962) leaves no room for the distance, are redrawn."""
+    terminal pose collides, or whose T_max (obca.py:961-962) leaves no room for the distance, are redrawn.
+    ``native_planner=False`` plans with the Python A* (a_star.py; identical paths, tests/test_planner.py) so that the
+    CUDA library is never loaded - what bench.py's CPU arm does."""
     cells = [(cx, cy) for cx in range(*x_cells) for cy in range(*y_cells)
              if grid[max(cy - 2, 0):cy + 3, max(cx - 2, 0):cx + 3].sum() == 0]
-    # one native batched A* call for every candidate cell (identical to plan_reference per cell)
-    pref, plen_ = plan_batch(grid, [[cx, cy, 0] for cx, cy in cells], [goal])
-    paths = {c: (pref[j, :plen_[j]].T.copy() if plen_[j] > 0 else None) for j, c in enumerate(cells)}
+    if native_planner:
+        # one native batched A* call for every candidate cell (identical to plan_reference per cell)
+        pref, plen_ = plan_batch(grid, [[cx, cy, 0] for cx, cy in cells], [goal])
+        paths = {c: (pref[j, :plen_[j]].T.copy() if plen_[j] > 0 else None) for j, c in enumerate(cells)}
+    else:
+        paths = {c: plan_reference(grid, (c[0], c[1], 0), goal) for c in cells}
     x0 = np.zeros((B, 3)); xref = np.zeros((B, 3, N + 1))
     n = 0
     while n < B:
@@ -150,7 +155,7 @@ def sample_instances(rng, grid, static_polys, goal, N, B, free, x_cells=(1, 36),
     return x0, xref
 
 
-def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_seed=None):
+def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_seed=None, native_planner=True):
     """cfg 2: N=10, 2 quads, FREE.  cfg 3: N=20, 4 quads, FREE (headline).  cfg 5: cfg 3 + 2 dynamic boxes,
     FIXED_SET with Ts = 2.0 and terminal set [x0.x+5, 99] x [1, 9] (closed_loop.py:371).
     ``pose_seed`` draws the start poses from their own stream (same scene, different instances: one shard per
@@ -186,7 +191,7 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_se
 
     if pose_seed is not None:
         rng = np.random.default_rng(pose_seed)
-    x0, xref = sample_instances(rng, grid, polys[:nq], goal, N, B, mode == _o.MODE_FREE)
+    x0, xref = sample_instances(rng, grid, polys[:nq], goal, N, B, mode == _o.MODE_FREE, native_planner=native_planner)
     free = mode == _o.MODE_FREE
     ts = None
     if cfg == 5:
@@ -196,6 +201,24 @@ def make_batch(cfg, B, N=None, n_quads=None, seed=None, goal=(38, 4, 0), pose_se
                  R=[r.copy() for r in (R_FREE if free else R_FIX)], xL=xL, xU=xU, uL=U_L.copy(), uU=U_U.copy(),
                  ego=EGO.copy(), dmin=DMIN, nObs=len(vObs), vObs=vObs, AObs=AObs, bObs=bObs, x0=x0,
                  u0=np.zeros((B, 2)), xref=xref, terminal_set=ts, polygons=polys)
+
+
+def batch_arrays(b, init=None, **opts):
+    """A Batch as the arrays of the C-ABI (include/obca_b200.h): -> (obca_params, dict(x0 [B,3], u0 [B,2],
+    xref [B,N+1,3], edge_ptr, A [R,2], b0 [R], db [R] | None, T_max [B] | None, term [B,3] | None)).  ``opts`` go to
+    _abi.make_params (mu_init, bound_push, retry, ...)."""
+    from . import _abi
+    ep, A, b0, db = _abi.pack_obstacles(b.mode, b.N, b.nObs, b.vObs, b.AObs, b.bObs)
+    prm = _abi.make_params(b.mode, b.N, b.nObs, int(ep[-1]), b.Ts, b.P, b.Q, b.R, b.xL, b.xU, b.uL, b.uU, b.dmin,
+                           b.ego, init=_abi.INIT_WARM if init is None else init, **opts)
+    xref = np.ascontiguousarray(b.xref.transpose(0, 2, 1))
+    Tm = None
+    if _abi.is_free(b.mode):
+        Tm = ((b.xref[:, 0, b.N] - b.x0[:, 0]) + (b.xref[:, 1, b.N] - b.x0[:, 1])) / (b.N * b.uU[0] * b.Ts) + 1.0
+    term = None
+    if b.terminal_set is not None:
+        term = np.stack([b.terminal_set[:, 0, 0], b.terminal_set[:, 1, 0], b.terminal_set[:, 1, 1]], axis=1)
+    return prm, dict(x0=b.x0, u0=b.u0, xref=xref, edge_ptr=ep, A=A, b0=b0, db=db, T_max=Tm, term=term)
 
 
 def regular_polygon(cx, cy, radius, sides, phase=0.0):

@@ -59,15 +59,16 @@ class PackedOutputs:
         return v
 
 
-def gather_packed(packed: PackedOutputs, dst=0, group=None):
+def gather_packed(packed: PackedOutputs, dst=0, group=None, out=None):
     """The single collective of the path: gather every rank's packed buffer to ``dst``.
-    Returns a [world, words] tensor on ``dst`` and None elsewhere."""
+    Returns a [world, words] tensor on ``dst`` (``out`` if given: callers that overlap the gather of one launch with
+    the next launch keep two of them) and None elsewhere.  Runs on the current CUDA stream (NCCL)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if rank == dst:
-        full = torch.empty((world, packed.words), dtype=torch.float64, device=packed.buf.device)
+        full = out if out is not None else torch.empty((world, packed.words), dtype=torch.float64, device=packed.buf.device)
         dist.gather(packed.buf, list(full.unbind(0)), dst=dst, group=group)
         return full
     dist.gather(packed.buf, None, dst=dst, group=group)
