@@ -154,6 +154,9 @@ int  obca_b200_solve_host(obca_ctx* ctx, int batch,
                        int32_t* status, int32_t* iters);
 /* kernel launches issued by this context so far (bench.py's gpu_launches) */
 int64_t obca_b200_launch_count(const obca_ctx* ctx);
+/* diagnostics: input prefetches (cp.async.bulk) that did not complete within the kernel's bounded wait, so that plain
+ * loads took over; expected 0.  Synchronises the device. */
+int64_t obca_b200_bulk_timeouts(obca_ctx* ctx);
 /* elapsed device time (ms) of the last solve's kernel, measured with CUDA events on its stream;
  * valid after the stream was synchronised */
 float obca_b200_last_kernel_ms(obca_ctx* ctx);

@@ -107,3 +107,24 @@ def test_lockstep_batch_equals_single_loops():
         assert np.allclose(got, np.asarray(x_opt, float), rtol=0, atol=1e-7), (i, np.abs(got - np.asarray(x_opt, float)).max())
     # at least one scenario must have met the obstacle (fixed-time phase exercised)
     assert (_abi.MODE_FIXED_SET in modes) or (_abi.MODE_FIXED_NOTERM in modes) or out["failed"].any()
+
+
+def test_sensor_keeps_polygon_and_velocity_paired():
+    """two live moving obstacles (demo11), only the second within lidar range: the fixed-time NLP must be built from the
+    second obstacle's polygon AND the second obstacle's velocity row"""
+    s = ds.problemSetting("demo11")
+    s.senseDis = 8
+    c = cl.closedLoop(s, solver=common.oracle_obca())
+    rows = [list(r) for r in s.dyn_obs_info]
+    assert len(rows) == 2
+    c.x0 = np.array([rows[1][0] - 5.0, rows[1][1], 0.0])          # next to the second obstacle, far from the first
+    rows[0][0] += 60.0                                            # (make sure the first one is out of range)
+    s.dyn_obs_info = rows
+    c.update_obstacle(max(int(r[9]) for r in rows), c.Ts)
+    c.sensor()
+    assert c.fixtime == 1 and s.dyn_nObs == 1 and len(s.dyn_lObs) == 1
+    want = ds.mo.get_obstacle(*s.dyn_obs_info[0][:5])
+    assert np.allclose(np.asarray(s.dyn_lObs[0], float)[:, :2], np.asarray(want, float)[:, :2])
+    assert abs(s.dyn_obs_info[0][0] - (c.x0[0] + 5.0)) < 3.0       # it is the obstacle next to the car
+    nObs, vObs, lObs, info = s.combine_obstacle(1)
+    assert nObs == s.static_nObs + 1 and info[-1] == list(s.dyn_obs_info[0])

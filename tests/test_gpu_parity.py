@@ -393,3 +393,31 @@ def test_restoration_phase_raises_the_success_rate():
     assert ok.mean() >= 0.99
     for k in ("x", "u", "T", "obj", "iters", "status"):
         assert np.array_equal(r0[k][ok], r1[k][ok]), k
+
+
+def test_bulk_copy_staging_completes():
+    """cp.async.bulk prefetch of the next instance's inputs / bulk store of the duals: no prefetch may time out (a timeout
+    falls back to plain loads, so results alone would not show it), for shared and per-instance obstacle rows, odd row
+    sizes (rows that are not 16-byte aligned take the coalesced-copy path) and a batch smaller than the grid"""
+    for cfg, B in ((3, 2048), (2, 700), (3, 5)):
+        b = sc.make_batch(cfg, B)
+        prm, a = common.batch_arrays(b)
+        s = obca_mod.BatchSolver(prm, a["edge_ptr"], B)
+        g = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"])
+        # per-instance obstacle rows: same numbers, every instance its own copy
+        rep = lambda v: None if v is None else np.repeat(v[None], B, 0)
+        g2 = s.solve_host(a["x0"], a["u0"], a["xref"], rep(a["A"]), rep(a["b0"]), rep(a["db"]), T_max=a["T_max"])
+        assert s.bulk_timeouts == 0
+        s.close()
+        for k in ("x", "u", "lam", "mu", "T", "obj", "status", "iters"):
+            assert np.array_equal(g[k], g2[k]), k
+        c = _cpu(prm, a)
+        _compare(g, c)
+    b = sc.make_polygon_batch([3, 5, 7], 96, 9, seed=2)          # R = 15 (odd), N + 1 = 10: lam rows of odd instances unaligned
+    prm, a = common.batch_arrays(b)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], 96)
+    g = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], T_max=a["T_max"], term=a["term"])
+    assert s.bulk_timeouts == 0
+    s.close()
+    _compare(g, _cpu(prm, a), min_ok=0.6)
+    _certificate(prm, a, g, b.dmin, b.ego)

@@ -6,7 +6,7 @@
 import bisect, collections, csv, os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HDR = os.path.join(ROOT, "vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200", "csrc", "obca_cta.cuh")
+HDR = os.environ.get("OBCA_HDR") or os.path.join(ROOT, "vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200", "csrc", "obca_cta.cuh")
 
 
 def main():
@@ -18,8 +18,13 @@ def main():
     starts = [f[0] for f in funcs]
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cub = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))   # the solver's
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+    # one cubin per kernel variant (one translation unit each): take the one that holds the kernel asked for
+    dis = []
+    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+        if any(l.startswith(".text.") and kname in l for l in out.splitlines()):
+            dis = out.splitlines()
+            break
     lines = []; cur = None; infn = False
     for l in dis:
         if l.startswith(".text."):

@@ -84,7 +84,7 @@ def build(force=False, verbose=False, extra_flags=(), out=None, objdir=None):
 
 
 _lib = None
-EXPORTS = ["obca_b200_fp64_peak", "obca_b200_abi_version", "obca_b200_create", "obca_b200_destroy", "obca_b200_scratch_bytes",
+EXPORTS = ["obca_b200_bulk_timeouts", "obca_b200_fp64_peak", "obca_b200_abi_version", "obca_b200_create", "obca_b200_destroy", "obca_b200_scratch_bytes",
            "obca_b200_solve", "obca_b200_solve_host", "obca_b200_launch_count", "obca_b200_last_kernel_ms",
            "obca_b200_strerror", "obca_b200_astar_batch", "obca_b200_reference_windows",
            "obca_b200_solve_indexed", "obca_b200_build_rows", "obca_b200_loop_create", "obca_b200_loop_reset",
@@ -113,6 +113,8 @@ def lib():
     L.obca_b200_launch_count.argtypes = [C.c_void_p]
     L.obca_b200_last_kernel_ms.restype = C.c_float
     L.obca_b200_last_kernel_ms.argtypes = [C.c_void_p]
+    L.obca_b200_bulk_timeouts.restype = C.c_int64
+    L.obca_b200_bulk_timeouts.argtypes = [C.c_void_p]
     L.obca_b200_fp64_peak.restype = C.c_int
     L.obca_b200_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.obca_b200_strerror.restype = C.c_char_p

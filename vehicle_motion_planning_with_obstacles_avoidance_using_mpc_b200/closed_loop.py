@@ -231,8 +231,10 @@ class closedLoop:
                 self.fixtime = 1
                 seen.append(self.setting.dyn_obs_info[i])
             poly.append(1 if hit else 0)
-        self.setting.dyn_obs_info = seen
-        self.setting.dyn_nObs = len(seen)
+        # polygons, vertex counts and info rows of the DETECTED obstacles only, kept paired (with two live obstacles and
+        # only the second one in range the reference's combine_obstacle, demo_setting.py:445-452, would pair the first
+        # polygon with the second velocity - SURVEY Q8 - or raise; the detected obstacle must be the constrained one)
+        self.setting.add_dynamic_obstacle(seen)
 
 
 # ==========================================================================================================

@@ -202,8 +202,10 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   obca_ctx* c = (obca_ctx*)calloc(1, sizeof(obca_ctx));
   if (!c) return OBCA_E_NOMEM;
   c->device = device; c->max_batch = max_batch; c->P = *p;
-  // per launch slot: work counters of the two kernels and the length of the list of failed instances
-  if (cudaMalloc(&c->counter, 3 * OBCA_HOST_CHUNKS * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
+  // per launch slot: work counters of the two kernels and the length of the list of failed instances; last word:
+  // bulk-copy prefetches that timed out (diagnostics, obca_b200_bulk_timeouts)
+  if (cudaMalloc(&c->counter, (3 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(c->counter, 0, (3 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
   if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError(); cudaFree(c->counter); free(c); return OBCA_E_NOMEM;
   }
@@ -252,6 +254,16 @@ int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
                        c->stage_bytes + c->wd_bytes) : 0;
 }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
+
+// diagnostics: bulk-copy input prefetches that did not land within the kernel's bounded wait (the plain loads took
+// over).  Expected 0; synchronises the device.
+int64_t obca_b200_bulk_timeouts(obca_ctx* c) {
+  if (!c) return -1;
+  unsigned int v = 0;
+  if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(&v, c->counter + 3 * OBCA_HOST_CHUNKS, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return (int64_t)v;
+}
 
 // Kernel time of the last solve call.  A chunked host solve keeps several launches in flight on separate streams: its
 // kernel time is the span from the start of the first chunk's launch to the end of the last one to finish.
@@ -307,6 +319,7 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   kp.index = index_dev; kp.count_dev = count_dev;
   const bool recover = obca::recovery_follows(P.init, OBCA_ST_LSFAIL);   // do the flags allow anything after a failed pass?
   if (recover) { kp.fail_list = c->fail_list + (size_t)slot * c->max_batch; kp.fail_count = cnt + 2; }
+  kp.bulk_timeouts = c->counter + 3 * OBCA_HOST_CHUNKS;
 #ifdef OBCA_PROFILE
   kp.prof = prof_buffer();
 #endif

@@ -60,6 +60,7 @@ struct KParams {
   // kernel then solves exactly this work list); NULL: report the failure
   int32_t* fail_list;
   unsigned int* fail_count;
+  unsigned int* bulk_timeouts;   // diagnostics: bulk-copy prefetches that did not complete in time (plain loads took over)
 };
 
 // block-uniform scalar state of one instance (shared memory)
@@ -96,6 +97,7 @@ struct Sm {
   double *A, *B0, *DB, *XREF, *UREF;
   double *NXY, *VXY, *DNXY, *ZR, *UR, *ND, *VD, *DND;   // restoration pass (ZR also carries the caller's guess, OBCA_INIT_GUESS)
   double *RIC, *RED, *SCR_D, *SCR_H;
+  double* PF;   // staging buffer of the next instance's inputs (bulk-copy prefetch, obca_kernel.cuh); starts 16-byte aligned
   uint32_t* TAB;
   Glob* G;
   OB_HD double& st(double* p, int e, int k) const { return p[e * S1 + k]; }
@@ -118,6 +120,22 @@ constexpr int TFH = TF + 29 * 4;   // 29      F entry index | dw class << 8 | (f
 constexpr int TB = TFH + 29;       // 27 x 3  elimination of (v, w): operand references (2 per word)
 constexpr int TAB_N = TB + 27 * 3;
 constexpr uint32_t REF_S = 0x8000u;   // reference flag: add the stage index
+
+// Prefetch buffer: one slot per input array of an instance, each with room for the array plus one double of alignment
+// shift, rounded to an even number of doubles so that every slot starts 16-byte aligned (bulk copies move 16-byte
+// units: an array that starts on an odd double is shifted by one inside its slot).  Slot 0 holds the mbarrier.
+enum { PF_MBAR = 0, PF_XREF, PF_UREF, PF_A, PF_B0, PF_DB, PF_X0, PF_U0, PF_TMAX, PF_TS, PF_TERM, PF_NSLOT };
+OB_HD int pf_len(int slot, int N, int R, int has_uref) {
+  const int n = slot == PF_MBAR ? 2 : slot == PF_XREF ? 3 * (N + 1) : slot == PF_UREF ? (has_uref ? 2 * N : 0) : slot == PF_A ? 2 * R :
+                (slot == PF_B0 || slot == PF_DB) ? R : slot == PF_X0 ? 3 : slot == PF_U0 ? 2 : slot == PF_TERM ? 3 : 1;
+  return n;
+}
+OB_HD int pf_off(int slot, int N, int R, int has_uref) {
+  int o = 0;
+  for (int j = 0; j < slot; ++j) o += (pf_len(j, N, R, has_uref) + 1 + 1) & ~1;
+  return o;
+}
+OB_HD int pf_doubles(int N, int R, int has_uref) { return pf_off(PF_NSLOT, N, R, has_uref); }
 
 OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int has_uref) {
   const int S1 = N + 1, nb = no * S1;
@@ -152,6 +170,8 @@ OB_HD size_t sm_carve(Sm& s, double* base, int N, int no, int R, int nwarps, int
   s.NXY = take(4 * S1); s.VXY = take(4 * S1); s.DNXY = take(4 * S1); s.ZR = take(3 * S1); s.UR = take(2 * S1);
   s.ND = take(nb); s.VD = take(nb); s.DND = take(nb);
   s.RIC = s.SCR_D;   // scratch of the sweep: the step arrays are dead while the sweep runs
+  if (o & 1) take(1);
+  s.PF = take(pf_doubles(N, R, has_uref));
   s.RED = take(NPART + 8 * NPART);
   s.TAB = (uint32_t*)take((TAB_N + 1) / 2);
   s.G = (Glob*)(base + o); o += (sizeof(Glob) + 7) / 8;
@@ -418,31 +438,46 @@ struct Solver {
   // ------------------------------------------------------------------------------------------------
   // instance load (all threads): inputs HBM -> shared, once
   // ------------------------------------------------------------------------------------------------
-  OB_HD void load(int tid, size_t b, bool load_obs) const {
+  // the input arrays of ONE instance (each pointer already at the instance; Tmax / Ts / term / uref / db may be null)
+  struct InstPtrs { const double *xref, *uref, *A, *b0, *db, *x0, *u0, *Tmax, *Ts, *term; };
+  OB_HD InstPtrs inst_ptrs(size_t b) const {
+    const int R = sm.R;
+    const size_t ob = kp.shared_obs ? 0 : b;
+    InstPtrs q;
+    q.xref = kp.xref + b * 3 * S1; q.uref = (sm.has_uref && kp.uref) ? kp.uref + b * 2 * N : nullptr;
+    q.A = kp.A ? kp.A + ob * 2 * R : nullptr; q.b0 = kp.b0 ? kp.b0 + ob * R : nullptr; q.db = kp.db ? kp.db + ob * R : nullptr;
+    q.x0 = kp.x0 + 3 * b; q.u0 = kp.u0 + 2 * b;
+    q.Tmax = (free_ && kp.Tmax) ? kp.Tmax + b : nullptr; q.Ts = kp.Ts_inst ? kp.Ts_inst + b : nullptr;
+    q.term = (has_term && kp.term) ? kp.term + 3 * b : nullptr;
+    return q;
+  }
+  OB_HD void load(int tid, size_t b, bool load_obs) const { load_from(tid, b, inst_ptrs(b), load_obs); }
+  // inputs of instance b -> shared memory, from global memory (inst_ptrs) or from the prefetch buffer the bulk copies
+  // filled (obca_kernel.cuh)
+  OB_HD void load_from(int tid, size_t b, const InstPtrs& q, bool load_obs) const {
     Glob& G = *sm.G;
     const int T = sm.T, R = sm.R;
-    for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = kp.xref[b * 3 * S1 + i];
+    for (int i = tid; i < 3 * S1; i += T) sm.XREF[i] = q.xref[i];
     if ((P.init & 15) == OBCA_INIT_GUESS)   // the caller's poses, read from the output array before it is written
       for (int i = tid; i < 3 * S1; i += T) sm.ZR[(i % 3) * S1 + i / 3] = kp.x[b * 3 * S1 + i];
     if (sm.has_uref)
-      for (int i = tid; i < 2 * N; i += T) sm.UREF[i] = kp.uref[b * 2 * N + i];
+      for (int i = tid; i < 2 * N; i += T) sm.UREF[i] = q.uref[i];
     if (load_obs) {
-      const size_t ob = kp.shared_obs ? 0 : b;
-      for (int i = tid; i < 2 * R; i += T) sm.A[i] = kp.A[ob * 2 * R + i];
+      for (int i = tid; i < 2 * R; i += T) sm.A[i] = q.A[i];
       for (int i = tid; i < R; i += T) {
-        sm.B0[i] = kp.b0[ob * R + i];
-        sm.DB[i] = kp.db ? kp.db[ob * R + i] : 0.0;
+        sm.B0[i] = q.b0[i];
+        sm.DB[i] = q.db ? q.db[i] : 0.0;
       }
     }
     if (tid == 0) {
-      for (int j = 0; j < 3; ++j) G.x0[j] = kp.x0[3 * b + j];
-      for (int j = 0; j < 2; ++j) G.u0[j] = kp.u0[2 * b + j];
-      G.Tmax = (free_ && kp.Tmax) ? kp.Tmax[b] : 1.0;
-      G.Ts = kp.Ts_inst ? kp.Ts_inst[b] : P.Ts;
+      for (int j = 0; j < 3; ++j) G.x0[j] = q.x0[j];
+      for (int j = 0; j < 2; ++j) G.u0[j] = q.u0[j];
+      G.Tmax = q.Tmax ? *q.Tmax : 1.0;
+      G.Ts = q.Ts ? *q.Ts : P.Ts;
       G.init = ((P.init & 15) == OBCA_INIT_GUESS) ? OBCA_INIT_GUESS : (P.init & 15) % 3;
       G.T = 1.0; G.dT = 0.0;
       for (int j = 0; j < 3; ++j) {
-        G.term[j] = (has_term && kp.term) ? kp.term[3 * b + j] : 0.0;
+        G.term[j] = q.term ? q.term[j] : 0.0;
         G.Stm[j] = G.Ztm[j] = 1.0; G.dStm[j] = 0.0; G.yt[j] = 0.0; G.dyt[j] = 0.0;
       }
       G.STb[0] = G.STb[1] = G.ZTb[0] = G.ZTb[1] = 1.0; G.dSTb[0] = G.dSTb[1] = 0.0;
@@ -1974,17 +2009,18 @@ struct Solver {
   // results -> HBM, once:  x [B,N+1,3]  u [B,N,2]  lam [B,N+1,R]  mu [B,N+1,4 no]  T  obj  status  iters
   // ------------------------------------------------------------------------------------------------
   OB_HD void store(int tid, const BlockRegs<EMAX>& br, size_t b, int status, int iters, double obj) const {
+    store_stage(tid, b, status, iters, obj, kp.u + b * N * 2);
+    store_blocks(tid, br, kp.lam + b * S1 * sm.R, kp.mu + b * S1 * 4 * no);
+  }
+  // poses, time scale, objective, status, iterations straight to the result arrays; inputs to `uo` [N,2]
+  OB_HD void store_stage(int tid, size_t b, int status, int iters, double obj, double* uo) const {
     const Glob& G = *sm.G;
-    const int R = sm.R;
     if (is_stage(tid)) {
       const int k = stage_lane(tid);
       double* xo = kp.x + (b * S1 + k) * 3;
 #pragma unroll
       for (int j = 0; j < 3; ++j) xo[j] = sm.st(sm.Z, j, k);
-      if (k < N) {
-        double* uo = kp.u + (b * N + k) * 2;
-        uo[0] = sm.st(sm.U, 0, k); uo[1] = sm.st(sm.U, 1, k);
-      }
+      if (k < N) { uo[2 * k] = sm.st(sm.U, 0, k); uo[2 * k + 1] = sm.st(sm.U, 1, k); }
       if (k == 0) {
         kp.T[b] = free_ ? G.T : 1.0;
         kp.obj[b] = obj;
@@ -1992,15 +2028,18 @@ struct Solver {
         kp.iters[b] = iters;
       }
     }
+  }
+  // OBCA duals of the thread's (obstacle, stage) block to `lo` [N+1,R] / `mo` [N+1,4*n_obs] of this instance
+  OB_HD void store_blocks(int tid, const BlockRegs<EMAX>& br, double* lo, double* mo) const {
     if (is_block(tid)) {
       const int i = br.i, k = br.k, r0 = br.r0, E = br.E;
-      double* lo = kp.lam + (b * S1 + k) * R + r0;
+      double* l = lo + k * sm.R + r0;
 #pragma unroll
       for (int j = 0; j < EMAX; ++j)
-        if (j < E) lo[j] = br.lam[j];
-      double* mo = kp.mu + (b * S1 + k) * 4 * no + 4 * i;
+        if (j < E) l[j] = br.lam[j];
+      double* m = mo + k * 4 * no + 4 * i;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) mo[q] = br.mu[q];
+      for (int q = 0; q < 4; ++q) m[q] = br.mu[q];
     }
   }
 };

@@ -125,7 +125,85 @@ struct DevExec {
   }
 };
 
-extern __shared__ double obca_smem[];
+extern __shared__ __align__(16) double obca_smem[];
+
+// ======================================================================================================
+// Bulk-copy staging (cp.async.bulk + mbarrier; SASS: UBLKCP / SYNCS).  The inputs of an instance are ten small arrays
+// (0.9 KB at the headline shape): while one instance is being solved the copy engine fetches the inputs of the next one
+// into the prefetch buffer Sm::PF, and the OBCA duals of a finished instance - 5.4 KB that the threads would otherwise
+// write as scattered 32-byte pieces - leave through a shared-memory tile as two bulk stores.
+// Bulk copies move multiples of 16 bytes between 16-byte aligned addresses; rows of an [B, n] double array start on an
+// odd double for every other instance, so an array is fetched as  [head double] + 16-byte aligned middle + [tail double]
+// with the middle by bulk copy and the (at most two) end doubles by ordinary loads, shifted by one double inside its
+// slot when the source starts on an odd double.
+// ======================================================================================================
+namespace bulk {
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(void* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(saddr(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s2g_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one input array: n doubles from src into slot `dst` (16-byte aligned).  Returns the bytes the bulk copy will deliver.
+// Element i ends up at dst[shift + i], shift = 1 if src starts on an odd double.
+__device__ __forceinline__ unsigned fetch(double* dst, const double* src, int n, void* bar, bool issue) {
+  if (!src || n <= 0) return 0;
+  const int shift = (int)(((uintptr_t)src >> 3) & 1);
+  const int tail = (n - shift) & 1;                    // a double left over after the 16-byte units
+  const int mid = n - shift - tail;                    // doubles moved by the bulk copy
+  if (!issue) return (unsigned)mid * 8u;
+  if (shift) dst[1] = src[0];
+  if (tail) dst[shift + n - 1] = src[n - 1];
+  if (mid > 0) g2s(dst + 2 * shift, src + shift, (unsigned)mid * 8u, bar);
+  return (unsigned)mid * 8u;
+}
+__device__ __forceinline__ const double* fetched(const double* slot, const double* src) {
+  return src ? slot + (((uintptr_t)src >> 3) & 1) : nullptr;
+}
+}  // namespace bulk
+
+// Prefetch of the inputs of instance b by the stage warp: lane j < 10 owns input array j.
+template <int EMAX>
+__device__ __forceinline__ void prefetch_inputs(const Solver<EMAX>& S, const Sm& sm, size_t b, int lane, bool with_obs) {
+  const typename Solver<EMAX>::InstPtrs q = S.inst_ptrs(b);
+  const int N = sm.N, R = sm.R, hu = sm.has_uref;
+  const double* src[10] = {q.xref, q.uref, with_obs ? q.A : nullptr, with_obs ? q.b0 : nullptr, with_obs ? q.db : nullptr,
+                           q.x0, q.u0, q.Tmax, q.Ts, q.term};
+  const double* my = nullptr;
+  int slot = PF_XREF, n = 0;
+#pragma unroll
+  for (int j = 0; j < 10; ++j)
+    if (lane == j) { my = src[j]; slot = PF_XREF + j; }
+  if (lane < 10) n = pf_len(slot, N, R, hu);
+  double* dst = sm.PF + pf_off(slot, N, R, hu);
+  void* bar = sm.PF;   // slot PF_MBAR
+  const unsigned mine = (lane < 10) ? bulk::fetch(dst, my, n, bar, false) : 0u;
+  const unsigned total = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) bulk::mbar_expect(bar, total);   // the one arrival of this phase + the bytes the copies will deliver
+  __syncwarp();
+  if (lane < 10) bulk::fetch(dst, my, n, bar, true);
+}
 
 // NT/NOT/RT > 0: kernel specialised for horizon NT, NOT obstacles, RT half-space rows (sizes are literals);
 // 0: generic kernel, sizes read from the parameter block.
@@ -151,7 +229,14 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
   ex.stage_warp = (ex.warp == nwarps - 1);
   bool first = true;
   const unsigned int n_items = kp.count_dev ? (unsigned)*kp.count_dev : (unsigned)kp.batch;
+#ifndef OBCA_NO_BULK
+  if (threadIdx.x == 0) bulk::mbar_init(sm.PF, 1);
+  unsigned pf_parity = 0;
+  unsigned int next = 0xfffffffeu;   // 0xfffffffe: no item claimed ahead; 0xffffffff: the queue is empty
+  __syncthreads();
+#endif
   for (;;) {
+#ifdef OBCA_NO_BULK
     if (threadIdx.x == 0) {
       const unsigned int w = atomicAdd(kp.counter, 1u);
       s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
@@ -159,13 +244,67 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     __syncthreads();
     const unsigned int inst = s_inst;
     if (inst == 0xffffffffu) break;
+#else
+    // work item: the one claimed (and prefetched) during the previous solve, else claim now and fetch
+    unsigned int inst = next;
+    if (inst == 0xfffffffeu) {
+      if (threadIdx.x == 0) {
+        const unsigned int w = atomicAdd(kp.counter, 1u);
+        s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
+      }
+      __syncthreads();
+      inst = s_inst;
+      if (inst != 0xffffffffu && ex.stage_warp) prefetch_inputs(S, sm, inst, ex.lane, first || !kp.shared_obs);
+    }
+    if (inst == 0xffffffffu) break;
+#endif
 #if defined(OBCA_P_TICK) || defined(OBCA_P_PAR) || defined(OBCA_P_SWEEP)
     for (int i = 0; i < 16; ++i) { ex.prof[i] = 0; ex.work[i] = 0; }
     ex.prof_t = clock64(); ex.phase = 0;
 #endif
+#ifdef OBCA_NO_BULK
     S.load(ex.tid, inst, first || !kp.shared_obs);
     first = false;
     __syncthreads();
+#else
+    {
+      // wait for the bulk copies of this instance's inputs (bounded: a copy that never lands must not hang the GPU -
+      // the plain loads take over and the event is counted), then move them from the prefetch buffer to their places
+      bool landed = false;
+      for (int spin = 0; spin < (1 << 20) && !landed; ++spin) landed = bulk::mbar_try(sm.PF, pf_parity);
+      pf_parity ^= 1u;
+      landed = __syncthreads_and(landed);
+      const bool with_obs = first || !kp.shared_obs;
+      if (landed) {
+        const int N_ = sm.N, R_ = sm.R, hu = sm.has_uref;
+        const typename Solver<EMAX>::InstPtrs g = S.inst_ptrs(inst);
+        typename Solver<EMAX>::InstPtrs q;
+        auto at = [&](int slot, const double* src) { return bulk::fetched(sm.PF + pf_off(slot, N_, R_, hu), src); };
+        q.xref = at(PF_XREF, g.xref); q.uref = at(PF_UREF, g.uref);
+        q.A = at(PF_A, g.A); q.b0 = at(PF_B0, g.b0); q.db = at(PF_DB, g.db);
+        q.x0 = at(PF_X0, g.x0); q.u0 = at(PF_U0, g.u0); q.Tmax = at(PF_TMAX, g.Tmax); q.Ts = at(PF_TS, g.Ts); q.term = at(PF_TERM, g.term);
+        S.load_from(ex.tid, inst, q, with_obs);
+      } else {
+        if (ex.tid == 0 && kp.bulk_timeouts) atomicAdd(kp.bulk_timeouts, 1u);
+        S.load(ex.tid, inst, with_obs);
+      }
+      first = false;
+      __syncthreads();
+      // claim the next item now and let the copy engine fetch its inputs under this solve - but only while the queue
+      // is long: the last items are claimed when a block is free, so that the end of the batch stays balanced
+      if (threadIdx.x == 0) {
+        unsigned int nx = 0xfffffffeu;
+        if (landed && *(volatile unsigned int*)kp.counter + 2u * gridDim.x < n_items) {
+          const unsigned int w = atomicAdd(kp.counter, 1u);
+          nx = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
+        }
+        s_inst = nx;
+      }
+      __syncthreads();
+      next = s_inst;
+      if (next < 0xfffffffeu && ex.stage_warp) prefetch_inputs(S, sm, next, ex.lane, !kp.shared_obs);
+    }
+#endif
 #if !defined(OBCA_P_PAR)
     ex.phase_id = (int)(inst & 3u);
     for (int i = 0; i < 4; ++i) ex.phase_hits[i] = 0;
@@ -178,8 +317,32 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     else status = solve_pass<EMAX, false>(S, ex, (size_t)inst, ckpt, iters, obj);
     if (!FULL && kp.fail_list && recovery_follows(kp.P.init, status)) {   // (block-uniform)
       if (ex.tid == 0) kp.fail_list[atomicAdd(kp.fail_count, 1u)] = (int32_t)inst;
-    } else if (status != OBCA_ST_STORED) S.store(ex.tid, ex.br, inst, status, iters, obj);
-    else if (ex.tid == 0) { kp.obj[inst] = obj; kp.iters[inst] = iters; }
+    } else if (status != OBCA_ST_STORED) {
+#ifdef OBCA_NO_BULK
+      S.store(ex.tid, ex.br, inst, status, iters, obj);
+#else
+      // results: the small per-stage part straight to HBM; the duals (and inputs) through a shared-memory tile laid out
+      // like the result arrays (in the dual-block scratch, dead now) and out as bulk stores - or, where the instance's
+      // rows are not 16-byte aligned, as a coalesced copy of the tile
+      const int S1_ = sm.S1, R_ = sm.R, no_ = sm.no, N_ = sm.N;
+      double* tile = (double*)(((uintptr_t)sm.ETA + 15) & ~(uintptr_t)15);
+      const int n_lam = S1_ * R_, n_mu = S1_ * 4 * no_, n_u = 2 * N_;
+      double* t_lam = tile; double* t_mu = tile + ((n_lam + 1) & ~1); double* t_u = t_mu + n_mu;
+      double* g_lam = kp.lam + (size_t)inst * n_lam; double* g_mu = kp.mu + (size_t)inst * n_mu; double* g_u = kp.u + (size_t)inst * n_u;
+      S.store_stage(ex.tid, inst, status, iters, obj, t_u);
+      S.store_blocks(ex.tid, ex.br, t_lam, t_mu);
+      bulk::fence_async_smem();
+      __syncthreads();
+      double* const tl[3] = {t_lam, t_mu, t_u}; double* const gl[3] = {g_lam, g_mu, g_u}; const int nn[3] = {n_lam, n_mu, n_u};
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const bool can = (((uintptr_t)gl[j] & 15) == 0) && ((nn[j] & 1) == 0) && nn[j] > 0;
+        if (can) { if (ex.tid == 0) bulk::s2g(gl[j], tl[j], (unsigned)nn[j] * 8u); }
+        else for (int i = ex.tid; i < nn[j]; i += sm.T) gl[j][i] = tl[j][i];
+      }
+      if (ex.tid == 0) bulk::s2g_commit_wait_read();
+#endif
+    } else if (ex.tid == 0) { kp.obj[inst] = obj; kp.iters[inst] = iters; }
 #if !defined(OBCA_P_PAR)
     if (ex.phase_hits[ex.phase_id & 3] < 0) kp.iters[inst] = -1;   // never true: keeps the member alive
 #endif

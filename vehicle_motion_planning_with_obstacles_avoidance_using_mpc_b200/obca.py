@@ -64,6 +64,11 @@ class BatchSolver:
         return int(self._L.obca_b200_launch_count(self._ctx))
 
     @property
+    def bulk_timeouts(self):
+        """input prefetches (cp.async.bulk) that timed out inside the kernel - diagnostics, expected 0"""
+        return int(self._L.obca_b200_bulk_timeouts(self._ctx))
+
+    @property
     def scratch_bytes(self):
         return int(self._L.obca_b200_scratch_bytes(self._ctx))
 
