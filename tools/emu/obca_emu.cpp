@@ -28,6 +28,7 @@ struct HostExec {
   template <class F> void sweep(F&& f) { for (int l = 0; l < 32; ++l) f(l, srs[l]); }
   template <class F> void stage(F&& f) { for (int l = 0; l < 32; ++l) f(l); }
   void stage_end() {}
+  void align() {}
   template <class F> void once(F&& f) { f(); }
   void tick(int) {}
   void trace(int it, double f, double th, double E0, double mu, double dw, double a) {

@@ -42,8 +42,9 @@ struct obca_ctx {
   int max_batch;
   obca_params P;
   int emax;               // largest edge count seen at the last solve (selects the kernel variant)
-  int nwarps, threads, grid;
-  size_t smem_bytes;
+  int nwarps, threads, grid;   // per instance: warps, threads; grid = instances resident on the device (blocks x groups)
+  int groups, blocks;          // first-pass kernel: instances per block, blocks launched (one per SM)
+  size_t smem_bytes;           // per instance
   kernel_fn fn, fn_rec;   // first-pass kernel, recovery kernel
   int grid_rec;
   int32_t* fail_list;     // per launch slot: instances whose first pass failed (max_batch entries each)
@@ -70,18 +71,22 @@ static int sm_count_of(int device) {
 
 // kernel variant for (max edges per obstacle, threads per block); the BASELINE configurations have kernels with
 // compile-time sizes
-static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R) {
+// `groups`: instances a first-pass block hosts side by side (the variant's blocks-per-SM figure: one block per SM)
+static kernel_fn pick_kernel(int emax, int threads, int N, int no, int R, int* groups) {
+  *groups = 3;
   if (emax <= 4 && N == 20 && no == 4 && R == 16) return obca_kv_cfg3();
-  if (emax <= 4 && N == 20 && no == 6 && R == 24) return obca_kv_cfg5();
+  if (emax <= 4 && N == 20 && no == 6 && R == 24) { *groups = 2; return obca_kv_cfg5(); }
   if (emax <= 4 && N == 10 && no == 2 && R == 8) return obca_kv_cfg2();
   if (emax <= 4 && N == 5 && no == 6 && R == 18) return obca_kv_cfg4d();
   if (emax <= 4 && N == 5 && no == 5 && R == 14) return obca_kv_cfg4f();
   if (emax <= 4) {
     if (threads <= 128) return obca_kv_g4_128();
-    if (threads <= 192) return obca_kv_g4_192();
+    if (threads <= 192) { *groups = 2; return obca_kv_g4_192(); }
+    *groups = 1;
     return obca_kv_g4_416();
   }
-  if (threads <= 128) return obca_kv_g8_128();
+  if (threads <= 128) { *groups = 2; return obca_kv_g8_128(); }
+  *groups = 1;
   return obca_kv_g8_416();
 }
 static kernel_fn pick_recovery_kernel(int emax, int threads) {
@@ -97,20 +102,21 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   c->threads = 32 * c->nwarps;
   obca::Sm sm;
   c->smem_bytes = obca::sm_carve(sm, nullptr, P.N, P.n_obs, P.rows, c->nwarps, has_uref) * sizeof(double);
-  c->fn = pick_kernel(emax, c->threads, P.N, P.n_obs, P.rows);
+  c->fn = pick_kernel(emax, c->threads, P.N, P.n_obs, P.rows, &c->groups);
+  c->smem_bytes = (c->smem_bytes + 15) & ~(size_t)15;
   if (c->smem_bytes > 227 * 1024) return OBCA_E_SIZE;
-  if (cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess) {
+  while (c->groups > 1 && c->groups * c->smem_bytes > 227 * 1024) c->groups -= 1;
+  if (cudaFuncSetAttribute(c->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->groups * c->smem_bytes)) != cudaSuccess) {
     cudaGetLastError();
     return OBCA_E_CUDA;
   }
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->fn, c->threads, c->smem_bytes) != cudaSuccess || per_sm < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, c->fn, c->groups * c->threads, c->groups * c->smem_bytes) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     return OBCA_E_CUDA;
   }
-  const char* env = getenv("OBCA_CTAS_PER_SM");
-  if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
-  c->grid = sm_count_of(c->device) * per_sm;
+  c->blocks = sm_count_of(c->device);
+  c->grid = c->blocks * c->groups;
   c->fn_rec = pick_recovery_kernel(emax, c->threads);
   int per_sm_rec = 0;
   if (cudaFuncSetAttribute(c->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
@@ -119,7 +125,7 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
     return OBCA_E_CUDA;
   }
   c->grid_rec = sm_count_of(c->device) * per_sm_rec;
-  if (c->grid_rec > c->grid) c->grid_rec = c->grid;   // (the checkpoint slots are sized for c->grid blocks)
+  if (c->grid_rec > c->grid) c->grid_rec = c->grid;   // (the checkpoint slots are sized for c->grid instances)
   c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
   const size_t need = (size_t)c->slots * c->grid * 2 * c->wd_stride * sizeof(double);   // two checkpoints per resident block
   if (need > c->wd_bytes) {
@@ -324,11 +330,13 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   kp.prof = prof_buffer();
 #endif
   if (cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
-  const int grid = c->grid < batch ? c->grid : batch;
+  kp.smem_stride = (int64_t)(c->smem_bytes / sizeof(double));
+  const int need = (batch + c->groups - 1) / c->groups;
+  const int grid = c->blocks < need ? c->blocks : need;
   cudaEventRecord(c->ev0[slot], st);
   int nwarps = c->nwarps, has_uref = uref != nullptr;
   void* args[3] = {&kp, &nwarps, &has_uref};
-  cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->threads), args, c->smem_bytes, st);
+  cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->groups * c->threads), args, c->groups * c->smem_bytes, st);
   // the recovery kernel over the instances whose first pass failed (restoration phase, fresh starts, other start
   // points).  Their number is only known on the device: the blocks of an empty list exit at once.
   if (lerr == cudaSuccess && recover) {

@@ -61,6 +61,7 @@ struct KParams {
   int32_t* fail_list;
   unsigned int* fail_count;
   unsigned int* bulk_timeouts;   // diagnostics: bulk-copy prefetches that did not complete in time (plain loads took over)
+  int64_t smem_stride;           // doubles of shared memory per instance (a first-pass block hosts several side by side)
 };
 
 // block-uniform scalar state of one instance (shared memory)
@@ -2142,6 +2143,7 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
 
   ex.tick(0);
   for (;;) {
+    ex.align();   // (device, first-pass kernel: rendezvous of the instances that share a block; nothing elsewhere)
     // ---- assemble
     ex.par([&](int tid, BR& br, double* part) {
       if (S.is_block(tid)) S.template assemble_block<RESTO>(tid, br, part);

@@ -16,7 +16,26 @@ namespace obca {
 // slot each fold T/8 consecutive values; stage B: one thread per slot folds the 8 partials into RED[slot].
 // Slots [0, ns) are sums, [ns, ns+nm) maxima, the rest minima.  (Inlined: as a real call it cost ~5 k cycles per
 // reduction in caller-saved register traffic - the block threads carry their iterate in registers.)
-__device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt) {
+// Barrier of one GROUP of threads.  A first-pass block hosts G instances side by side (G groups of T threads, each with
+// its own shared-memory region and its own named barrier 1 + group); the recovery kernel and G = 1 use barrier 0.
+template <int G>
+struct GroupBar {
+  int id, n;   // barrier number, threads taking part
+  __device__ __forceinline__ void sync() const {
+    if constexpr (G == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+  }
+  __device__ __forceinline__ bool sync_and(bool p) const {
+    if constexpr (G == 1) return __syncthreads_and(p);
+    unsigned r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.and.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                 : "=r"(r) : "r"((unsigned)p), "r"(id), "r"(n) : "memory");
+    return r != 0;
+  }
+};
+
+template <class GB>
+__device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T, int tid, int ns, int nm, int nt, const GB& gb) {
   const int L = T >> 3;
   double* P2 = RED + NPART;
   for (int j = tid; j < nt * 8; j += T) {
@@ -33,7 +52,7 @@ __device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T
     }
     P2[j] = a;
   }
-  __syncthreads();
+  gb.sync();
   if (tid < nt) {
     double a = P2[tid * 8];
 #pragma unroll
@@ -43,17 +62,18 @@ __device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T
     }
     RED[tid] = a;
   }
-  __syncthreads();
+  gb.sync();
 }
 
 // Execution model of solve_instance() on the device: one CTA, registers for the per-thread state
-template <int EMAX>
+template <int EMAX, int G>
 struct DevExec {
   BlockRegs<EMAX> br;
   double part[NPART_X];
   double* red;   // block-reduced values (shared memory), valid after reduce()
-  int tid, lane, warp, nwarps;
+  int tid, lane, warp, nwarps;   // (within the group)
   bool stage_warp;
+  GroupBar<G> gb;
 #ifdef OBCA_PROFILE
 #define OBCA_P_TICK
 #define OBCA_P_PAR
@@ -69,7 +89,7 @@ struct DevExec {
     const long long t0 = clock64();
     f(tid, br, part);
     work[phase] += clock64() - t0;
-    __syncthreads();
+    gb.sync();
   }
 #else
   // Home of the per-thread state.  A dynamically indexed member makes this object addressable, so ptxas keeps it in
@@ -82,10 +102,10 @@ struct DevExec {
   template <class F> __device__ __forceinline__ void par(F&& f) {
     f(tid, br, part);
     phase_hits[phase_id & 3] += 1;
-    __syncthreads();
+    gb.sync();
   }
 #endif
-  template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); __syncthreads(); }
+  template <class F> __device__ __forceinline__ void all(F&& f) { f(tid); gb.sync(); }
   SweepRegs sr;
   template <class F> __device__ __forceinline__ void sweep(F&& f) {
 #ifdef OBCA_P_SWEEP
@@ -97,7 +117,13 @@ struct DevExec {
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
   }
-  __device__ __forceinline__ void stage_end() { __syncthreads(); }
+  __device__ __forceinline__ void stage_end() { gb.sync(); }
+  // Top of an interior-point iteration.  The groups of a block run the same code on different instances; left alone
+  // they drift apart and the SM's instruction caches (32 KB against ~150 KB of straight-line code per iteration) serve
+  // three different streams - measured: 3.3 stall cycles per issue waiting for instructions against 1.3 with one block
+  // per SM.  Meeting once per iteration keeps the groups within a few hundred instructions of each other.  The
+  // rendezvous counts the threads of groups that have run out of work (they keep arriving until everybody has).
+  __device__ __forceinline__ void align() { if constexpr (G > 1) __syncthreads_count(0); }
   template <class F> __device__ __forceinline__ void once(F&& f) { if (tid == 0) f(); }
   __device__ __forceinline__ void trace(int, double, double, double, double, double, double) {}
   __device__ __forceinline__ void tick(int i) {
@@ -118,10 +144,10 @@ struct DevExec {
     for (int q = 0; q < NM; ++q) scratch[(NS + q) * rs + pos] = part[M0 + q];
 #pragma unroll
     for (int q = 0; q < NN; ++q) scratch[(NS + NM + q) * rs + pos] = part[N0 + q];
-    __syncthreads();
+    gb.sync();
     // results land at red[slot] = RED[slot]: shift the base so that RED[0] is slot S0 (or M0 / N0 when NS == 0)
     constexpr int first = (NS > 0) ? S0 : ((NM > 0) ? M0 : N0);
-    cta_reduce(scratch, red + first, T, tid, NS, NM, NS + NM + NN);
+    cta_reduce(scratch, red + first, T, tid, NS, NM, NS + NM + NN, gb);
   }
 };
 
@@ -215,44 +241,54 @@ __device__ __forceinline__ void prefetch_inputs(const Solver<EMAX>& S, const Sm&
 // single kernel would run; failures are rare, and the list spreads them over all blocks instead of leaving them as the
 // tail of the block that met them).
 template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0, bool FULL = false>
-__global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
-  __shared__ unsigned int s_inst;
+__global__ void __launch_bounds__(FULL ? MAXT : MAXT * MINB, FULL ? MINB : 1)
+obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
+  // first-pass kernel: G = MINB instances side by side in one block per SM (groups in lockstep, see DevExec::align);
+  // recovery kernel: one instance per block, MINB blocks per SM
+  constexpr int G = FULL ? 1 : MINB;
+  __shared__ unsigned int s_inst_g[G];
   Sm sm;
   constexpr bool fixed = NT > 0;
   const int nwarps = fixed ? (NOT * (NT + 1) + 31) / 32 + 1 : nwarps_rt;
-  if (fixed) sm_carve(sm, obca_smem, NT, NOT, RT, (NOT * (NT + 1) + 31) / 32 + 1, has_uref);
-  else sm_carve(sm, obca_smem, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps_rt, has_uref);
+  const int Tg = 32 * nwarps;                       // threads per group
+  const int gid = (G == 1) ? 0 : (int)threadIdx.x / Tg;
+  const int ltid = (int)threadIdx.x - gid * Tg;
+  double* const base = obca_smem + (size_t)gid * kp.smem_stride;
+  if (fixed) sm_carve(sm, base, NT, NOT, RT, (NOT * (NT + 1) + 31) / 32 + 1, has_uref);
+  else sm_carve(sm, base, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps_rt, has_uref);
+  unsigned int& s_inst = s_inst_g[gid];
   const Solver<EMAX> S(kp, sm);
-  DevExec<EMAX> ex;
+  DevExec<EMAX, G> ex;
   ex.red = sm.RED;
-  ex.tid = threadIdx.x; ex.lane = threadIdx.x & 31; ex.warp = threadIdx.x >> 5; ex.nwarps = nwarps;
+  ex.tid = ltid; ex.lane = ltid & 31; ex.warp = ltid >> 5; ex.nwarps = nwarps;
   ex.stage_warp = (ex.warp == nwarps - 1);
+  ex.gb.id = (G == 1) ? 0 : 1 + gid; ex.gb.n = Tg;
   bool first = true;
   const unsigned int n_items = kp.count_dev ? (unsigned)*kp.count_dev : (unsigned)kp.batch;
 #ifndef OBCA_NO_BULK
-  if (threadIdx.x == 0) bulk::mbar_init(sm.PF, 1);
+  if (ltid == 0) bulk::mbar_init(sm.PF, 1);
   unsigned pf_parity = 0;
   unsigned int next = 0xfffffffeu;   // 0xfffffffe: no item claimed ahead; 0xffffffff: the queue is empty
-  __syncthreads();
+  ex.gb.sync();
 #endif
   for (;;) {
 #ifdef OBCA_NO_BULK
-    if (threadIdx.x == 0) {
+    if (ltid == 0) {
       const unsigned int w = atomicAdd(kp.counter, 1u);
       s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
     }
-    __syncthreads();
+    ex.gb.sync();
     const unsigned int inst = s_inst;
     if (inst == 0xffffffffu) break;
 #else
     // work item: the one claimed (and prefetched) during the previous solve, else claim now and fetch
     unsigned int inst = next;
     if (inst == 0xfffffffeu) {
-      if (threadIdx.x == 0) {
+      if (ltid == 0) {
         const unsigned int w = atomicAdd(kp.counter, 1u);
         s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
       }
-      __syncthreads();
+      ex.gb.sync();
       inst = s_inst;
       if (inst != 0xffffffffu && ex.stage_warp) prefetch_inputs(S, sm, inst, ex.lane, first || !kp.shared_obs);
     }
@@ -265,7 +301,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
 #ifdef OBCA_NO_BULK
     S.load(ex.tid, inst, first || !kp.shared_obs);
     first = false;
-    __syncthreads();
+    ex.gb.sync();
 #else
     {
       // wait for the bulk copies of this instance's inputs (bounded: a copy that never lands must not hang the GPU -
@@ -273,7 +309,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
       bool landed = false;
       for (int spin = 0; spin < (1 << 20) && !landed; ++spin) landed = bulk::mbar_try(sm.PF, pf_parity);
       pf_parity ^= 1u;
-      landed = __syncthreads_and(landed);
+      landed = ex.gb.sync_and(landed);
       const bool with_obs = first || !kp.shared_obs;
       if (landed) {
         const int N_ = sm.N, R_ = sm.R, hu = sm.has_uref;
@@ -289,18 +325,18 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
         S.load(ex.tid, inst, with_obs);
       }
       first = false;
-      __syncthreads();
+      ex.gb.sync();
       // claim the next item now and let the copy engine fetch its inputs under this solve - but only while the queue
-      // is long: the last items are claimed when a block is free, so that the end of the batch stays balanced
-      if (threadIdx.x == 0) {
+      // is long: the last items are claimed when a group is free, so that the end of the batch stays balanced
+      if (ltid == 0) {
         unsigned int nx = 0xfffffffeu;
-        if (landed && *(volatile unsigned int*)kp.counter + 2u * gridDim.x < n_items) {
+        if (landed && *(volatile unsigned int*)kp.counter + 2u * gridDim.x * G < n_items) {
           const unsigned int w = atomicAdd(kp.counter, 1u);
           nx = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
         }
         s_inst = nx;
       }
-      __syncthreads();
+      ex.gb.sync();
       next = s_inst;
       if (next < 0xfffffffeu && ex.stage_warp) prefetch_inputs(S, sm, next, ex.lane, !kp.shared_obs);
     }
@@ -311,11 +347,11 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
 #endif
     int iters = 0;
     double obj = 0.0;
-    double* const ckpt = kp.wd_buf + (size_t)blockIdx.x * 2 * kp.wd_stride;   // watchdog reference | point of failure
+    double* const ckpt = kp.wd_buf + ((size_t)blockIdx.x * G + gid) * 2 * kp.wd_stride;   // watchdog reference | point of failure
     int status;
     if constexpr (FULL) status = solve_with_recovery(S, ex, (size_t)inst, ckpt, ckpt + kp.wd_stride, iters, obj);
     else status = solve_pass<EMAX, false>(S, ex, (size_t)inst, ckpt, iters, obj);
-    if (!FULL && kp.fail_list && recovery_follows(kp.P.init, status)) {   // (block-uniform)
+    if (!FULL && kp.fail_list && recovery_follows(kp.P.init, status)) {   // (group-uniform)
       if (ex.tid == 0) kp.fail_list[atomicAdd(kp.fail_count, 1u)] = (int32_t)inst;
     } else if (status != OBCA_ST_STORED) {
 #ifdef OBCA_NO_BULK
@@ -332,7 +368,7 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
       S.store_stage(ex.tid, inst, status, iters, obj, t_u);
       S.store_blocks(ex.tid, ex.br, t_lam, t_mu);
       bulk::fence_async_smem();
-      __syncthreads();
+      ex.gb.sync();
       double* const tl[3] = {t_lam, t_mu, t_u}; double* const gl[3] = {g_lam, g_mu, g_u}; const int nn[3] = {n_lam, n_mu, n_u};
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -352,8 +388,12 @@ __global__ void __launch_bounds__(MAXT, MINB) obca_solve_kernel(const __grid_con
     if (ex.stage_warp && ex.lane == 0 && kp.prof)
       for (int i = 0; i < 16; ++i) atomicAdd(&kp.prof[32 + i], (unsigned long long)ex.work[i]);
 #endif
-    __syncthreads();
+    ex.gb.sync();
   }
+  // out of work: keep the block's rendezvous going until every group is (the count is taken by the barrier itself, so
+  // all threads of the block see the same number in the same round and leave together)
+  if constexpr (G > 1)
+    while (__syncthreads_count(1) < (int)blockDim.x) {}
 }
 
 }  // namespace obca
