@@ -210,10 +210,25 @@ def main():
     d = {k: t(a[k]) for k in KEYS}
     # two result buffers: the gather of launch k (side stream) runs under launch k+1
     packed = [sharding.PackedOutputs(B, prm.N, prm.rows, prm.n_obs, device=dev) for _ in range(2 if world > 1 else 1)]
-    full = [torch.empty((world, packed[0].words), dtype=torch.float64, device=dev) for _ in packed] if (world > 1 and rank == 0) else [None, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
-    side = torch.cuda.Stream(dev) if world > 1 else None
+    # the gather: peer-to-peer copies into rank 0's buffer on a side stream (copy engines, overlapped with the next
+    # launch); if the node refuses peer access, ONE NCCL gather per step on the launch stream
+    peer = None
+    full = [None, None]
+    if world > 1:
+        try:
+            peer = sharding.PeerGather(packed[0].words, 2, dev)
+            if rank == 0:
+                full = [peer.full[0], peer.full[1]]
+        except Exception as e:                                     # noqa: BLE001
+            peer = None
+            if rank == 0:
+                print("bench: peer-to-peer gather unavailable (%s); NCCL gather on the launch stream" % e, file=sys.stderr)
+                full = [torch.empty((world, packed[0].words), dtype=torch.float64, device=dev) for _ in packed]
+        config["parallelism"] = "batch-sharded x%d, %s" % (world, "one peer-to-peer copy of the packed results per rank into rank 0's "
+                                                          "buffer (NVLink, copy engines), overlapped with the next launch" if peer else
+                                                          "one NCCL gather of the packed results")
 
     def solve_into(pk, src=d):
         solver.solve(src["x0"], src["u0"], src["xref"], src["A"], src["b0"], src["db"], T_max=src["T_max"], term=src["term"],
@@ -235,17 +250,14 @@ def main():
             solve_into(packed[j], src)
             e1.record(stream)
             evs.append((e0, e1))
-            if world > 1:
-                side.wait_event(e1)
-                with torch.cuda.stream(side):
-                    sharding.gather_packed(packed[j], dst=0, out=full[j])
-                    if after:
-                        after(k, j)
-                    done[j] = torch.cuda.Event(); done[j].record(side)
-            elif after:
+            if peer is not None:
+                done[j] = peer.push(packed[j], j, e1)
+            elif world > 1:
+                sharding.gather_packed(packed[j], dst=0, out=full[j])
+            if after:
                 after(k, j)
-        if world > 1:
-            stream.wait_stream(side)
+        if peer is not None:
+            stream.wait_stream(peer.side)
         return evs
 
     def barrier():
@@ -315,6 +327,8 @@ def main():
                     dd[key].copy_(v, non_blocking=True)
 
         def d2h_copy(k, j):
+            if peer is not None:
+                peer.wait_all()                        # every rank's row of step k has landed in rank 0's buffer
             if rank == 0:
                 hfull.copy_(full[j], non_blocking=True)
         run_steps(1, src=dd, before=h2d_copy, after=d2h_copy)

@@ -46,7 +46,6 @@ struct obca_ctx {
   int groups, blocks;          // first-pass kernel: instances per block, blocks launched (one per SM)
   size_t smem_bytes;           // per instance
   kernel_fn fn, fn_rec;   // first-pass kernel, recovery kernel
-  int grid_rec;
   int32_t* fail_list;     // per launch slot: instances whose first pass failed (max_batch entries each)
   int cfg_emax, cfg_uref; // configuration the launch geometry was computed for
   unsigned int* counter;
@@ -60,6 +59,8 @@ struct obca_ctx {
   size_t stage_bytes;
   int slots, cfg_slots;   // launches that may be in flight at once (own work counter and checkpoint slots each)
   cudaStream_t hs[OBCA_HOST_CHUNKS];   // host path: one stream per chunk of a large batch
+  cudaStream_t aux[OBCA_HOST_CHUNKS];  // per launch slot: stream of the recovery block that runs beside the first pass
+  cudaEvent_t ev_fork[OBCA_HOST_CHUNKS], ev_join[OBCA_HOST_CHUNKS];
   cudaEvent_t ev_shared;
 };
 
@@ -119,15 +120,14 @@ static int configure(obca_ctx* c, int emax, int has_uref) {
   c->grid = c->blocks * c->groups;
   c->fn_rec = pick_recovery_kernel(emax, c->threads);
   int per_sm_rec = 0;
-  if (cudaFuncSetAttribute(c->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rec, c->fn_rec, c->threads, c->smem_bytes) != cudaSuccess || per_sm_rec < 1) {
+  if (cudaFuncSetAttribute(c->fn_rec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->groups * c->smem_bytes)) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_rec, c->fn_rec, c->groups * c->threads, c->groups * c->smem_bytes) != cudaSuccess || per_sm_rec < 1) {
     cudaGetLastError();
     return OBCA_E_CUDA;
   }
-  c->grid_rec = sm_count_of(c->device) * per_sm_rec;
-  if (c->grid_rec > c->grid) c->grid_rec = c->grid;   // (the checkpoint slots are sized for c->grid instances)
   c->wd_stride = (emax <= 4) ? obca::Solver<4>::wd_doubles(c->threads, P.N + 1) : obca::Solver<8>::wd_doubles(c->threads, P.N + 1);
-  const size_t need = (size_t)c->slots * c->grid * 2 * c->wd_stride * sizeof(double);   // two checkpoints per resident block
+  // two checkpoints per resident instance; one block more than the first pass uses: the recovery block beside it
+  const size_t need = (size_t)c->slots * (c->grid + c->groups) * 2 * c->wd_stride * sizeof(double);
   if (need > c->wd_bytes) {
     if (c->wd_buf) cudaFree(c->wd_buf);
     c->wd_buf = nullptr; c->wd_bytes = 0;
@@ -208,10 +208,11 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   obca_ctx* c = (obca_ctx*)calloc(1, sizeof(obca_ctx));
   if (!c) return OBCA_E_NOMEM;
   c->device = device; c->max_batch = max_batch; c->P = *p;
-  // per launch slot: work counters of the two kernels and the length of the list of failed instances; last word:
+  // per launch slot: work counter of the first pass, of the recovery, length of the list of failed instances, flag
+  // 'first pass finished'; last word:
   // bulk-copy prefetches that timed out (diagnostics, obca_b200_bulk_timeouts)
-  if (cudaMalloc(&c->counter, (3 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess ||
-      cudaMemset(c->counter, 0, (3 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
+  if (cudaMalloc(&c->counter, (4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMemset(c->counter, 0, (4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
   if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError(); cudaFree(c->counter); free(c); return OBCA_E_NOMEM;
   }
@@ -231,7 +232,10 @@ int obca_b200_destroy(obca_ctx* c) {
   if (c->wd_buf) cudaFree(c->wd_buf);
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventDestroy(c->ev0[j]); cudaEventDestroy(c->ev1[j]); }
   cudaEventDestroy(c->ev_shared);
-  for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) if (c->hs[j]) cudaStreamDestroy(c->hs[j]);
+  for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) {
+    if (c->hs[j]) cudaStreamDestroy(c->hs[j]);
+    if (c->aux[j]) { cudaStreamDestroy(c->aux[j]); cudaEventDestroy(c->ev_fork[j]); cudaEventDestroy(c->ev_join[j]); }
+  }
   free(c);
   return OBCA_OK;
 }
@@ -256,7 +260,7 @@ int obca_b200_prof_read(unsigned long long* out, int reset) {
 // device bytes held by the context: the solver keeps its whole working set on-chip, so this is only the work-queue
 // counter, the watchdog checkpoint slots (one per resident block) and the staging buffer of the host entry point
 int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
-  return c ? (int64_t)(3 * OBCA_HOST_CHUNKS * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * sizeof(int32_t) +
+  return c ? (int64_t)((4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * sizeof(int32_t) +
                        c->stage_bytes + c->wd_bytes) : 0;
 }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
@@ -267,7 +271,7 @@ int64_t obca_b200_bulk_timeouts(obca_ctx* c) {
   if (!c) return -1;
   unsigned int v = 0;
   if (cudaSetDevice(c->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
-      cudaMemcpy(&v, c->counter + 3 * OBCA_HOST_CHUNKS, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+      cudaMemcpy(&v, c->counter + 4 * OBCA_HOST_CHUNKS, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
   return (int64_t)v;
 }
 
@@ -320,33 +324,62 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   kp.x0 = x0; kp.u0 = u0; kp.xref = xref; kp.uref = uref; kp.Tmax = T_max; kp.term = term; kp.Ts_inst = Ts_inst;
   kp.A = A; kp.b0 = b0; kp.db = db;
   kp.x = x; kp.u = u; kp.lam = lam; kp.mu = mu; kp.T = T; kp.obj = obj; kp.status = status; kp.iters = iters;
-  unsigned int* const cnt = c->counter + 3 * slot;   // work counter of the first pass | of the recovery kernel | failures
-  kp.counter = cnt; kp.wd_buf = c->wd_buf + (size_t)slot * c->grid * 2 * c->wd_stride; kp.wd_stride = c->wd_stride;
+  unsigned int* const cnt = c->counter + 4 * slot;   // work counter of the first pass | of the recovery | failures | done flag
+  kp.counter = cnt; kp.wd_buf = c->wd_buf + (size_t)slot * (c->grid + c->groups) * 2 * c->wd_stride; kp.wd_stride = c->wd_stride;
   kp.index = index_dev; kp.count_dev = count_dev;
   const bool recover = obca::recovery_follows(P.init, OBCA_ST_LSFAIL);   // do the flags allow anything after a failed pass?
-  if (recover) { kp.fail_list = c->fail_list + (size_t)slot * c->max_batch; kp.fail_count = cnt + 2; }
-  kp.bulk_timeouts = c->counter + 3 * OBCA_HOST_CHUNKS;
+  int32_t* const fail_list = c->fail_list + (size_t)slot * c->max_batch;
+  if (recover) { kp.fail_list = fail_list; kp.fail_count = cnt + 2; }
+  kp.bulk_timeouts = c->counter + 4 * OBCA_HOST_CHUNKS;
 #ifdef OBCA_PROFILE
   kp.prof = prof_buffer();
 #endif
-  if (cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   kp.smem_stride = (int64_t)(c->smem_bytes / sizeof(double));
-  const int need = (batch + c->groups - 1) / c->groups;
-  const int grid = c->blocks < need ? c->blocks : need;
-  cudaEventRecord(c->ev0[slot], st);
+  if (cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned int), st) != cudaSuccess) return OBCA_E_CUDA;
   int nwarps = c->nwarps, has_uref = uref != nullptr;
-  void* args[3] = {&kp, &nwarps, &has_uref};
-  cudaError_t lerr = cudaLaunchKernel(c->fn, dim3(grid), dim3(c->groups * c->threads), args, c->groups * c->smem_bytes, st);
-  // the recovery kernel over the instances whose first pass failed (restoration phase, fresh starts, other start
-  // points).  Their number is only known on the device: the blocks of an empty list exit at once.
-  if (lerr == cudaSuccess && recover) {
-    obca::KParams kr = kp;
-    kr.counter = cnt + 1; kr.index = kp.fail_list; kr.count_dev = (const int32_t*)kp.fail_count;
+  const dim3 block(c->groups * c->threads);
+  const size_t smem = c->groups * c->smem_bytes;
+  cudaError_t lerr = cudaSuccess;
+  // the recovery block that runs BESIDE the first pass, on the SM that launch leaves free: it polls the list of failed
+  // instances while it is being written (restoration phase, fresh starts, other start points: 100-300 iterations per
+  // instance - as a tail after the launch a single failure would hold the batch for 5-15 ms)
+  obca::KParams kr = kp;
+  const bool beside = recover && c->blocks > 1;
+  if (recover) {
+    kr.counter = cnt + 1; kr.index = fail_list; kr.count_dev = (const int32_t*)(cnt + 2);
     kr.fail_list = nullptr; kr.fail_count = nullptr;
-    void* args_r[3] = {&kr, &nwarps, &has_uref};
-    const int grid_r = c->grid_rec < batch ? c->grid_rec : batch;
-    lerr = cudaLaunchKernel(c->fn_rec, dim3(grid_r), dim3(c->threads), args_r, c->smem_bytes, st);
+    if (cudaMemsetAsync(fail_list, 0xff, (size_t)batch * sizeof(int32_t), st) != cudaSuccess) return OBCA_E_CUDA;
+  }
+  if (beside) {
+    if (!c->aux[slot]) {
+      if (cudaStreamCreateWithFlags(&c->aux[slot], cudaStreamNonBlocking) != cudaSuccess) return OBCA_E_CUDA;
+      cudaEventCreateWithFlags(&c->ev_fork[slot], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&c->ev_join[slot], cudaEventDisableTiming);
+    }
+    obca::KParams kb = kr;
+    kb.poll = cnt + 3; kb.heartbeat = cnt; kb.wd_block0 = c->blocks;
+    void* args_b[3] = {&kb, &nwarps, &has_uref};
+    cudaEventRecord(c->ev_fork[slot], st);
+    cudaStreamWaitEvent(c->aux[slot], c->ev_fork[slot], 0);
+    lerr = cudaLaunchKernel(c->fn_rec, dim3(1), block, args_b, smem, c->aux[slot]);
+    cudaEventRecord(c->ev_join[slot], c->aux[slot]);
     c->launches += 1;
+  }
+  const int width = beside ? c->blocks - 1 : c->blocks;
+  const int need_blocks = (batch + c->groups - 1) / c->groups;
+  const int grid = width < need_blocks ? width : need_blocks;
+  cudaEventRecord(c->ev0[slot], st);
+  void* args[3] = {&kp, &nwarps, &has_uref};
+  if (lerr == cudaSuccess) lerr = cudaLaunchKernel(c->fn, dim3(grid), block, args, smem, st);
+  if (lerr == cudaSuccess && recover) {
+    // first pass finished: tell the block beside it to stop claiming (it finishes the instances it holds), and let the
+    // whole device take what is left of the list - the two share the work counter; the stream joins the side block last
+    if (beside) cudaMemsetAsync(cnt + 3, 1, 1, st);   // (low byte = 1)
+    void* args_r[3] = {&kr, &nwarps, &has_uref};
+    const int grid_r = c->blocks < need_blocks ? c->blocks : need_blocks;
+    lerr = cudaLaunchKernel(c->fn_rec, dim3(grid_r), block, args_r, smem, st);
+    c->launches += 1;
+    if (beside) cudaStreamWaitEvent(st, c->ev_join[slot], 0);
   }
   cudaEventRecord(c->ev1[slot], st);
   c->timed_slots = slot + 1 > c->timed_slots || slot == 0 ? slot + 1 : c->timed_slots;

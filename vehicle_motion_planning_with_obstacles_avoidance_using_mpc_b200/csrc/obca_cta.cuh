@@ -61,7 +61,10 @@ struct KParams {
   int32_t* fail_list;
   unsigned int* fail_count;
   unsigned int* bulk_timeouts;   // diagnostics: bulk-copy prefetches that did not complete in time (plain loads took over)
-  int64_t smem_stride;           // doubles of shared memory per instance (a first-pass block hosts several side by side)
+  int64_t smem_stride;           // doubles of shared memory per instance (a block hosts several side by side)
+  const unsigned int* poll;      // recovery kernel running beside the first pass: != NULL -> poll the list until *poll != 0
+  const unsigned int* heartbeat; // ... and the producer's work counter (no movement for 4 ms: the producer is not running)
+  int32_t wd_block0;             // first checkpoint slot of this launch (the concurrent recovery block has its own)
 };
 
 // block-uniform scalar state of one instance (shared memory)

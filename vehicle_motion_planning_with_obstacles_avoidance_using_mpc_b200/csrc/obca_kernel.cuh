@@ -66,7 +66,7 @@ __device__ __forceinline__ void cta_reduce(const double* buf, double* RED, int T
 }
 
 // Execution model of solve_instance() on the device: one CTA, registers for the per-thread state
-template <int EMAX, int G>
+template <int EMAX, int G, bool LOCKSTEP>
 struct DevExec {
   BlockRegs<EMAX> br;
   double part[NPART_X];
@@ -123,7 +123,7 @@ struct DevExec {
   // three different streams - measured: 3.3 stall cycles per issue waiting for instructions against 1.3 with one block
   // per SM.  Meeting once per iteration keeps the groups within a few hundred instructions of each other.  The
   // rendezvous counts the threads of groups that have run out of work (they keep arriving until everybody has).
-  __device__ __forceinline__ void align() { if constexpr (G > 1) __syncthreads_count(0); }
+  __device__ __forceinline__ void align() { if constexpr (LOCKSTEP && G > 1) __syncthreads_count(0); }
   template <class F> __device__ __forceinline__ void once(F&& f) { if (tid == 0) f(); }
   __device__ __forceinline__ void trace(int, double, double, double, double, double, double) {}
   __device__ __forceinline__ void tick(int i) {
@@ -238,14 +238,15 @@ __device__ __forceinline__ void prefetch_inputs(const Solver<EMAX>& S, const Sm&
 // frame); an instance whose pass fails and that may recover is appended to kp.fail_list instead of being stored.
 // FULL = true: the recovery kernel - the complete sequence (pass, restoration phase, fresh starts, other start points)
 // over that list, started from scratch per instance (the first pass is deterministic, so the sequence is the one a
-// single kernel would run; failures are rare, and the list spreads them over all blocks instead of leaving them as the
-// tail of the block that met them).
+// single kernel would run).  It runs twice per solve: as ONE block on an SM the first-pass launch leaves free, polling
+// the list while the first pass is still running (kp.poll; failures are rare but long - 100 to 300 iterations - and
+// would otherwise be a serial tail after the launch), and then over the whole device for what is left.
 template <int EMAX, int MAXT, int MINB, int NT = 0, int NOT = 0, int RT = 0, bool FULL = false>
-__global__ void __launch_bounds__(FULL ? MAXT : MAXT * MINB, FULL ? MINB : 1)
+__global__ void __launch_bounds__(MAXT * MINB, 1)
 obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_uref) {
-  // first-pass kernel: G = MINB instances side by side in one block per SM (groups in lockstep, see DevExec::align);
-  // recovery kernel: one instance per block, MINB blocks per SM
-  constexpr int G = FULL ? 1 : MINB;
+  // G = MINB instances side by side in one block per SM; in the first-pass kernel the groups run in lockstep (see
+  // DevExec::align), in the recovery kernel they are independent
+  constexpr int G = MINB;
   __shared__ unsigned int s_inst_g[G];
   Sm sm;
   constexpr bool fixed = NT > 0;
@@ -258,7 +259,7 @@ obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_ure
   else sm_carve(sm, base, kp.P.N, kp.P.n_obs, kp.P.rows, nwarps_rt, has_uref);
   unsigned int& s_inst = s_inst_g[gid];
   const Solver<EMAX> S(kp, sm);
-  DevExec<EMAX, G> ex;
+  DevExec<EMAX, G, !FULL> ex;
   ex.red = sm.RED;
   ex.tid = ltid; ex.lane = ltid & 31; ex.warp = ltid >> 5; ex.nwarps = nwarps;
   ex.stage_warp = (ex.warp == nwarps - 1);
@@ -285,8 +286,41 @@ obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_ure
     unsigned int inst = next;
     if (inst == 0xfffffffeu) {
       if (ltid == 0) {
-        const unsigned int w = atomicAdd(kp.counter, 1u);
-        s_inst = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
+        if (FULL && kp.poll) {
+          // consumer of a list that is still being written: claim entry c only once it exists (compare-and-swap, no
+          // overshoot), wait for its value to be published, leave when the producer has finished and nothing is unclaimed
+          // The producer must be RUNNING for this to make sense: under a profiler or sanitizer kernels are serialised and
+          // the first pass would only start after this block has left - so the block also leaves when the producer's
+          // work counter (kp.heartbeat) has not moved for 4 ms; the launch over the whole device that follows takes over.
+          unsigned int got = 0xffffffffu;
+          unsigned int beat = *(volatile unsigned int*)kp.heartbeat;
+          unsigned long long t_beat;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_beat));
+          for (;;) {
+            if (*(volatile unsigned int*)kp.poll) break;      // the first pass has finished: the whole device takes over
+            const unsigned int n = *(volatile unsigned int*)kp.count_dev, c = *(volatile unsigned int*)kp.counter;
+            if (c < n) {
+              if (atomicCAS(kp.counter, c, c + 1u) == c) {
+                int v;
+                while ((v = *(volatile int32_t*)(kp.index + c)) < 0) __nanosleep(200);
+                got = (unsigned)v;
+                break;
+              }
+              continue;
+            }
+            const unsigned int b2 = *(volatile unsigned int*)kp.heartbeat;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (b2 != beat) { beat = b2; t_beat = t; }
+            else if (t - t_beat > 4000000ull) break;
+            __nanosleep(1000);
+          }
+          s_inst = got;
+        } else {
+          const unsigned int w = atomicAdd(kp.counter, 1u);
+          const unsigned int n = (FULL && kp.count_dev) ? *(volatile unsigned int*)kp.count_dev : n_items;
+          s_inst = (w < n) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
+        }
       }
       ex.gb.sync();
       inst = s_inst;
@@ -330,7 +364,7 @@ obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_ure
       // is long: the last items are claimed when a group is free, so that the end of the batch stays balanced
       if (ltid == 0) {
         unsigned int nx = 0xfffffffeu;
-        if (landed && *(volatile unsigned int*)kp.counter + 2u * gridDim.x * G < n_items) {
+        if (!FULL && landed && *(volatile unsigned int*)kp.counter + 2u * gridDim.x * G < n_items) {
           const unsigned int w = atomicAdd(kp.counter, 1u);
           nx = (w < n_items) ? (kp.index ? (unsigned)kp.index[w] : w) : 0xffffffffu;
         }
@@ -347,12 +381,15 @@ obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_ure
 #endif
     int iters = 0;
     double obj = 0.0;
-    double* const ckpt = kp.wd_buf + ((size_t)blockIdx.x * G + gid) * 2 * kp.wd_stride;   // watchdog reference | point of failure
+    double* const ckpt = kp.wd_buf + ((size_t)(kp.wd_block0 + blockIdx.x) * G + gid) * 2 * kp.wd_stride;   // watchdog reference | point of failure
     int status;
     if constexpr (FULL) status = solve_with_recovery(S, ex, (size_t)inst, ckpt, ckpt + kp.wd_stride, iters, obj);
     else status = solve_pass<EMAX, false>(S, ex, (size_t)inst, ckpt, iters, obj);
     if (!FULL && kp.fail_list && recovery_follows(kp.P.init, status)) {   // (group-uniform)
-      if (ex.tid == 0) kp.fail_list[atomicAdd(kp.fail_count, 1u)] = (int32_t)inst;
+      if (ex.tid == 0) {   // (the entry is published after the count: consumers wait for a value >= 0)
+        *(volatile int32_t*)(kp.fail_list + atomicAdd(kp.fail_count, 1u)) = (int32_t)inst;
+        __threadfence();
+      }
     } else if (status != OBCA_ST_STORED) {
 #ifdef OBCA_NO_BULK
       S.store(ex.tid, ex.br, inst, status, iters, obj);
@@ -392,7 +429,7 @@ obca_solve_kernel(const __grid_constant__ KParams kp, int nwarps_rt, int has_ure
   }
   // out of work: keep the block's rendezvous going until every group is (the count is taken by the barrier itself, so
   // all threads of the block see the same number in the same round and leave together)
-  if constexpr (G > 1)
+  if constexpr (G > 1 && !FULL)
     while (__syncthreads_count(1) < (int)blockDim.x) {}
 }
 

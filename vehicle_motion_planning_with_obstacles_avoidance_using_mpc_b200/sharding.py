@@ -75,6 +75,61 @@ def gather_packed(packed: PackedOutputs, dst=0, group=None, out=None):
     return None
 
 
+class PeerGather:
+    """The gather of the packed results as peer-to-peer copies over NVLink: rank 0 owns the [nbuf, world, words] result
+    buffer and shares it with the other ranks of the node (CUDA IPC); every rank copies its packed buffer straight into
+    its row with one asynchronous device-to-device copy on a side stream.  The copy engines move the data, no SM is
+    involved - an NCCL gather issued under the next solver launch has to wait for SMs the persistent solver blocks hold
+    and, once running, keeps them spinning on its peers (measured on two B200: the solver launch 23.4 -> 27.7 ms).
+    Completion is per rank (its own stream); `wait_all` (a barrier) tells rank 0 that every row has landed.
+    Construction is collective and may raise (no peer access, IPC refused): callers fall back to `gather_packed`."""
+
+    def __init__(self, words, nbuf, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.rank, self.world, self.group = dist.get_rank(group), dist.get_world_size(group), group
+        self.side = torch.cuda.Stream(device)
+        ok = 1
+        box = [None]
+        try:
+            if self.rank == 0:
+                self.full = torch.empty((nbuf, self.world, words), dtype=torch.float64, device=device)
+                box = [reduce_tensor(self.full)]
+        except Exception:
+            ok = 0
+        dist.broadcast_object_list(box, src=0, group=group)
+        try:
+            if self.rank != 0:
+                fn, args = box[0]
+                self.full = fn(*args)                   # rank 0's buffer, mapped into this process
+                self.full[0, self.rank, :1].copy_(torch.zeros(1, dtype=torch.float64, device=device))   # (peer access works?)
+                torch.cuda.synchronize(device)
+        except Exception:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag[0]) != 1:
+            raise RuntimeError("peer-to-peer result buffer not available on this node")
+
+    def push(self, packed: PackedOutputs, j, after_event):
+        """row (j, rank) <- this rank's packed buffer, on the side stream, once `after_event` (the solve) has completed.
+        Returns the event that marks the copy done (the packed buffer may be reused after it)."""
+        import torch
+        self.side.wait_event(after_event)
+        with torch.cuda.stream(self.side):
+            self.full[j, self.rank].copy_(packed.buf, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        return done
+
+    def wait_all(self):
+        """every rank's outstanding pushes have landed in rank 0's buffer"""
+        import torch.distributed as dist
+        self.side.synchronize()
+        dist.barrier(group=self.group)
+
+
 def unpack_gathered(packed: PackedOutputs, full, B):
     """[world, words] -> dict of arrays for the first ``B`` instances in global order."""
     import torch
