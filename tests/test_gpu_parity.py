@@ -238,6 +238,91 @@ def test_obca2_uref_and_obca_free():
     assert feas2 and abs(s.obj - 4334.19729465) < 1e-3
 
 
+def _fixture_in_mode(name, mode, has_term, uref=None, **opts):
+    """arrays of a fixed-time fixture re-posed in another mode of the same call family"""
+    _, d = common.load_fixture(name)
+    N, nObs = int(d["N"]), int(d["nObs"])
+    ep, A, b0, db = _abi.pack_obstacles(mode, N, nObs, d["vObs"], d["AObs"], d["bObs"])
+    prm = _abi.make_params(mode, N, nObs, int(ep[-1]), float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], d["xL"], d["xU"],
+                           d["uL"], d["uU"], float(d["dmin"]), d["ego"], has_term=has_term, **opts)
+    a = dict(x0=np.asarray(d["x0"], float).reshape(1, 3), u0=np.asarray(d["u0"], float).reshape(1, 2),
+             xref=np.ascontiguousarray(np.asarray(d["xref"], float).T).reshape(1, N + 1, 3), edge_ptr=ep, A=A, b0=b0, db=db,
+             T_max=None, term=_abi.term_of(d["terminal_set"]).reshape(1, 3) if has_term else None, uref=uref)
+    return prm, a, d
+
+
+def _value_parity(prm, a, g, c):
+    assert g["status"][0] >= 0 and c["status"][0] >= 0, (g["status"], c["status"])
+    e = common.component_errors(g, c, np.array([True]))
+    assert max(e["pos"][0], e["hdg"][0], e["v"][0], e["w"][0], e["T"][0]) <= PRIMAL_RTOL, e
+    assert e["obj"][0] <= OBJ_RTOL, e
+    k = common.kkt_of(prm, a, g)
+    assert k["c_max"] <= 1e-6 and k["d_min"] >= -1e-6 and k["stat"] <= 1e-5 and k["z_min"] >= -1e-6, k
+
+
+@pytest.mark.parametrize("name", ["demo1_N6_fixed", "demo9_N5_fixed"])
+@pytest.mark.parametrize("init", [_abi.INIT_WARM, _abi.INIT_ZERO | _abi.INIT_RETRY])
+def test_fixed_time_legacy_modes_value_parity(name, init):
+    """MODE_FIXED_NOTERM (obca_mpc8, obca.py:1564-1758) and MODE_FIXED_OBCA2 (obca2 with fixtime = 1, obca.py:518-521: with
+    a terminal set, and without one but with uref in the cost) on the reference-generated fixed-time fixtures: x, u within
+    1e-4, objective within 1e-6 of the oracle, first-order optimality certificate of the GPU result; then the same
+    problems through the drop-in methods"""
+    from oracle import c_oracle
+    _, d = common.load_fixture(name)
+    N = int(d["N"])
+    uref = np.tile(np.array([[0.4, 0.0]]), (1, N, 1))
+    cases = [(_abi.MODE_FIXED_NOTERM, False, None), (_abi.MODE_FIXED_OBCA2, True, None), (_abi.MODE_FIXED_OBCA2, False, uref)]
+    objs = []
+    for mode, has_term, ur in cases:
+        prm, a, _ = _fixture_in_mode(name, mode, has_term, ur, init=init)
+        s = obca_mod.BatchSolver(prm, a["edge_ptr"], 1)
+        g = s.solve_host(a["x0"], a["u0"], a["xref"], a["A"], a["b0"], a["db"], term=a["term"], uref=a["uref"])
+        s.close()
+        c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], term=a["term"], uref=a["uref"])
+        _value_parity(prm, a, g, c)
+        objs.append(float(c["obj"][0]))
+    if init != _abi.INIT_WARM:
+        return
+    s = obca_mod.obca()
+    args = (float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], N, d["x0"])
+    rest = (d["xL"], d["xU"], d["uL"], d["uU"], d["xref"])
+    obs = (int(d["nObs"]), d["vObs"], d["AObs"], d["bObs"], float(d["dmin"]), d["ego"])
+    x, u, feas, Ts_opt = s.obca_mpc8(*args, *rest, *obs, d["u0"], None)
+    assert feas is True and Ts_opt == float(d["Ts"]) and abs(s.obj - objs[0]) <= OBJ_RTOL * max(1.0, abs(objs[0]))
+    x, u, feas, Ts_opt = s.obca2(*args, d["u0"], *rest, [], *obs, 1, '', d["terminal_set"])
+    assert feas is True and Ts_opt == float(d["Ts"]) and abs(s.obj - objs[1]) <= OBJ_RTOL * max(1.0, abs(objs[1]))
+    x, u, feas, Ts_opt = s.obca2(*args, d["u0"], *rest, uref[0].T, *obs, 1, '', [])
+    assert feas is True and abs(s.obj - objs[2]) <= OBJ_RTOL * max(1.0, abs(objs[2]))
+
+
+@pytest.mark.parametrize("step,T_expected", [(0.045, 0.8), (0.05, None)])
+def test_obca_small_time_scale_bounds(step, T_expected):
+    """obca.obca(..., fixtime=0, timeScale_size='small'): the time scale confined to [0.8, 1.2] (obca.py:239-240), on a
+    straight reference the car can follow at that scale (from 0.5 m/s); with 4.5 cm between reference points the lower
+    bound is active.  Against the oracle with the same box, through the drop-in method"""
+    from oracle import c_oracle
+    _, d = common.load_fixture("demo1_N6_astar_free")
+    N, nObs = int(d["N"]), int(d["nObs"])
+    xref = np.stack([3 + step * np.arange(N + 1), np.full(N + 1, 4.0), np.zeros(N + 1)], 0)        # (3, N+1), the reference's layout
+    x0 = np.array([3.0, 4.0, 0.0]); u0 = np.array([0.5, 0.0])
+    ep, A, b0, db = _abi.pack_obstacles(_abi.MODE_FREE_STACKED, N, nObs, d["vObs"], d["AObs"], d["bObs"])
+    prm = _abi.make_params(_abi.MODE_FREE_STACKED, N, nObs, int(ep[-1]), float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], d["xL"],
+                           d["xU"], d["uL"], d["uU"], float(d["dmin"]), d["ego"], T_min=0.8)
+    a = dict(x0=x0.reshape(1, 3), u0=u0.reshape(1, 2), xref=np.ascontiguousarray(xref.T)[None], edge_ptr=ep, A=A, b0=b0, db=db,
+             T_max=np.array([1.2]), term=None)
+    c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], ep, A, b0, db, T_max=a["T_max"])
+    g = _gpu(prm, a)
+    _value_parity(prm, a, g, c)
+    assert 0.8 - 1e-7 <= g["T"][0] <= 1.2 + 1e-7
+    if T_expected is not None:
+        assert abs(g["T"][0] - T_expected) <= 1e-6
+    s = obca_mod.obca()
+    x, u, feas, Ts_opt = s.obca(float(d["Ts"]), d["P"], d["Q"], [d["R1"], d["R2"]], N, x0, u0, d["xL"], d["xU"], d["uL"], d["uU"],
+                                xref, [], nObs, d["vObs"], d["AObs"], d["bObs"], float(d["dmin"]), d["ego"], 0, 'small')
+    assert feas is True and abs(s.obj - c["obj"][0]) <= OBJ_RTOL * abs(c["obj"][0])
+    assert abs(Ts_opt - c["T"][0] * float(d["Ts"])) <= 1e-6 and np.abs(x.T - c["x"][0]).max() <= 1e-4
+
+
 def test_sharded_single_rank_path():
     import torch
     from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import sharding

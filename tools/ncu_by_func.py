@@ -16,12 +16,17 @@ def main():
         if re.match(r"\s*(OB_HD|template|struct)\b", l) and ("(" in l or l.startswith("struct")):
             funcs.append((n, l.strip()[:58]))
     starts = [f[0] for f in funcs]
-    tmp = tempfile.mkdtemp()
-    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-    # one cubin per kernel variant (one translation unit each): take the one that holds the kernel asked for
+    # one cubin per kernel variant (one translation unit each, all called obca_variant - extracted from the library they
+    # would overwrite each other, so they are taken from the objects of the build): take the one that holds the kernel
+    objdir = os.path.join(os.path.dirname(os.path.abspath(lib)), "_obj_prof" if "prof" in os.path.basename(lib) else "_obj")
     dis = []
-    for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
-        out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
+    for ob in sorted(f for f in os.listdir(objdir) if f.startswith("obca_kv_") and f.endswith(".o")):
+        tmp = tempfile.mkdtemp()
+        subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(objdir, ob)], cwd=tmp, stdout=subprocess.DEVNULL)
+        cubs = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
+        if not cubs:
+            continue
+        out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubs[0])], capture_output=True, text=True).stdout
         if any(l.startswith(".text.") and kname in l for l in out.splitlines()):
             dis = out.splitlines()
             break
