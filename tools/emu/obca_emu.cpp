@@ -26,6 +26,14 @@ struct HostExec {
   template <class F> void all(F&& f) { for (int t = 0; t < T; ++t) f(t); }
   SweepRegs srs[32];
   template <class F> void sweep(F&& f) { for (int l = 0; l < 32; ++l) f(l, srs[l]); }
+  template <class SolverT> void sweep_stages(const SolverT& S, double mu, double dw) {
+    const obca::SwMemPtr m = S.sweep_mem();
+    for (int s = S.N - 1; s >= 0; --s) {
+      for (int l = 0; l < 32; ++l) obca::SweepOps<obca::SwMemPtr>::w(m, s, srs[l]);
+      for (int l = 0; l < 32; ++l) obca::SweepOps<obca::SwMemPtr>::f(m, s, mu, dw, srs[l]);
+      for (int l = 0; l < 32; ++l) obca::SweepOps<obca::SwMemPtr>::b(m, l, s, srs[l]);
+    }
+  }
   template <class F> void stage(F&& f) { for (int l = 0; l < 32; ++l) f(l); }
   void stage_end() {}
   void align() {}

@@ -14,4 +14,6 @@ for i in range(3):
     torch.cuda.synchronize()
     print('cfg',cfg,'B',B,'kernel ms %.2f -> %.0f solves/s'%(s.last_kernel_ms(),B/s.last_kernel_ms()*1e3), 'scratch MB %.1f'%(s.scratch_bytes/1e6))
 st=out['status'].cpu().numpy(); it=out['iters'].cpu().numpy()
-print('status',{int(v):int((st==v).sum()) for v in np.unique(st)},'iters mean %.1f max %d'%(it.mean(),it.max()))
+import hashlib
+print('status',{int(v):int((st==v).sum()) for v in np.unique(st)},'iters mean %.1f max %d sum %d'%(it.mean(),it.max(),it.sum()),
+      'sha(x,u,obj)',hashlib.sha256(out['x'].cpu().numpy().tobytes()+out['u'].cpu().numpy().tobytes()+out['obj'].cpu().numpy().tobytes()).hexdigest()[:16])

@@ -192,14 +192,22 @@ struct BlockRegs {
   double gf[8];      // stage lanes only: objective gradient of the stage, assemble -> directional derivative
 };
 
-// registers of a stage-warp lane during the Riccati sweep: the operand addresses of its three tasks, decoded once per
-// sweep from the task tables (offsets in doubles from the first shared array; "+s" = add the stage index)
+// registers of a stage-warp lane during the Riccati sweep: the operands of its three tasks, decoded once per sweep from
+// the task tables into BYTE offsets from the first shared array, and a word of flags.  Every lane runs every sub-step
+// without a branch: idle lanes (and absent second destinations) read a per-stage zero and write a dummy scratch word,
+// the two or three forms a sub-step has are selected by flag.  (Measured before this layout, cfg 3: 1,665 cycles per
+// stage, a third of them in reconvergence after the `if (t < 21) ... else ...` bodies and in loads the compiler had
+// serialised between the FMAs - profiles/r2_sweep_sass_before.txt.)
 struct SweepRegs {
-  uint32_t wc[4], wo[4];         // sub-step 1: coefficient / operand offsets, all +s
-  uint32_t fc[4], fo[4], fs;     // sub-step 2: coefficient offsets (+s), operand offsets, fs = 1 if the operands are +s
-  uint32_t fmeta;                //             F entry | dw class << 8 | (feedback slot + 1) << 12
-  uint32_t bo[5], bs;            // sub-step 3: operand offsets, bit p of bs = operand p is +s
+  uint32_t wa[4], wb[4], wp, wd;           // sub-step 1: coefficients (+s), operands (+s), base term (+s), destination
+  uint32_t fa[4], fb[4], fx, fy, fd, fk;   // sub-step 2: coefficients (+s), operands (+s if SW_FS), x, y (+s), destination, feedback slot (+s if SW_FK)
+  uint32_t bo[5], bd;                      // sub-step 3: operands (+s if bit SW_B0 + p), destination (+s if SW_BD)
+  uint32_t ric, bad;                       // the sweep scratch, the "pivot not positive" flag of the instance
+  uint32_t flags;
 };
+enum : uint32_t { SW_PC = 1u, SW_FS = 2u, SW_FF = 4u, SW_FK = 8u, SW_DW_ALL = 16u, SW_DW_GE1 = 32u, SW_DW_EQ0 = 64u,
+                  SW_B0 = 256u, SW_BD = 1u << 13, SW_PV = 1u << 14 };
+constexpr int RIC_DUMMY = 70;   // scratch word nobody reads (RIC: 0..43 F|f, 44..67 W, 80..85 pc)
 
 OB_HD void ob_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
@@ -237,6 +245,97 @@ OB_HD double ob_rsqrt(double x) {
   return 1.0 / sqrt(x);
 #endif
 }
+
+// how the sub-steps reach shared memory: through the generic pointer of the first array (host emulation) or through a
+// 32-bit shared-window address (the device's sweep function, which is a real call and would otherwise see a generic
+// pointer and issue generic loads)
+struct SwMemPtr {
+  char* zb;
+  OB_HD double ld(uint32_t o) const { return *(const double*)(zb + o); }
+  OB_HD void st(uint32_t o, double v) const { *(double*)(zb + o) = v; }
+  OB_HD void set(uint32_t o) const { *(int*)(zb + o) = 1; }
+};
+#if defined(__CUDACC__)
+struct SwMemShared {
+  uint32_t base;
+  __device__ __forceinline__ double ld(uint32_t o) const { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + o)); return v; }
+  __device__ __forceinline__ void st(uint32_t o, double v) const { asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + o), "d"(v) : "memory"); }
+  __device__ __forceinline__ void set(uint32_t o) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + o), "r"(1) : "memory"); }
+};
+#endif
+
+// The three sub-steps of a stage of the Riccati sweep (Solver::fill_tables has the tasks).  Branch-free; all loads of a
+// sub-step are issued before its arithmetic.
+template <class Mem>
+struct SweepOps {
+  // sub-step 1:  W = P_{s+1} At (columns th, T, v, w),  pc = p_{s+1} - P_{s+1} c
+  OB_HD static void w(const Mem& m, int s, const SweepRegs& r) {
+    const uint32_t sb = 8u * (uint32_t)s;
+    double a[4], b[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { a[p] = m.ld(r.wa[p] + sb); b[p] = m.ld(r.wb[p] + sb); }
+    const double pv = m.ld(r.wp + sb);
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc = fma(a[p], b[p], acc);
+    m.st(r.wd, (r.flags & SW_PC) ? pv - acc : acc);
+  }
+  // sub-step 2:  F = H + At^T W (+ dw on the regularised diagonal),  f = mu ra + rb + At^T pc
+  OB_HD static void f(const Mem& m, int s, double mu, double dw, const SweepRegs& r) {
+    const uint32_t sb = 8u * (uint32_t)s, fl = r.flags;
+    const uint32_t sbo = (fl & SW_FS) ? sb : 0u, sbk = (fl & SW_FK) ? sb : 0u;
+    double a[4], b[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) { a[p] = m.ld(r.fa[p] + sb); b[p] = m.ld(r.fb[p] + sbo); }
+    const double x = m.ld(r.fx + sb), y = m.ld(r.fy + sb);
+    double acc = 0.0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc = fma(a[p], b[p], acc);
+    acc += (fl & SW_FF) ? fma(mu, x, y) : y;
+    const bool reg = (fl & SW_DW_ALL) || ((fl & SW_DW_GE1) && s >= 1) || ((fl & SW_DW_EQ0) && s == 0);
+    acc += reg ? dw : 0.0;
+    m.st(r.fd, acc);
+    m.st(r.fk + sbk, acc);
+  }
+  // sub-step 3: eliminate (v, w); cost-to-go of stage s (the feedback gains follow in fwd_prep, lane-parallel)
+  OB_HD static void b(const Mem& m, int t, int s, const SweepRegs& r) {
+    const uint32_t sb = 8u * (uint32_t)s, fl = r.flags;
+    double v[5];
+#pragma unroll
+    for (int p = 0; p < 5; ++p) v[p] = m.ld(r.bo[p] + ((fl & (SW_B0 << p)) ? sb : 0u));
+    const double q00 = m.ld(r.ric + 8u * 27u), q01 = m.ld(r.ric + 8u * 34u), q11 = m.ld(r.ric + 8u * 35u);   // (6,6) (7,6) (7,7)
+    const double det = q00 * q11 - q01 * q01;
+    if (t == 0 && (!(q00 > 0) || !(det > 0))) m.set(r.bad);
+    const double idet = ob_rcp(det);
+    const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
+    // entries: v0 - (v1 X + v2 Y) with (X, Y) = Q^-1 (v3, v4);  p_s rows: the same with (v3, v4) = (f6, f7), i.e. (X, Y) = kap
+    const double X = fma(i00, v[3], i01 * v[4]), Y = fma(i01, v[3], i11 * v[4]);
+    const double pm = v[0] - fma(v[1], X, v[2] * Y);
+    const double pv = fma(-v[2], Y, fma(-v[1], X, v[0]));
+    m.st(r.bd + ((fl & SW_BD) ? sb : 0u), (fl & SW_PV) ? pv : pm);
+  }
+};
+#if defined(__CUDACC__)
+// The stages of the sweep for one lane of the stage warp, as a real call THROUGH A POINTER.  Inlined into the
+// interior-point loop the sub-steps compete for registers with everything that is live across the sweep (~90 block-uniform
+// scalars of the loop), and at the kernel's 168 registers ptxas then interleaves every load with the FMA that consumes it:
+// four shared-memory latencies in a row per sub-step instead of one.  A direct call does not help (ptxas allocates the
+// callee inside the caller's budget); through a pointer the call follows the ABI, the callee saves what it needs
+// (38 registers, once per sweep, stage warp only) and issues the loads of a sub-step together.
+// -DOBCA_SWEEP_DIRECT: the direct call (A/B).
+static __device__ __noinline__ void sweep_lane_dev(uint32_t zbase, SweepRegs r, int t, int N, double mu, double dw) {
+  const SwMemShared m{zbase};
+  for (int s = N - 1; s >= 0; --s) {
+    SweepOps<SwMemShared>::w(m, s, r); __syncwarp();
+    SweepOps<SwMemShared>::f(m, s, mu, dw, r); __syncwarp();
+    SweepOps<SwMemShared>::b(m, t, s, r); __syncwarp();
+  }
+}
+typedef void (*sweep_fn_t)(uint32_t, SweepRegs, int, int, double, double);
+#ifndef OBCA_SWEEP_DIRECT
+static __constant__ sweep_fn_t c_sweep_fn = sweep_lane_dev;
+#endif
+#endif
 // sum of logarithms as the logarithm of a product: mantissas are multiplied, exponents added (one log per thread
 // and phase instead of one per inequality).  Non-positive arguments poison the mantissa with NaN.
 struct LogAcc {
@@ -1337,10 +1436,11 @@ struct Solver {
         tab[TB + 3 * t + 1] = fref(7, a) | (fref(6, b) << 16);
         tab[TB + 3 * t + 2] = fref(7, b);
       } else {
+        // p_s[a] = f[a] - F(6,a) kap0 - F(7,a) kap1, kap = Q^-1 (f6, f7): same operand pattern as the entries above
         const int a = t - 21;
-        tab[TB + 3 * t] = fref(6, a) | (fref(7, a) << 16);
-        tab[TB + 3 * t + 1] = ref_abs(sm.RIC + 36 + a);
-        tab[TB + 3 * t + 2] = 0;
+        tab[TB + 3 * t] = ref_abs(sm.RIC + 36 + a) | (fref(6, a) << 16);
+        tab[TB + 3 * t + 1] = fref(7, a) | (ref_abs(sm.RIC + 42) << 16);
+        tab[TB + 3 * t + 2] = ref_abs(sm.RIC + 43);
       }
     }
   }
@@ -1372,71 +1472,59 @@ struct Solver {
   // decode this lane's three tasks (once per sweep)
   OB_HD void sweep_load(int t, SweepRegs& r) const {
     const uint32_t* tab = sm.TAB;
+    const uint32_t zero = ref_st(sm.DYN, 9);            // DYN element 9 is 0 at every stage
+    const uint32_t dummy = ref_abs(sm.RIC + RIC_DUMMY);
+    auto off = [](uint32_t ref) -> uint32_t { return (ref & 0x7fffu) * 8u; };
+    uint32_t fl = 0;
+    // sub-step 1
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const uint32_t w = (t < 30) ? tab[TW + 4 * t + p] : 0u, f = (t < 29) ? tab[TF + 4 * t + p] : 0u;
-      r.wc[p] = w & 0x7fffu; r.wo[p] = (w >> 16) & 0x7fffu;
-      r.fc[p] = f & 0x7fffu; r.fo[p] = (f >> 16) & 0x7fffu;
-      if (p == 0) r.fs = (f >> 31) & 1u;     // all four operands of a task live in the same array
+      const uint32_t w = (t < 30) ? tab[TW + 4 * t + p] : (zero | (zero << 16));
+      r.wa[p] = off(w); r.wb[p] = off(w >> 16);
     }
-    r.fmeta = (t < 29) ? tab[TFH + t] : 0u;
-    const uint32_t b0 = (t < 27) ? tab[TB + 3 * t] : 0u, b1 = (t < 27) ? tab[TB + 3 * t + 1] : 0u, b2 = (t < 27) ? tab[TB + 3 * t + 2] : 0u;
+    const bool pc = (t >= 24 && t < 30);
+    r.wp = off(pc ? ref_st(sm.PV, t - 24, 1) : zero);
+    r.wd = off((t < 24) ? ref_abs(sm.RIC + 44 + t) : (pc ? ref_abs(sm.RIC + 80 + (t - 24)) : dummy));
+    if (pc) fl |= SW_PC;
+    // sub-step 2
+    uint32_t f0 = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t f = (t < 29) ? tab[TF + 4 * t + p] : (zero | (zero << 16));
+      if (p == 0) f0 = f;
+      r.fa[p] = off(f); r.fb[p] = off(f >> 16);
+    }
+    if ((f0 >> 31) & 1u) fl |= SW_FS;     // all four operands of a task live in the same array
+    const uint32_t fmeta = (t < 29) ? tab[TFH + t] : 0u;
+    const int e = (int)(fmeta & 255u), cls = (int)((fmeta >> 8) & 15u), slot = (int)(fmeta >> 12) - 1;
+    if (t < 21) {
+      r.fx = r.fy = off(ref_st(sm.H, e));
+      if (cls == 2) fl |= SW_DW_ALL;
+      if (cls == 1) fl |= SW_DW_GE1;
+      if (cls == 3 && free_) fl |= SW_DW_EQ0;
+    } else if (t < 29) {
+      r.fx = off(ref_st(sm.RA, e - 36)); r.fy = off(ref_st(sm.RB, e - 36));
+      fl |= SW_FF;
+    } else {
+      r.fx = r.fy = off(zero);
+    }
+    r.fd = off((t < 29) ? ref_abs(sm.RIC + e) : dummy);
+    r.fk = off((t < 29 && slot >= 0) ? ref_st(sm.K, slot) : dummy);
+    if (t < 29 && slot >= 0) fl |= SW_FK;
+    // sub-step 3
+    const uint32_t zz = zero | (zero << 16);
+    const uint32_t b0 = (t < 27) ? tab[TB + 3 * t] : zz, b1 = (t < 27) ? tab[TB + 3 * t + 1] : zz, b2 = (t < 27) ? tab[TB + 3 * t + 2] : zero;
     const uint32_t refs[5] = {b0 & 0xffffu, b0 >> 16, b1 & 0xffffu, b1 >> 16, b2 & 0xffffu};
-    r.bs = 0;
 #pragma unroll
-    for (int p = 0; p < 5; ++p) { r.bo[p] = refs[p] & 0x7fffu; r.bs |= ((refs[p] >> 15) & 1u) << p; }
+    for (int p = 0; p < 5; ++p) { r.bo[p] = off(refs[p]); if (refs[p] & REF_S) fl |= SW_B0 << p; }
+    r.bd = off((t < 21) ? ref_st(sm.PM, t) : ((t < 27) ? ref_st(sm.PV, t - 21) : dummy));
+    if (t < 27) fl |= SW_BD;
+    if (t >= 21 && t < 27) fl |= SW_PV;
+    r.ric = off(ref_abs(sm.RIC));
+    r.bad = (uint32_t)((const char*)&sm.G->bad - (const char*)sm.Z);
+    r.flags = fl;
   }
-  // sub-step 1:  W = P_{s+1} At (columns th, T, v, w),  pc = p_{s+1} - P_{s+1} c
-  OB_HD void ric_w(int t, int s, const SweepRegs& r) const {
-    if (t >= 30) return;
-    const double* B = sm.Z + s;
-    double acc = 0.0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) acc += B[r.wc[p]] * B[r.wo[p]];
-    if (t < 24) sm.RIC[44 + t] = acc;
-    else sm.RIC[80 + (t - 24)] = sm.st(sm.PV, t - 24, s + 1) - acc;
-  }
-  // sub-step 2:  F = H + At^T W (+ dw on the regularised diagonal),  f = mu ra + rb + At^T pc
-  OB_HD void ric_f(int t, int s, double mu, double dw, const SweepRegs& r) const {
-    if (t >= 29) return;
-    const double* B = sm.Z + s;
-    const double* O = sm.Z + (r.fs ? s : 0);
-    double acc = 0.0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) acc += B[r.fc[p]] * O[r.fo[p]];
-    const int e = r.fmeta & 255, cls = (r.fmeta >> 8) & 15, slot = (int)(r.fmeta >> 12) - 1;
-    if (t < 21) {
-      acc += sm.st(sm.H, e, s);
-      if ((cls == 1 && s >= 1) || cls == 2 || (cls == 3 && s == 0 && free_)) acc += dw;
-    } else {
-      const int a = e - 36;
-      acc += mu * sm.st(sm.RA, a, s) + sm.st(sm.RB, a, s);
-    }
-    sm.RIC[e] = acc;
-    if (slot >= 0) sm.st(sm.K, slot, s) = acc;
-  }
-  // sub-step 3: eliminate (v, w); cost-to-go of stage s (the feedback gains follow in fwd_prep, lane-parallel)
-  OB_HD void ric_b(int t, int s, const SweepRegs& r) const {
-    if (t >= 27) return;
-    Glob& G = *sm.G;
-    const double* F = sm.RIC;
-    const double q00 = F[27], q01 = F[34], q11 = F[35];   // (6,6) (7,6) (7,7)
-    const double det = q00 * q11 - q01 * q01;
-    if (t == 0 && (!(q00 > 0) || !(det > 0))) G.bad = 1;
-    const double idet = ob_rcp(det);
-    const double i00 = q11 * idet, i01 = -q01 * idet, i11 = q00 * idet;
-    double v[5];
-#pragma unroll
-    for (int p = 0; p < 5; ++p) v[p] = sm.Z[r.bo[p] + (((r.bs >> p) & 1u) ? s : 0)];
-    if (t < 21) {
-      sm.st(sm.PM, t, s) = v[0] - (v[1] * (i00 * v[3] + i01 * v[4]) + v[2] * (i01 * v[3] + i11 * v[4]));
-    } else {
-      const int a = t - 21;
-      const double f6 = F[42], f7 = F[43];
-      const double kap0 = i00 * f6 + i01 * f7, kap1 = i01 * f6 + i11 * f7;
-      sm.st(sm.PV, a, s) = v[2] - v[0] * kap0 - v[1] * kap1;
-    }
-  }
+  OB_HD SwMemPtr sweep_mem() const { return SwMemPtr{(char*)sm.Z}; }
   OB_HD void ric_finish(int t) const {
     Glob& G = *sm.G;
     if (t == 0 && free_ && !(sm.st(sm.PM, 20, 0) > 0)) G.bad = 1;
@@ -2055,6 +2143,7 @@ struct Solver {
 //                     max of M0.., min of N0.. (results in ex.red[] at the same slots)
 //   all(f)            run f(tid) on every thread of the block, then a block barrier (no per-thread state)
 //   sweep(f)          like stage(f) with the lane's SweepRegs: f(lane, SweepRegs&)
+//   sweep_stages(S, mu, dw)  for s = N-1 .. 0: the three sub-steps (SweepOps) on the stage warp, a warp barrier after each
 //   stage(f)          run f(lane) on the 32 lanes of the stage warp, then a warp barrier (no block barrier)
 //   stage_end()       block barrier closing a run of stage() calls
 //   trace(...), tick(i)  per-iteration / per-phase hooks (no-ops unless profiling)
@@ -2242,11 +2331,7 @@ OB_HD int solve_pass(const Solver<EMAX>& S, Exec& ex, size_t inst, double* wd_bu
       ex.once([&]() { G.bad = 0; });
       ex.stage_end();
       ex.sweep([&](int t, SweepRegs& sr) { S.sweep_load(t, sr); S.template ric_terminal<RESTO>(t, mu, dw, dc); });
-      for (int s = N - 1; s >= 0; --s) {
-        ex.sweep([&](int t, SweepRegs& sr) { S.ric_w(t, s, sr); });
-        ex.sweep([&](int t, SweepRegs& sr) { S.ric_f(t, s, mu, dw, sr); });
-        ex.sweep([&](int t, SweepRegs& sr) { S.ric_b(t, s, sr); });
-      }
+      ex.sweep_stages(S, mu, dw);
       ex.stage([&](int t) { S.ric_finish(t); });
       ex.stage_end();
       if (!G.bad) break;

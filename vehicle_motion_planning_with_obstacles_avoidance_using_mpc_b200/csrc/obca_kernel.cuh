@@ -114,6 +114,22 @@ struct DevExec {
     if (stage_warp) { f(lane, sr); __syncwarp(); }
 #endif
   }
+  // the stages of the Riccati sweep: one warp-uniform branch (the other warps go straight to the block barrier that
+  // follows) around one call per lane
+  template <class SolverT> __device__ __forceinline__ void sweep_stages(const SolverT& S, double mu, double dw) {
+    if (!stage_warp) return;
+#ifdef OBCA_P_SWEEP
+    const long long t0 = clock64();
+#endif
+#ifndef OBCA_SWEEP_DIRECT
+    c_sweep_fn((uint32_t)__cvta_generic_to_shared(S.sm.Z), sr, lane, S.N, mu, dw);
+#else
+    sweep_lane_dev((uint32_t)__cvta_generic_to_shared(S.sm.Z), sr, lane, S.N, mu, dw);
+#endif
+#ifdef OBCA_P_SWEEP
+    work[15] += clock64() - t0; work[14] += 3 * S.N;
+#endif
+  }
   template <class F> __device__ __forceinline__ void stage(F&& f) {
     if (stage_warp) { f(lane); __syncwarp(); }
   }
