@@ -183,3 +183,35 @@ def test_spec_recovery_sequence_matches_c_oracle():
         assert r["iters"] >= r0["iters"]
         agree += abs(r["obj"] - c["obj"][i]) <= 1e-6 * max(1.0, abs(c["obj"][i]))
     assert agree >= 1
+
+
+def test_cfg5_outcomes_against_independent_geometry():
+    """cfg 5 (fixed time, moving boxes): an audit that uses none of the solver's NLP code (tools/audit_cfg5.py: rectangle
+    corners + separating-axis clearance at the 21 sample times).  No instance whose terminal set lies outside the map, or
+    whose fixed start pose is already closer than dmin to an obstacle, may be reported feasible; every trajectory reported
+    feasible keeps the clearance at every sample time and ends in its terminal set.  (The full audit, with the lattice
+    search for the failures that are in neither class, is profiles/r2_cfg5_audit.json.)"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("audit_cfg5", os.path.join(os.path.dirname(common.GOLDEN), "..", "tools", "audit_cfg5.py"))
+    import sys
+    argv = sys.argv; sys.argv = ["audit_cfg5.py"]
+    try:
+        au = importlib.util.module_from_spec(spec); spec.loader.exec_module(au)
+    finally:
+        sys.argv = argv
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import scenario as sc
+    B = 96
+    b = au.prepare(sc.make_batch(5, B))
+    prm, a = sc.batch_arrays(b, init=_abi.INIT_WARM)
+    c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], term=a["term"], nthreads=os.cpu_count() or 1)
+    ok = c["status"] >= 0
+    clsA = b.x0[:, 0] + 5 > b.xU[0]
+    clsB = ~au.clear(b.x0, au.polys_at(b, 0), b.ego, b.dmin)
+    assert (clsA | clsB).sum() >= 5 and ok.sum() >= B // 2
+    assert not (ok & (clsA | clsB)).any()
+    for i in np.flatnonzero(ok):
+        for k in range(b.N + 1):
+            assert au.clear(c["x"][i, k][None], au.polys_at(b, k), b.ego, b.dmin - 1e-6)[0], (i, k)
+        xN = c["x"][i, b.N]
+        assert xN[0] >= b.x0[i, 0] + 5 - 1e-6 and 1 - 1e-6 <= xN[1] <= 9 + 1e-6

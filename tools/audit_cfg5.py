@@ -118,6 +118,21 @@ def search(b, x0, lvl, margin):
 _B = None
 
 
+def prepare(b):
+    """attach the motion (speed, heading) of the two moving boxes to a cfg-5 Batch (make_batch appends them after the
+    static obstacles): recovered from the time-stacked rows, b_k = b_0 + k Ts v A (cos, sin)"""
+    nq = len(b.polygons) - 2
+    b.dyn = {}
+    AObs = np.asarray(b.AObs).reshape(b.N + 1, -1, 2); bObs = np.asarray(b.bObs).reshape(b.N + 1, -1)
+    R0 = 4 * nq
+    for j in range(2):
+        rows = slice(R0 + 4 * j, R0 + 4 * j + 4)
+        db = (bObs[b.N, rows] - bObs[0, rows]) / b.N
+        vel = np.linalg.lstsq(AObs[0, rows], db, rcond=None)[0] / b.Ts
+        b.dyn[nq + j] = (float(np.hypot(*vel)), float(np.arctan2(vel[1], vel[0])))
+    return b
+
+
 def audit_one(i):
     b = _B
     x0 = b.x0[i]
@@ -132,18 +147,7 @@ def audit_one(i):
 def main():
     global _B
     from oracle import c_oracle
-    b = sc.make_batch(5, B)
-    # moving obstacles: index -> (speed, heading); make_batch appends them after the static ones
-    nq = len(b.polygons) - 2
-    rng = np.random.default_rng(20221209 + 5)
-    b.dyn = {}
-    AObs = np.asarray(b.AObs).reshape(b.N + 1, -1, 2); bObs = np.asarray(b.bObs).reshape(b.N + 1, -1)
-    R0 = 4 * nq
-    for j in range(2):                                    # recover (speed, heading) of box j from its time-stacked rows
-        rows = slice(R0 + 4 * j, R0 + 4 * j + 4)
-        db = (bObs[b.N, rows] - bObs[0, rows]) / b.N       # = Ts * speed * A (cos, sin)
-        vel = np.linalg.lstsq(AObs[0, rows], db, rcond=None)[0] / b.Ts
-        b.dyn[nq + j] = (float(np.hypot(*vel)), float(np.arctan2(vel[1], vel[0])))
+    b = prepare(sc.make_batch(5, B))
     _B = b
     prm, a = sc.batch_arrays(b, init=_abi.INIT_WARM)
     c = c_oracle.solve(prm, a["x0"], a["u0"], a["xref"], a["edge_ptr"], a["A"], a["b0"], a["db"], term=a["term"],
