@@ -13,6 +13,6 @@ timeout 600 python bench.py --start reference --steps 5 --warmup 3 --no-cpu-base
 timeout 300 python tools/phase_profile.py 3 8192 > gpurun_out/phase_cfg3.log 2>&1; cat gpurun_out/phase_cfg3.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
 timeout 600 ncu --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum,gpu__time_duration.sum --clock-control none -k regex:obca_solve -s 6 -c 3 --csv --log-file gpurun_out/fp64_counts_cfg3.csv python tools/gpu_quick.py 3 8192 > gpurun_out/fp64_quick.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:obca_solve -s 6 -c 1 -o gpurun_out/prof -f python tools/gpu_quick.py 3 8192 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:obca_solve -s 7 -c 1 -o gpurun_out/prof -f python tools/gpu_quick.py 3 8192 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
