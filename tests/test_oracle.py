@@ -52,7 +52,7 @@ def test_kkt_certificate(name):
     assert k["stat"] <= 1e-4 and k["z_min"] >= 0
 
 
-@pytest.mark.parametrize("name", ["demo1_N6_astar_free", "demo9_N5_astar_free", "demo9_N6_astar_free", "demo1_N6_fixed"])
+@pytest.mark.parametrize("name", common.FEASIBLE)
 def test_scipy_cross_check(name):
     """SLSQP (independent SQP code, SciPy) on the NumPy restatement, started near the oracle's solution, ends at the same
     objective to 1e-6 relative"""
@@ -215,3 +215,17 @@ def test_cfg5_outcomes_against_independent_geometry():
             assert au.clear(c["x"][i, k][None], au.polys_at(b, k), b.ego, b.dmin - 1e-6)[0], (i, k)
         xN = c["x"][i, b.N]
         assert xN[0] >= b.x0[i, 0] + 5 - 1e-6 and 1 - 1e-6 <= xN[1] <= 9 + 1e-6
+
+
+@pytest.mark.parametrize("name", common.FEASIBLE)
+def test_scipy_from_the_warm_start_reaches_the_oracle_optimum(name):
+    """SLSQP - an SQP code that shares nothing with the interior-point method - started from the warm start point of
+    oracle/obca_nlp.start_point (poses on the reference window, T from the arc length, duals from the most separating
+    face: no solver output in it) ends at the oracle's objective to 1e-6 on every reference-generated fixture, free-time and
+    fixed-time.  With test_kkt_certificate this is what stands in for the IPOPT run that cannot be made here."""
+    prm, a, c = _c(name, _abi.INIT_WARM)
+    f, T, cmax, dmin = common.slsqp_polish(prm, a, None, start="warm", maxiter=300)
+    assert cmax <= 1e-6 and dmin >= -1e-6
+    assert abs(f - c["obj"][0]) <= 1e-6 * abs(c["obj"][0]), (f, c["obj"][0])
+    if _abi.is_free(prm.mode):
+        assert abs(T - c["T"][0]) <= 1e-5 * c["T"][0]
