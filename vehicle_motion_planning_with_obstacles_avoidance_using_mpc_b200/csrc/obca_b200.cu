@@ -340,37 +340,45 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   const dim3 block(c->groups * c->threads);
   const size_t smem = c->groups * c->smem_bytes;
   cudaError_t lerr = cudaSuccess;
-  // the recovery block that runs BESIDE the first pass, on the SM that launch leaves free: it polls the list of failed
-  // instances while it is being written (restoration phase, fresh starts, other start points: 100-300 iterations per
-  // instance - as a tail after the launch a single failure would hold the batch for 5-15 ms)
+  // The recovery block that runs BESIDE the first pass: it polls the list of failed instances while it is being written
+  // (restoration phase, fresh starts, other start points: 100-300 iterations per instance - as a tail after the launch a
+  // single failure would hold the batch for 5-15 ms).  It is launched AFTER the first pass, which takes every SM: the block
+  // becomes resident when the first first-pass block runs out of work, i.e. in the tail of the launch, where SMs are free
+  // anyway (reserving an SM for it from the start cost 1/148 of the first pass's throughput and bought nothing: what it
+  // can recover early is 1/148 of the recovery work).  OBCA_B200_RESERVE_SM=1 restores the reserved SM (A/B).
   obca::KParams kr = kp;
   const bool beside = recover && c->blocks > 1;
+  static const bool reserve_sm = getenv("OBCA_B200_RESERVE_SM") && atoi(getenv("OBCA_B200_RESERVE_SM")) != 0;
   if (recover) {
     kr.counter = cnt + 1; kr.index = fail_list; kr.count_dev = (const int32_t*)(cnt + 2);
     kr.fail_list = nullptr; kr.fail_count = nullptr;
     if (cudaMemsetAsync(fail_list, 0xff, (size_t)batch * sizeof(int32_t), st) != cudaSuccess) return OBCA_E_CUDA;
   }
+  auto launch_beside = [&]() {
+    obca::KParams kb = kr;
+    kb.poll = cnt + 3; kb.heartbeat = cnt; kb.wd_block0 = c->blocks;
+    void* args_b[3] = {&kb, &nwarps, &has_uref};
+    lerr = cudaLaunchKernel(c->fn_rec, dim3(1), block, args_b, smem, c->aux[slot]);
+    cudaEventRecord(c->ev_join[slot], c->aux[slot]);
+    c->launches += 1;
+  };
   if (beside) {
     if (!c->aux[slot]) {
       if (cudaStreamCreateWithFlags(&c->aux[slot], cudaStreamNonBlocking) != cudaSuccess) return OBCA_E_CUDA;
       cudaEventCreateWithFlags(&c->ev_fork[slot], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&c->ev_join[slot], cudaEventDisableTiming);
     }
-    obca::KParams kb = kr;
-    kb.poll = cnt + 3; kb.heartbeat = cnt; kb.wd_block0 = c->blocks;
-    void* args_b[3] = {&kb, &nwarps, &has_uref};
     cudaEventRecord(c->ev_fork[slot], st);
     cudaStreamWaitEvent(c->aux[slot], c->ev_fork[slot], 0);
-    lerr = cudaLaunchKernel(c->fn_rec, dim3(1), block, args_b, smem, c->aux[slot]);
-    cudaEventRecord(c->ev_join[slot], c->aux[slot]);
-    c->launches += 1;
+    if (reserve_sm) launch_beside();
   }
-  const int width = beside ? c->blocks - 1 : c->blocks;
+  const int width = (beside && reserve_sm) ? c->blocks - 1 : c->blocks;
   const int need_blocks = (batch + c->groups - 1) / c->groups;
   const int grid = width < need_blocks ? width : need_blocks;
   cudaEventRecord(c->ev0[slot], st);
   void* args[3] = {&kp, &nwarps, &has_uref};
   if (lerr == cudaSuccess) lerr = cudaLaunchKernel(c->fn, dim3(grid), block, args, smem, st);
+  if (lerr == cudaSuccess && beside && !reserve_sm) launch_beside();
   if (lerr == cudaSuccess && recover) {
     // first pass finished: tell the block beside it to stop claiming (it finishes the instances it holds), and let the
     // whole device take what is left of the list - the two share the work counter; the stream joins the side block last
