@@ -47,6 +47,8 @@ struct obca_ctx {
   size_t smem_bytes;           // per instance
   kernel_fn fn, fn_rec;   // first-pass kernel, recovery kernel
   int32_t* fail_list;     // per launch slot: instances whose first pass failed (max_batch entries each)
+  int32_t* order;         // per launch slot: longest-first work order of the first pass (max_batch entries each)
+  float* score;           // ... and the difficulty estimates it is sorted by
   int cfg_emax, cfg_uref; // configuration the launch geometry was computed for
   unsigned int* counter;
   double* wd_buf;         // watchdog checkpoints, one slot per resident block
@@ -151,6 +153,95 @@ __global__ void __launch_bounds__(256) obca_dfma_probe(double* out, int iters, d
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Longest-first work order.  A launch ends with its last instance: with the queue in the caller's order the makespan is
+// ~6 % above the ideal (the longest of the last few hundred instances decides), and an instance whose first pass fails
+// near the end of the queue starts its recovery when everything else has finished.  The instances are therefore handed
+// out in descending order of a difficulty estimate computed from the inputs alone - how much of the reference window
+// is in collision (separating-axis clearance of the ego rectangle at every reference pose against every obstacle), how
+// sharply the window turns, how far the start heading is from the first reference heading.  The weights are a
+// least-squares fit of the iteration count on the headline workload (correlation 0.6); the order changes nothing but
+// the time (every instance is solved independently - tests compare ordered and unordered launches bit for bit).
+// Measured: cfg 3, eight batches, profiles/r2_order_ab.log.  OBCA_B200_FIFO=1 keeps the caller's order.
+__global__ void obca_order_score(const obca::KParams kp, float* score) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= kp.batch) return;
+  const obca_params& P = kp.P;
+  const int N = P.N, no = P.n_obs, R = P.rows;
+  const double* x0 = kp.x0 + (size_t)3 * b;
+  const double* xr = kp.xref + (size_t)b * (N + 1) * 3;
+  const size_t ob = kp.shared_obs ? 0 : (size_t)b * R;
+  const double* A = kp.A ? kp.A + 2 * ob : nullptr;
+  const double* b0 = kp.b0 ? kp.b0 + ob : nullptr;
+  const double* db = (kp.db && kp.stacked) ? kp.db + ob : nullptr;
+  const double e0 = P.ego[0], e1 = P.ego[1], e2 = P.ego[2], e3 = P.ego[3];
+  const double ax[4] = {e0, e0, -e2, -e2}, ay[4] = {e1, -e3, -e3, e1};
+  double smin = 10.0, s_first = 10.0, dsum = 0.0, dmax = 0.0;
+  int c0 = 0, c05 = 0, c15 = 0;
+  for (int k = 0; k <= N; ++k) {
+    const double px = xr[3 * k], py = xr[3 * k + 1], th = xr[3 * k + 2];
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    double cx[4], cy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cx[j] = px + cs * ax[j] - sn * ay[j]; cy[j] = py + sn * ax[j] + cs * ay[j]; }
+    double Sk = 10.0;
+    for (int i = 0; i < no; ++i) {
+      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+      double sep = -1e30;
+      for (int r = r0; r < r0 + E; ++r) {              // face normals of the obstacle
+        const double a0 = A[2 * r], a1 = A[2 * r + 1], bk = b0[r] + (db ? k * db[r] : 0.0);
+        double m = a0 * cx[0] + a1 * cy[0];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) m = fmin(m, a0 * cx[j] + a1 * cy[j]);
+        sep = fmax(sep, (m - bk) * rsqrt(a0 * a0 + a1 * a1));
+      }
+      if (E >= 3) {                                    // axes of the ego rectangle against the obstacle's vertices
+        double ulo = 1e30, uhi = -1e30, vlo = 1e30, vhi = -1e30;
+        for (int r = r0; r < r0 + E; ++r) {
+          const int q = (r + 1 < r0 + E) ? r + 1 : r0;
+          const double a0 = A[2 * r], a1 = A[2 * r + 1], c0_ = A[2 * q], c1_ = A[2 * q + 1];
+          const double br = b0[r] + (db ? k * db[r] : 0.0), bq = b0[q] + (db ? k * db[q] : 0.0);
+          const double det = a0 * c1_ - a1 * c0_;
+          if (fabs(det) < 1e-12) continue;
+          const double vx = (br * c1_ - a1 * bq) / det - px, vy = (a0 * bq - br * c0_) / det - py;
+          const double u = vx * cs + vy * sn, v = -vx * sn + vy * cs;
+          ulo = fmin(ulo, u); uhi = fmax(uhi, u); vlo = fmin(vlo, v); vhi = fmax(vhi, v);
+        }
+        if (uhi >= ulo) sep = fmax(sep, fmax(fmax(ulo - e0, -e2 - uhi), fmax(vlo - e1, -e3 - vhi)));
+      }
+      Sk = fmin(Sk, sep);
+    }
+    smin = fmin(smin, Sk);
+    if (k == 0) s_first = Sk;
+    c0 += Sk < 0.0; c05 += Sk < 0.5; c15 += Sk < 1.5;
+    if (k < N) { const double d = fabs(xr[3 * (k + 1) + 2] - th); dsum += d; dmax = fmax(dmax, d); }
+  }
+  const double hd = fabs(x0[2] - xr[2]);
+  score[b] = (float)(13.41 + 0.37 * smin - 0.17 * c05 + 2.29 * c0 + 0.17 * c15 - 0.38 * dsum + 1.12 * hd + 5.34 * dmax +
+                     0.03 * x0[0] + 0.35 * fmin(s_first, 3.0));
+}
+// rank by counting (stable: ties in index order): order[rank] = instance.  n <= OBCA_ORDER_MAX.
+#define OBCA_ORDER_MAX 16384
+__global__ void __launch_bounds__(256) obca_order_rank(const float* score, int n, int32_t* order) {
+  __shared__ float tile[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float si = (i < n) ? score[i] : 0.0f;
+  int rank = 0;
+  for (int j0 = 0; j0 < n; j0 += 256) {
+    const int j = j0 + threadIdx.x;
+    tile[threadIdx.x] = (j < n) ? score[j] : -3.0e38f;
+    __syncthreads();
+    const int m = (n - j0 < 256) ? n - j0 : 256;
+    for (int q = 0; q < m; ++q) {
+      const float sj = tile[q];
+      rank += (sj > si) || (sj == si && j0 + q < i);
+    }
+    __syncthreads();
+  }
+  if (i < n) order[rank] = i;
+}
+
 extern "C" {
 
 int obca_b200_abi_version(void) { return OBCA_B200_ABI_VERSION; }
@@ -213,8 +304,10 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
   // bulk-copy prefetches that timed out (diagnostics, obca_b200_bulk_timeouts)
   if (cudaMalloc(&c->counter, (4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess ||
       cudaMemset(c->counter, 0, (4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
-  if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
-    cudaGetLastError(); cudaFree(c->counter); free(c); return OBCA_E_NOMEM;
+  if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&c->order, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&c->score, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(c->counter); if (c->fail_list) cudaFree(c->fail_list); if (c->order) cudaFree(c->order); free(c); return OBCA_E_NOMEM;
   }
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventCreate(&c->ev0[j]); cudaEventCreate(&c->ev1[j]); }
   cudaEventCreateWithFlags(&c->ev_shared, cudaEventDisableTiming);
@@ -228,6 +321,8 @@ int obca_b200_destroy(obca_ctx* c) {
   cudaSetDevice(c->device);
   cudaFree(c->counter);
   cudaFree(c->fail_list);
+  cudaFree(c->order);
+  cudaFree(c->score);
   if (c->stage) cudaFree(c->stage);
   if (c->wd_buf) cudaFree(c->wd_buf);
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventDestroy(c->ev0[j]); cudaEventDestroy(c->ev1[j]); }
@@ -260,7 +355,7 @@ int obca_b200_prof_read(unsigned long long* out, int reset) {
 // device bytes held by the context: the solver keeps its whole working set on-chip, so this is only the work-queue
 // counter, the watchdog checkpoint slots (one per resident block) and the staging buffer of the host entry point
 int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
-  return c ? (int64_t)((4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * sizeof(int32_t) +
+  return c ? (int64_t)((4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * (2 * sizeof(int32_t) + sizeof(float)) +
                        c->stage_bytes + c->wd_bytes) : 0;
 }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
@@ -340,15 +435,15 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   const dim3 block(c->groups * c->threads);
   const size_t smem = c->groups * c->smem_bytes;
   cudaError_t lerr = cudaSuccess;
-  // The recovery block that runs BESIDE the first pass: it polls the list of failed instances while it is being written
-  // (restoration phase, fresh starts, other start points: 100-300 iterations per instance - as a tail after the launch a
-  // single failure would hold the batch for 5-15 ms).  It is launched AFTER the first pass, which takes every SM: the block
-  // becomes resident when the first first-pass block runs out of work, i.e. in the tail of the launch, where SMs are free
-  // anyway (reserving an SM for it from the start cost 1/148 of the first pass's throughput and bought nothing: what it
-  // can recover early is 1/148 of the recovery work).  OBCA_B200_RESERVE_SM=1 restores the reserved SM (A/B).
+  // The recovery block that runs BESIDE the first pass, on an SM that launch leaves free: it polls the list of failed
+  // instances while it is being written (restoration phase, fresh starts, other start points: 100-300 iterations per
+  // instance - as a tail after the launch a single failure holds the batch for 2-15 ms).  Launching it behind a first
+  // pass that takes all 148 SMs (it then becomes resident in the tail of the launch) was measured over the batches of
+  // eight ranks: 0.5 % faster where no first pass fails, 8-10 % slower where one or two do (mean 21.1 against 20.3 ms,
+  // profiles/r2_seeds_ab.log) - the reserved SM is the default, OBCA_B200_RESERVE_SM=0 switches to the other.
   obca::KParams kr = kp;
   const bool beside = recover && c->blocks > 1;
-  static const bool reserve_sm = getenv("OBCA_B200_RESERVE_SM") && atoi(getenv("OBCA_B200_RESERVE_SM")) != 0;
+  static const bool reserve_sm = !(getenv("OBCA_B200_RESERVE_SM") && atoi(getenv("OBCA_B200_RESERVE_SM")) == 0);
   if (recover) {
     kr.counter = cnt + 1; kr.index = fail_list; kr.count_dev = (const int32_t*)(cnt + 2);
     kr.fail_list = nullptr; kr.fail_count = nullptr;
@@ -376,6 +471,15 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   const int need_blocks = (batch + c->groups - 1) / c->groups;
   const int grid = width < need_blocks ? width : need_blocks;
   cudaEventRecord(c->ev0[slot], st);
+  static const bool fifo = getenv("OBCA_B200_FIFO") && atoi(getenv("OBCA_B200_FIFO")) != 0;
+  if (!fifo && !index_dev && !count_dev && P.n_obs > 0 && batch >= 4 * c->grid && batch <= OBCA_ORDER_MAX) {
+    float* const score = c->score + (size_t)slot * c->max_batch;
+    int32_t* const order = c->order + (size_t)slot * c->max_batch;
+    obca_order_score<<<(batch + 127) / 128, 128, 0, st>>>(kp, score);
+    obca_order_rank<<<(batch + 255) / 256, 256, 0, st>>>(score, batch, order);
+    kp.index = order;
+    c->launches += 2;
+  }
   void* args[3] = {&kp, &nwarps, &has_uref};
   if (lerr == cudaSuccess) lerr = cudaLaunchKernel(c->fn, dim3(grid), block, args, smem, st);
   if (lerr == cudaSuccess && beside && !reserve_sm) launch_beside();
