@@ -45,6 +45,33 @@ def test_indexed_solve_matches_plain_solve():
     s.close()
 
 
+def test_longest_first_order_changes_nothing_but_the_time():
+    """A plain solve of 4,096 instances is handed out longest-first (difficulty estimate computed on the device from the
+    inputs, csrc/obca_b200.cu); the same solve over an explicit work list keeps the caller's order.  Every instance is
+    solved independently, so the two must agree bit for bit - and so must a reversed list."""
+    import torch
+    B = 4096
+    b = sc.make_batch(3, B)
+    prm, a = sc.batch_arrays(b)
+    s = obca_mod.BatchSolver(prm, a["edge_ptr"], B)
+    t = lambda v: torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous()
+    args = (t(a["x0"]), t(a["u0"]), t(a["xref"]), t(a["A"]), t(a["b0"]), None)
+    n0 = s.launches
+    o = {k: v.clone() for k, v in s.solve(*args, T_max=t(a["T_max"])).items()}
+    torch.cuda.synchronize()
+    assert s.launches - n0 == 6            # estimate, rank, scatter, first pass, recovery block beside it, recovery over the device
+    cnt = torch.tensor([B], dtype=torch.int32, device="cuda")
+    for order in (np.arange(B), np.arange(B)[::-1]):
+        idx = torch.as_tensor(np.ascontiguousarray(order, dtype=np.int32), device="cuda")
+        n0 = s.launches
+        o2 = s.solve(*args, T_max=t(a["T_max"]), index=idx, count=cnt)
+        torch.cuda.synchronize()
+        assert s.launches - n0 == 3
+        for k in ("x", "u", "T", "obj", "lam", "mu", "status", "iters"):
+            assert torch.equal(o[k], o2[k]), k
+    s.close()
+
+
 def test_device_rows_match_host_hrep():
     """obca_b200_build_rows == obstacle_H_Represent on the first time block (bit for bit, axis-aligned and slanted
     edges, two-vertex walls) and b0 + k*db == the reference's time-stacked rows"""

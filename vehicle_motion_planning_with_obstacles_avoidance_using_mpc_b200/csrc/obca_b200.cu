@@ -49,6 +49,7 @@ struct obca_ctx {
   int32_t* fail_list;     // per launch slot: instances whose first pass failed (max_batch entries each)
   int32_t* order;         // per launch slot: longest-first work order of the first pass (max_batch entries each)
   float* score;           // ... and the difficulty estimates it is sorted by
+  int32_t* rank;          // ... and their ranks
   int cfg_emax, cfg_uref; // configuration the launch geometry was computed for
   unsigned int* counter;
   double* wd_buf;         // watchdog checkpoints, one slot per resident block
@@ -163,83 +164,101 @@ __global__ void __launch_bounds__(256) obca_dfma_probe(double* out, int iters, d
 // least-squares fit of the iteration count on the headline workload (correlation 0.6); the order changes nothing but
 // the time (every instance is solved independently - tests compare ordered and unordered launches bit for bit).
 // Measured: cfg 3, eight batches, profiles/r2_order_ab.log.  OBCA_B200_FIFO=1 keeps the caller's order.
-__global__ void obca_order_score(const obca::KParams kp, float* score) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per instance, lane = stage of the reference window (N + 1 <= 32).
+__global__ void __launch_bounds__(128) obca_order_score(const obca::KParams kp, float* score) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, k = threadIdx.x & 31;
   if (b >= kp.batch) return;
   const obca_params& P = kp.P;
   const int N = P.N, no = P.n_obs, R = P.rows;
   const double* x0 = kp.x0 + (size_t)3 * b;
   const double* xr = kp.xref + (size_t)b * (N + 1) * 3;
   const size_t ob = kp.shared_obs ? 0 : (size_t)b * R;
-  const double* A = kp.A ? kp.A + 2 * ob : nullptr;
-  const double* b0 = kp.b0 ? kp.b0 + ob : nullptr;
+  const double* A = kp.A + 2 * ob;
+  const double* b0 = kp.b0 + ob;
   const double* db = (kp.db && kp.stacked) ? kp.db + ob : nullptr;
   const double e0 = P.ego[0], e1 = P.ego[1], e2 = P.ego[2], e3 = P.ego[3];
   const double ax[4] = {e0, e0, -e2, -e2}, ay[4] = {e1, -e3, -e3, e1};
-  double smin = 10.0, s_first = 10.0, dsum = 0.0, dmax = 0.0;
-  int c0 = 0, c05 = 0, c15 = 0;
-  for (int k = 0; k <= N; ++k) {
-    const double px = xr[3 * k], py = xr[3 * k + 1], th = xr[3 * k + 2];
-    double sn, cs;
-    sincos(th, &sn, &cs);
-    double cx[4], cy[4];
+  const bool on = k <= N;
+  const int kk = on ? k : N;
+  const double px = xr[3 * kk], py = xr[3 * kk + 1], th = xr[3 * kk + 2];
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  double cx[4], cy[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { cx[j] = px + cs * ax[j] - sn * ay[j]; cy[j] = py + sn * ax[j] + cs * ay[j]; }
-    double Sk = 10.0;
-    for (int i = 0; i < no; ++i) {
-      const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
-      double sep = -1e30;
-      for (int r = r0; r < r0 + E; ++r) {              // face normals of the obstacle
-        const double a0 = A[2 * r], a1 = A[2 * r + 1], bk = b0[r] + (db ? k * db[r] : 0.0);
-        double m = a0 * cx[0] + a1 * cy[0];
+  for (int j = 0; j < 4; ++j) { cx[j] = px + cs * ax[j] - sn * ay[j]; cy[j] = py + sn * ax[j] + cs * ay[j]; }
+  double Sk = 10.0;
+  for (int i = 0; i < no; ++i) {
+    const int r0 = kp.eptr[i], E = kp.eptr[i + 1] - r0;
+    double sep = -1e30;
+    for (int r = r0; r < r0 + E; ++r) {              // face normals of the obstacle
+      const double a0 = A[2 * r], a1 = A[2 * r + 1], bk = b0[r] + (db ? kk * db[r] : 0.0);
+      double m = a0 * cx[0] + a1 * cy[0];
 #pragma unroll
-        for (int j = 1; j < 4; ++j) m = fmin(m, a0 * cx[j] + a1 * cy[j]);
-        sep = fmax(sep, (m - bk) * rsqrt(a0 * a0 + a1 * a1));
-      }
-      if (E >= 3) {                                    // axes of the ego rectangle against the obstacle's vertices
-        double ulo = 1e30, uhi = -1e30, vlo = 1e30, vhi = -1e30;
-        for (int r = r0; r < r0 + E; ++r) {
-          const int q = (r + 1 < r0 + E) ? r + 1 : r0;
-          const double a0 = A[2 * r], a1 = A[2 * r + 1], c0_ = A[2 * q], c1_ = A[2 * q + 1];
-          const double br = b0[r] + (db ? k * db[r] : 0.0), bq = b0[q] + (db ? k * db[q] : 0.0);
-          const double det = a0 * c1_ - a1 * c0_;
-          if (fabs(det) < 1e-12) continue;
-          const double vx = (br * c1_ - a1 * bq) / det - px, vy = (a0 * bq - br * c0_) / det - py;
-          const double u = vx * cs + vy * sn, v = -vx * sn + vy * cs;
-          ulo = fmin(ulo, u); uhi = fmax(uhi, u); vlo = fmin(vlo, v); vhi = fmax(vhi, v);
-        }
-        if (uhi >= ulo) sep = fmax(sep, fmax(fmax(ulo - e0, -e2 - uhi), fmax(vlo - e1, -e3 - vhi)));
-      }
-      Sk = fmin(Sk, sep);
+      for (int j = 1; j < 4; ++j) m = fmin(m, a0 * cx[j] + a1 * cy[j]);
+      sep = fmax(sep, (m - bk) * rsqrt(a0 * a0 + a1 * a1));
     }
-    smin = fmin(smin, Sk);
-    if (k == 0) s_first = Sk;
-    c0 += Sk < 0.0; c05 += Sk < 0.5; c15 += Sk < 1.5;
-    if (k < N) { const double d = fabs(xr[3 * (k + 1) + 2] - th); dsum += d; dmax = fmax(dmax, d); }
+    if (E >= 3) {                                    // axes of the ego rectangle against the obstacle's vertices
+      double ulo = 1e30, uhi = -1e30, vlo = 1e30, vhi = -1e30;
+      for (int r = r0; r < r0 + E; ++r) {
+        const int q = (r + 1 < r0 + E) ? r + 1 : r0;
+        const double a0 = A[2 * r], a1 = A[2 * r + 1], c0_ = A[2 * q], c1_ = A[2 * q + 1];
+        const double br = b0[r] + (db ? kk * db[r] : 0.0), bq = b0[q] + (db ? kk * db[q] : 0.0);
+        const double det = a0 * c1_ - a1 * c0_;
+        if (fabs(det) < 1e-12) continue;
+        const double id = 1.0 / det;
+        const double vx = (br * c1_ - a1 * bq) * id - px, vy = (a0 * bq - br * c0_) * id - py;
+        const double u = vx * cs + vy * sn, v = -vx * sn + vy * cs;
+        ulo = fmin(ulo, u); uhi = fmax(uhi, u); vlo = fmin(vlo, v); vhi = fmax(vhi, v);
+      }
+      if (uhi >= ulo) sep = fmax(sep, fmax(fmax(ulo - e0, -e2 - uhi), fmax(vlo - e1, -e3 - vhi)));
+    }
+    Sk = fmin(Sk, sep);
   }
-  const double hd = fabs(x0[2] - xr[2]);
-  score[b] = (float)(13.41 + 0.37 * smin - 0.17 * c05 + 2.29 * c0 + 0.17 * c15 - 0.38 * dsum + 1.12 * hd + 5.34 * dmax +
-                     0.03 * x0[0] + 0.35 * fmin(s_first, 3.0));
+  const unsigned full = 0xffffffffu;
+  const int c0 = __popc(__ballot_sync(full, on && Sk < 0.0)), c05 = __popc(__ballot_sync(full, on && Sk < 0.5)),
+            c15 = __popc(__ballot_sync(full, on && Sk < 1.5));
+  const double th_next = __shfl_down_sync(full, th, 1);
+  double d = (k < N) ? fabs(th_next - th) : 0.0, dsum = d, dmax = d, smin = on ? Sk : 10.0;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    dsum += __shfl_xor_sync(full, dsum, o);
+    dmax = fmax(dmax, __shfl_xor_sync(full, dmax, o));
+    smin = fmin(smin, __shfl_xor_sync(full, smin, o));
+  }
+  if (k == 0) {
+    const double hd = fabs(x0[2] - th);
+    score[b] = (float)(13.41 + 0.37 * smin - 0.17 * c05 + 2.29 * c0 + 0.17 * c15 - 0.38 * dsum + 1.12 * hd + 5.34 * dmax +
+                       0.03 * x0[0] + 0.35 * fmin(Sk, 3.0));
+  }
 }
-// rank by counting (stable: ties in index order): order[rank] = instance.  n <= OBCA_ORDER_MAX.
+// rank by counting (stable: ties in index order), the comparisons of one instance spread over gridDim.y blocks;
+// then order[rank] = instance.  n <= OBCA_ORDER_MAX.
 #define OBCA_ORDER_MAX 16384
-__global__ void __launch_bounds__(256) obca_order_rank(const float* score, int n, int32_t* order) {
+#define OBCA_ORDER_SPLIT 8
+__global__ void __launch_bounds__(256) obca_order_rank(const float* score, int n, int32_t* rank) {
   __shared__ float tile[256];
   const int i = blockIdx.x * 256 + threadIdx.x;
   const float si = (i < n) ? score[i] : 0.0f;
-  int rank = 0;
-  for (int j0 = 0; j0 < n; j0 += 256) {
+  const int per = ((n + OBCA_ORDER_SPLIT - 1) / OBCA_ORDER_SPLIT + 255) & ~255;
+  const int jb = blockIdx.y * per, je = (jb + per < n) ? jb + per : n;
+  int r = 0;
+  for (int j0 = jb; j0 < je; j0 += 256) {
     const int j = j0 + threadIdx.x;
-    tile[threadIdx.x] = (j < n) ? score[j] : -3.0e38f;
+    tile[threadIdx.x] = (j < je) ? score[j] : -3.0e38f;
     __syncthreads();
-    const int m = (n - j0 < 256) ? n - j0 : 256;
+    const int m = (je - j0 < 256) ? je - j0 : 256;
+#pragma unroll 8
     for (int q = 0; q < m; ++q) {
       const float sj = tile[q];
-      rank += (sj > si) || (sj == si && j0 + q < i);
+      r += (sj > si) || (sj == si && j0 + q < i);
     }
     __syncthreads();
   }
-  if (i < n) order[rank] = i;
+  if (i < n && r) atomicAdd(&rank[i], r);
+}
+__global__ void obca_order_scatter(const int32_t* rank, int n, int32_t* order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[rank[i]] = i;
 }
 
 extern "C" {
@@ -306,7 +325,8 @@ int obca_b200_create(obca_ctx** out, int device, int max_batch, const obca_param
       cudaMemset(c->counter, 0, (4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); free(c); return OBCA_E_NOMEM; }
   if (cudaMalloc(&c->fail_list, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc(&c->order, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess ||
-      cudaMalloc(&c->score, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(float)) != cudaSuccess) {
+      cudaMalloc(&c->score, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&c->rank, (size_t)OBCA_HOST_CHUNKS * max_batch * sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError(); cudaFree(c->counter); if (c->fail_list) cudaFree(c->fail_list); if (c->order) cudaFree(c->order); free(c); return OBCA_E_NOMEM;
   }
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventCreate(&c->ev0[j]); cudaEventCreate(&c->ev1[j]); }
@@ -323,6 +343,7 @@ int obca_b200_destroy(obca_ctx* c) {
   cudaFree(c->fail_list);
   cudaFree(c->order);
   cudaFree(c->score);
+  cudaFree(c->rank);
   if (c->stage) cudaFree(c->stage);
   if (c->wd_buf) cudaFree(c->wd_buf);
   for (int j = 0; j < OBCA_HOST_CHUNKS; ++j) { cudaEventDestroy(c->ev0[j]); cudaEventDestroy(c->ev1[j]); }
@@ -355,7 +376,7 @@ int obca_b200_prof_read(unsigned long long* out, int reset) {
 // device bytes held by the context: the solver keeps its whole working set on-chip, so this is only the work-queue
 // counter, the watchdog checkpoint slots (one per resident block) and the staging buffer of the host entry point
 int64_t obca_b200_scratch_bytes(const obca_ctx* c) {
-  return c ? (int64_t)((4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * (2 * sizeof(int32_t) + sizeof(float)) +
+  return c ? (int64_t)((4 * OBCA_HOST_CHUNKS + 1) * sizeof(unsigned int) + (size_t)OBCA_HOST_CHUNKS * c->max_batch * (3 * sizeof(int32_t) + sizeof(float)) +
                        c->stage_bytes + c->wd_bytes) : 0;
 }
 int64_t obca_b200_launch_count(const obca_ctx* c) { return c ? c->launches : 0; }
@@ -475,10 +496,13 @@ static int solve_slot(obca_ctx* c, int slot, int batch, const int32_t* count_dev
   if (!fifo && !index_dev && !count_dev && P.n_obs > 0 && batch >= 4 * c->grid && batch <= OBCA_ORDER_MAX) {
     float* const score = c->score + (size_t)slot * c->max_batch;
     int32_t* const order = c->order + (size_t)slot * c->max_batch;
-    obca_order_score<<<(batch + 127) / 128, 128, 0, st>>>(kp, score);
-    obca_order_rank<<<(batch + 255) / 256, 256, 0, st>>>(score, batch, order);
+    int32_t* const rank = c->rank + (size_t)slot * c->max_batch;
+    cudaMemsetAsync(rank, 0, (size_t)batch * sizeof(int32_t), st);
+    obca_order_score<<<(batch + 3) / 4, 128, 0, st>>>(kp, score);
+    obca_order_rank<<<dim3((batch + 255) / 256, OBCA_ORDER_SPLIT), 256, 0, st>>>(score, batch, rank);
+    obca_order_scatter<<<(batch + 255) / 256, 256, 0, st>>>(rank, batch, order);
     kp.index = order;
-    c->launches += 2;
+    c->launches += 3;
   }
   void* args[3] = {&kp, &nwarps, &has_uref};
   if (lerr == cudaSuccess) lerr = cudaLaunchKernel(c->fn, dim3(grid), block, args, smem, st);
