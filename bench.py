@@ -144,6 +144,11 @@ def main():
                          "mu_init 0.1 / bound_push 1e-2")
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances of the CPU sample (0 = the whole batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="serial", choices=["serial", "overlapped"],
+                    help="N > 1: the peer-to-peer copies of a step's results land before the next launch starts (serial: a "
+                         "4-byte all-reduce after the copies orders the ranks) or under it (overlapped).  Measured: the "
+                         "copies arriving under rank 0's launch slow it by 0.7 ms at N = 4 and 1.3 ms at N = 8 (they sweep "
+                         "its L2, where the solver's per-thread state lives), more than the 0.1-0.4 ms they take")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -227,12 +232,14 @@ def main():
                 print("bench: peer-to-peer gather unavailable (%s); NCCL gather on the launch stream" % e, file=sys.stderr)
                 full = [torch.empty((world, packed[0].words), dtype=torch.float64, device=dev) for _ in packed]
         config["parallelism"] = "batch-sharded x%d, %s" % (world, "one peer-to-peer copy of the packed results per rank into rank 0's "
-                                                          "buffer (NVLink, copy engines), overlapped with the next launch" if peer else
+                                                          "buffer (NVLink, copy engines), %s" % ("landed before the next launch (4-byte all-reduce)" if args.gather == "serial" else "overlapped with the next launch") if peer else
                                                           "one NCCL gather of the packed results")
 
     def solve_into(pk, src=d):
         solver.solve(src["x0"], src["u0"], src["xref"], src["A"], src["b0"], src["db"], T_max=src["T_max"], term=src["term"],
                      out=pk.views)
+
+    sync_word = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def run_steps(K, src=d, before=None, after=None):
         """K steps back to back on the launch stream; the gather of step k is issued on the side stream and overlaps
@@ -252,6 +259,10 @@ def main():
             evs.append((e0, e1))
             if peer is not None:
                 done[j] = peer.push(packed[j], j, e1)
+                if args.gather == "serial":
+                    stream.wait_event(done[j])                    # this rank's copy, then everybody's, before the next step
+                    with torch.cuda.stream(stream):
+                        dist.all_reduce(sync_word)
             elif world > 1:
                 sharding.gather_packed(packed[j], dst=0, out=full[j])
             if after:
@@ -291,6 +302,11 @@ def main():
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms, kern_total_ms = float(tt[0]), float(tt[1])
+    per_rank_kernel_ms = [sum(kernel_ms) / len(kernel_ms)]
+    if world > 1:                                                 # which rank sets the step: the mean solver time of each
+        allk = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allk, torch.tensor([per_rank_kernel_ms[0]], dtype=torch.float64, device=dev))
+        per_rank_kernel_ms = [float(v[0]) for v in allk]
     value = world * B * args.steps / (total_ms * 1e-3)
     status = packed[(args.steps - 1) % len(packed)].views["status"].cpu().numpy()
     iters = packed[(args.steps - 1) % len(packed)].views["iters"].cpu().numpy()
@@ -369,7 +385,8 @@ def main():
     traffic = prof.get("dram_bytes_per_launch") if CFG == 3 and B == 8192 else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-                "kernel": "obca_solve_kernel", "kernel_ms": kern_ms, "bytes_per_solve": b_in + b_out,
+                "kernel": "obca_solve_kernel", "kernel_ms": kern_ms, "kernel_ms_per_rank": [round(v, 3) for v in per_rank_kernel_ms],
+                "bytes_per_solve": b_in + b_out,
                 "note": "fp64 interior-point iterations run on-chip/L2; compulsory HBM traffic is ~7 KB per solve, so the "
                         "kernel is fp64-latency bound, not HBM bound (see roofline_fp64, DESIGN.md, profiles/)"}
     # ---- second roofline, the one that binds: fp64 instructions of the launch (counted by ncu per interior-point
