@@ -70,7 +70,35 @@ class ClockSampler(threading.Thread):
         self.t0 = self.t1 = None
         self.proc = None
 
+    def run_nvml(self):
+        """the same readings straight from NVML in this process (OBCA_BENCH_SAMPLER=nvml): no second process polling the
+        driver while the timed region runs"""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, 3), (nv.nvmlClocksEventReasonHwThermalSlowdown, 4),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, 5), (nv.nvmlClocksEventReasonSwPowerCap, 6)]
+        while not self.quit:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), "%.2f" % (nv.nvmlDeviceGetPowerUsage(h) / 1000.0),
+                   "", "", "", ""]
+            for bit, col in bits:
+                row[col] = "Active" if (r & bit) else "Not Active"
+            self.rows.append((time.time(), row))
+            time.sleep(0.1)
+
+    quit = False
+
     def run(self):
+        mode = os.environ.get("OBCA_BENCH_SAMPLER", "smi")
+        if mode == "off":
+            return
+        if mode == "nvml":
+            try:
+                return self.run_nvml()
+            except Exception:
+                pass                       # no NVML binding on this box: the nvidia-smi line below
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -87,6 +115,7 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         time.sleep(0.15)                       # let the last in-window sample arrive
+        self.quit = True
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=6)

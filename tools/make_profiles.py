@@ -49,10 +49,28 @@ def main():
     rd = float(d['dram__bytes_read.sum'][1]) * sc[d['dram__bytes_read.sum'][0]]
     wr = float(d['dram__bytes_write.sum'][1]) * sc[d['dram__bytes_write.sum'][0]]
     kname = [x for x in h if False] or None
-    json.dump({"kernel": "obca_solve_kernel<4,128,3,20,4,16>", "workload": "cfg3 B=8192", "dram_bytes_read": rd, "dram_bytes_write": wr,
+    rt_path = os.path.join(PROF, "roofline_traffic.json")
+    rt = json.load(open(rt_path)) if os.path.exists(rt_path) else {}
+    rt.update({"kernel": "obca_solve_kernel<4,128,3,20,4,16>", "workload": "cfg3 B=8192", "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": 7160 * 8192,
-               "source": "ncu --set full --clock-control none, profiles/%s_cta_per_instance.md" % tag},
-              open(os.path.join(PROF, "roofline_traffic.json"), "w"), indent=1)
+               "source": "ncu --set full --clock-control none, profiles/%s_ncu_metrics.md" % tag})
+    # fp64 instruction counts of the first-pass kernel (tools/gpu_r2h.sh: gpurun_out/fp64_counts_cfg3.csv) -> FLOP per iteration
+    fc = os.path.join(OUT, "fp64_counts_cfg3.csv")
+    if os.path.exists(fc):
+        cnt = {}
+        for row in csv.reader(open(fc)):
+            if len(row) > 14 and "20, 4, 16" in row[4] and "_op_d" in row[12]:
+                cnt[row[12].split("_op_")[1].split("_")[0]] = int(row[14])
+        it = b_iters = None
+        try:
+            b_iters = json.loads(open(os.path.join(OUT, "bench.json")).read())["roofline_fp64"]["iterations_per_launch"]
+        except Exception:
+            pass
+        if len(cnt) == 3 and b_iters:
+            rt["fp64_thread_instructions_per_launch"] = dict(cnt, source="ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on.sum of the first-pass kernel (profiles/%s_fp64_counts_cfg3.csv)" % tag)
+            rt["iterations_per_launch"] = b_iters
+            rt["fp64_flop_per_iteration_cfg3"] = (2 * cnt["dfma"] + cnt["dmul"] + cnt["dadd"]) / b_iters
+    json.dump(rt, open(rt_path, "w"), indent=1)
     tab = ["| metric | value | unit |", "|---|---|---|"] + ["| `%s` | %s | %s |" % (k, d[k][1], d[k][0]) for k in KEYS if k in d]
     src = os.path.join("/tmp", "src_%s.csv" % tag)
     open(src, "w").write(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout)
