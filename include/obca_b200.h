@@ -11,7 +11,8 @@
  *                    mode 3  FREE_STACKED  obca.obca2 fixtime=0  src/obca.py:338-629 (closed_loop.py:170,263)
  *                    mode 4  FIXED_OBCA2   obca.obca2 fixtime=1  (terminal set optional, obca.py:518-521)
  *
- * One call solves `batch` independent NLPs (one thread block each).  All arrays are float64, C-contiguous,
+ * One call solves `batch` independent NLPs (a group of threads each, the groups of an SM in one thread block; large
+ * batches are handed out longest-first by a difficulty estimate - the order never changes a result).  All arrays are float64, C-contiguous,
  * batch-major; the caller owns every buffer, the library owns only the context.  Functions return 0 on
  * success and a negative code on argument / CUDA errors (obca_b200_strerror); they never throw and never
  * exit.  The per-instance solver outcome is in `status` (>= 0  <=>  the reference's feas == True).
