@@ -207,7 +207,9 @@ struct SweepRegs {
 };
 enum : uint32_t { SW_PC = 1u, SW_FS = 2u, SW_FF = 4u, SW_FK = 8u, SW_DW_ALL = 16u, SW_DW_GE1 = 32u, SW_DW_EQ0 = 64u,
                   SW_B0 = 256u, SW_BD = 1u << 13, SW_PV = 1u << 14 };
-constexpr int RIC_DUMMY = 70;   // scratch word nobody reads (RIC: 0..43 F|f, 44..67 W, 80..85 pc)
+constexpr int RIC_DUMMY = 96;   // scratch words nobody reads, one per lane (RIC: 0..43 F|f, 44..67 W, 80..85 pc; the region it
+                                // aliases holds at least 12 x 64 doubles, see sm_carve) - a word shared by the idle lanes would
+                                // be a write-write hazard for racecheck
 
 OB_HD void ob_sincos(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
@@ -1473,7 +1475,7 @@ struct Solver {
   OB_HD void sweep_load(int t, SweepRegs& r) const {
     const uint32_t* tab = sm.TAB;
     const uint32_t zero = ref_st(sm.DYN, 9);            // DYN element 9 is 0 at every stage
-    const uint32_t dummy = ref_abs(sm.RIC + RIC_DUMMY);
+    const uint32_t dummy = ref_abs(sm.RIC + RIC_DUMMY + t);
     auto off = [](uint32_t ref) -> uint32_t { return (ref & 0x7fffu) * 8u; };
     uint32_t fl = 0;
     // sub-step 1
