@@ -109,6 +109,40 @@ def test_lockstep_batch_equals_single_loops():
     assert (_abi.MODE_FIXED_SET in modes) or (_abi.MODE_FIXED_NOTERM in modes) or out["failed"].any()
 
 
+def test_lockstep_batch_with_two_moving_boxes_equals_single_loops():
+    """Two moving boxes per scenario (the reference's demos 6, 7, 8, 11 carry two): the fixed-time solve is built from the
+    boxes the lidar sees at that step - both, or only the second one, in which case polygon and velocity of THAT box must
+    be the ones in the NLP.  Lock-step batch == independent closedLoop.closed_loop_mpc4 runs with the same two rows."""
+    hp = -np.pi / 2
+    dyn = np.array([[[8, 20, hp, 2, 2, 0.6, 0], [8, 23.5, hp, 2, 2, 0.6, 0]],       # both come into range
+                    [[30, 50, hp, 2, 2, 0.4, 0], [8, 18, hp, 2, 2, 0.3, 2]],        # the first never does
+                    [[8, 50, hp, 2, 2, 0.5, 0], [8, 16, hp, 2, 2, 0.3, 0]]], float)
+    steps = 7
+    drv = cl.ClosedLoopBatch(_demo9_setting(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps,
+                             solver_factory=lambda prm, ep, cap: common.OracleSolver(prm, ep, cap))
+    # the lock-step driver runs the terminal-set solve without the recovery rules (it has its own fallback); the
+    # single-scenario object has one setting for all its solves - compare like with like
+    drv._init_of = lambda mode: drv.init
+    out = drv.run()
+    counts = {key[1] for key in drv._solvers if key[0] != _abi.MODE_FREE}
+    assert 1 in counts and 2 in counts, counts                  # NLPs with one and with two moving boxes were built
+    for i in range(3):
+        s = ds.problemSetting("demo9")
+        s.add_dynamic_obstacle([[r[0], r[1], r[2], r[3], r[4], r[5], 8, 10, hp, int(r[6]), 100] for r in dyn[i]])
+        s.senseDis = 8
+        solver = common.oracle_obca()
+        solver.mu_init, solver.bound_push, solver.recover = 10.0, 0.1, _abi.RECOVER
+        c = cl.closedLoop(s, solver=solver)
+        c.N_free = c.N_fix = 5
+        c.Q_free = 0.5 * np.eye(3); c.P_free = c.Q_free
+        c.max_steps = steps
+        x_open, x_opt, u_opt, T_opt = c.closed_loop_mpc4()
+        n = len(x_opt) - 1
+        assert n == out["steps"][i], (i, n, out["steps"][i])
+        got = out["traj"][i, :n + 1]
+        assert np.allclose(got, np.asarray(x_opt, float), rtol=0, atol=1e-7), (i, np.abs(got - np.asarray(x_opt, float)).max())
+
+
 def test_sensor_keeps_polygon_and_velocity_paired():
     """two live moving obstacles (demo11), only the second within lidar range: the fixed-time NLP must be built from the
     second obstacle's polygon AND the second obstacle's velocity row"""

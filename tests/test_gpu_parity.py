@@ -362,6 +362,35 @@ def test_closed_loop_lockstep_batch_matches_oracle_driver():
     assert (og["mode"] == _abi.MODE_FIXED_SET).any() or (og["mode"] == _abi.MODE_FIXED_NOTERM).any()
 
 
+def test_closed_loop_lockstep_batch_with_two_moving_boxes():
+    """Two moving boxes per scenario (the reference's demos 6, 7, 8, 11): NLPs with 5 + 1 and 5 + 2 obstacles in one
+    lock-step run, on the GPU against the same driver on the oracle"""
+    from vehicle_motion_planning_with_obstacles_avoidance_using_mpc_b200 import closed_loop as cl, demo_setting as ds
+    B, steps = 32, 8
+    one = cl.demo9_monte_carlo(B)
+    one[:, 1] = np.linspace(14, 26, B); one[:, 6] = 0; one[:, 5] = np.linspace(0.3, 0.7, B)
+    two = one.copy(); two[:, 1] += 3.5                          # the second box follows 3.5 m behind the first
+    two[B // 2:, 0] = 30.0                                      # ... or stays out of the lidar's range for good
+    dyn = np.stack([one, two], 1)                               # (B, 2, 7)
+    mk = lambda: (lambda s: (setattr(s, "senseDis", 8), s)[1])(ds.problemSetting("demo9"))
+    g = cl.ClosedLoopBatch(mk(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps)
+    og = g.run()
+    counts = {key[1] for key in g._solvers if key[0] != _abi.MODE_FREE}
+    g.close()
+    assert counts == {1, 2}, counts
+    c = cl.ClosedLoopBatch(mk(), dyn, N=5, Q_free=0.5, sense=8.0, max_steps=steps,
+                           solver_factory=lambda prm, ep, cap: common.OracleSolver(prm, ep, cap, nthreads=8))
+    oc = c.run()
+    assert np.nanmax(np.abs(og["traj"][:, 1] - oc["traj"][:, 1])) <= 1e-4
+    same = (og["steps"] == oc["steps"]) & (og["failed"] == oc["failed"])
+    assert same.mean() >= 0.9
+    n = np.minimum(og["steps"], oc["steps"])
+    close = [np.abs(og["traj"][i, :n[i] + 1] - oc["traj"][i, :n[i] + 1]).max() <= 1e-3 for i in range(B) if same[i]]
+    assert np.mean(close) >= 0.9
+    with pytest.raises(ValueError):
+        cl.ClosedLoopDevice(mk(), dyn, N=5)                     # the device-resident loop carries one box per scenario
+
+
 @pytest.mark.parametrize("name,sides,N,moving", [("ragged_3_to_8_edges", [3, 4, 5, 6, 7, 8], 12, 0),
                                                  ("longest_horizon", [4, 3], 31, 0),
                                                  ("twelve_obstacles_48_rows", [4] * 12, 10, 0),

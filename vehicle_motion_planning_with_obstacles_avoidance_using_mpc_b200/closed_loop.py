@@ -267,14 +267,20 @@ def box_hrep_batch(cx, cy, th, length, width):
 class ClosedLoopBatch:
     """``closed_loop_mpc4`` for B Monte-Carlo scenarios in lock-step on one GPU.
 
-    All scenarios share the static map, start/goal and hence the A* path; each has its own single moving box
-    ``dyn`` rows ``[cx, cy, theta, l, w, v, start_step]`` (B,7).  ``run`` returns the closed-loop logs."""
+    All scenarios share the static map, start/goal and hence the A* path; each has its own moving boxes: ``dyn`` rows
+    ``[cx, cy, theta, l, w, v, start_step]``, (B,7) for one box per scenario or (B,D,7) for D (the reference's demos 6, 7,
+    8 and 11 carry two, demo_setting.py:221-338).  As in the single-scenario loop (``sensor``), a fixed-time solve is
+    built from the static obstacles plus the boxes the lidar sees at that step, in their order, each with its own
+    velocity; scenarios are grouped by the number of boxes seen (one solver context per count).  ``run`` returns the
+    closed-loop logs."""
 
     def __init__(self, setting, dyn, N=5, Q_free=0.5, sense=8.0, device=-1, init=_abi.INIT_WARM | _abi.RECOVER, max_steps=30,
                  solver_factory=None):
         self.s = setting
         self.dyn = np.array(dyn, float)
-        self.B = self.dyn.shape[0]
+        if self.dyn.ndim == 2:
+            self.dyn = self.dyn[:, None, :]
+        self.B, self.D = self.dyn.shape[0], self.dyn.shape[1]
         self.N = int(N)
         self.sense = float(sense)
         self.max_steps = max_steps
@@ -299,9 +305,10 @@ class ClosedLoopBatch:
         self.solves = 0
 
     def _solver(self, mode, with_dyn):
-        key = (mode, with_dyn)
+        """solver context for `mode` with `with_dyn` moving boxes in the NLP (False / True count as 0 / 1)"""
+        key = (mode, int(with_dyn))
         if key not in self._solvers:
-            edges = self.edges_s + ([4] if with_dyn else [])
+            edges = self.edges_s + [4] * int(with_dyn)
             ep = np.concatenate([[0], np.cumsum(edges)]).astype(np.int32)
             free = _abi.is_free(mode)
             prm = _abi.make_params(mode, self.N, len(edges), int(ep[-1]), 0.1, self.Q_free if free else self.Q_fix,
@@ -345,15 +352,19 @@ class ClosedLoopBatch:
             if not alive.any():
                 break
             # update_obstacle: appear at k == start step, move afterwards by the last optimal step
-            mv = alive & (k > dyn[:, 6])
-            dyn[mv, 0] += Ts_opt[mv] * dyn[mv, 5] * np.cos(dyn[mv, 2])
-            dyn[mv, 1] += Ts_opt[mv] * dyn[mv, 5] * np.sin(dyn[mv, 2])
-            live = alive & (k >= dyn[:, 6])
-            A_d, b_d, V = box_hrep_batch(dyn[:, 0], dyn[:, 1], dyn[:, 2], dyn[:, 3], dyn[:, 4])
-            # sensor: car-front midpoint to the four obstacle vertices
+            mv = alive[:, None] & (k > dyn[:, :, 6])
+            step = np.where(mv, Ts_opt[:, None] * dyn[:, :, 5], 0.0)
+            dyn[:, :, 0] += step * np.cos(dyn[:, :, 2])
+            dyn[:, :, 1] += step * np.sin(dyn[:, :, 2])
+            live = alive[:, None] & (k >= dyn[:, :, 6])
+            flat = dyn.reshape(B * self.D, 7)
+            A_d, b_d, V = box_hrep_batch(flat[:, 0], flat[:, 1], flat[:, 2], flat[:, 3], flat[:, 4])
+            A_d = A_d.reshape(B, self.D, 4, 2); b_d = b_d.reshape(B, self.D, 4); V = V.reshape(B, self.D, 5, 2)
+            # sensor: car-front midpoint to the four vertices of every live box
             fx = x0[:, 0] + self.ego[0] * np.cos(x0[:, 2]); fy = x0[:, 1] + self.ego[0] * np.sin(x0[:, 2])
-            dist = np.hypot(fx[:, None] - V[:, :4, 0], fy[:, None] - V[:, :4, 1]).min(1)
-            fix = live & (dist <= self.sense) & (k > 0)
+            dist = np.hypot(fx[:, None, None] - V[:, :, :4, 0], fy[:, None, None] - V[:, :, :4, 1]).min(2)
+            seen = live & (dist <= self.sense)
+            fix = seen.any(1) & (k > 0)
             free = alive & ~fix
             xopt = np.zeros((B, N + 1, 3)); uopt = np.zeros((B, N, 2)); feas = np.zeros(B, bool)
             newT = Ts_opt.copy()
@@ -380,23 +391,34 @@ class ClosedLoopBatch:
                     term = np.stack([x0[i, 0] + 5, np.full(len(i), 1.0), np.full(len(i), 9.0)], 1)
                 else:   # the demo9 recommendation of simulation.py:72
                     term = np.stack([np.full(len(i), 5.0), x0[i, 1] + 4, np.full(len(i), 60.0)], 1)
-                A = np.concatenate([np.tile(self.A_s[None], (len(i), 1, 1)), A_d[i]], 1)
-                b0 = np.concatenate([np.tile(self.b_s[None], (len(i), 1)), b_d[i]], 1)
-                shift = (Ts_opt[i] * dyn[i, 5])[:, None] * (A_d[i, :, 0] * np.cos(dyn[i, 2])[:, None]
-                                                            + A_d[i, :, 1] * np.sin(dyn[i, 2])[:, None])
-                db = np.concatenate([np.zeros((len(i), self.b_s.shape[0])), shift], 1)
-                sol, ep = self._solver(_abi.MODE_FIXED_SET, True)
-                o = sol.solve_host(x0[i], u0[i], xr, A, b0, db, term=term, Ts=Ts[i])
-                self.launches += 1; self.solves += len(i)
-                ok = o["status"] >= 0
-                xo, uo = o["x"], o["u"]
-                if (~ok).any():
-                    j = np.where(~ok)[0]
-                    sol8, _ = self._solver(_abi.MODE_FIXED_NOTERM, True)
-                    o8 = sol8.solve_host(x0[i[j]], u0[i[j]], xr[j], A[j], b0[j], db[j], Ts=Ts[i[j]])
-                    self.launches += 1; self.solves += len(j)
-                    xo[j] = o8["x"]; uo[j] = o8["u"]; ok[j] = o8["status"] >= 0
-                    mode_log[i[j], k] = _abi.MODE_FIXED_NOTERM
+                # rows of the boxes each scenario sees, in their order; scenarios grouped by how many that is
+                nseen = seen[i].sum(1)
+                xo = np.zeros((len(i), N + 1, 3)); uo = np.zeros((len(i), N, 2)); ok = np.zeros(len(i), bool)
+                for c in np.unique(nseen):
+                    g = np.where(nseen == c)[0]                                  # positions within i
+                    ig = i[g]
+                    pick = np.argsort(~seen[ig], axis=1, kind="stable")[:, :c]        # indices of the seen boxes, ascending
+                    rows = np.arange(len(ig))[:, None]
+                    Ad = A_d[ig][rows, pick].reshape(len(ig), 4 * c, 2); bd = b_d[ig][rows, pick].reshape(len(ig), 4 * c)
+                    dd = dyn[ig][rows, pick]                                          # (n, c, 7)
+                    sh = (Ts_opt[ig][:, None] * dd[:, :, 5])[:, :, None] * (
+                        A_d[ig][rows, pick][..., 0] * np.cos(dd[:, :, 2])[:, :, None] + A_d[ig][rows, pick][..., 1] * np.sin(dd[:, :, 2])[:, :, None])
+                    A = np.concatenate([np.tile(self.A_s[None], (len(ig), 1, 1)), Ad], 1)
+                    b0 = np.concatenate([np.tile(self.b_s[None], (len(ig), 1)), bd], 1)
+                    db = np.concatenate([np.zeros((len(ig), self.b_s.shape[0])), sh.reshape(len(ig), 4 * c)], 1)
+                    sol, ep = self._solver(_abi.MODE_FIXED_SET, int(c))
+                    o = sol.solve_host(x0[ig], u0[ig], xr[g], A, b0, db, term=term[g], Ts=Ts[ig])
+                    self.launches += 1; self.solves += len(ig)
+                    okg = o["status"] >= 0
+                    xg, ug = o["x"], o["u"]
+                    if (~okg).any():
+                        j = np.where(~okg)[0]
+                        sol8, _ = self._solver(_abi.MODE_FIXED_NOTERM, int(c))
+                        o8 = sol8.solve_host(x0[ig[j]], u0[ig[j]], xr[g[j]], A[j], b0[j], db[j], Ts=Ts[ig[j]])
+                        self.launches += 1; self.solves += len(j)
+                        xg[j] = o8["x"]; ug[j] = o8["u"]; okg[j] = o8["status"] >= 0
+                        mode_log[ig[j], k] = _abi.MODE_FIXED_NOTERM
+                    xo[g] = xg; uo[g] = ug; ok[g] = okg
                 mode_log[i[ok & (mode_log[i, k] < 0)], k] = _abi.MODE_FIXED_SET
                 xopt[i] = xo; uopt[i] = uo; feas[i] = ok
                 newT[i] = Ts[i]
@@ -423,6 +445,9 @@ class ClosedLoopDevice(ClosedLoopBatch):
         """``speculative``: solve without the terminal set beside the solve with it on every detected scenario (same
         results as the sequential fallback; pays off where the terminal-set solve mostly fails)."""
         super().__init__(setting, dyn, N=N, Q_free=Q_free, sense=sense, device=device, init=init, max_steps=max_steps)
+        if self.D != 1:
+            raise ValueError("the device-resident loop carries one moving box per scenario (obca_b200_loop_*); "
+                             "ClosedLoopBatch runs scenarios with several")
         self.speculative = bool(speculative)
         self._loop = None
         self._rule = None
@@ -470,7 +495,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
             self.close()
             self._create(rule)
         L = _lib.lib()
-        dyn = np.ascontiguousarray(self.dyn, float)
+        dyn = np.ascontiguousarray(self.dyn[:, 0, :], float)
         cs = np.ascontiguousarray(np.stack([np.cos(dyn[:, 2]), np.sin(dyn[:, 2])], 1))
         _lib.check(L.obca_b200_loop_reset(self._loop, dyn.ctypes.data, cs.ctypes.data, None))
         _lib.check(L.obca_b200_loop_run(self._loop, self.max_steps if steps is None else int(steps), None))
