@@ -26,7 +26,9 @@ class PackedOutputs:
     obj [cap] | (status, iters) int32 [cap] each, padded to whole words."""
     FIELDS = ("x", "u", "lam", "mu", "T", "obj")
 
-    def __init__(self, cap, N, rows, n_obs, device="cpu"):
+    def __init__(self, cap, N, rows, n_obs, device="cpu", buf=None):
+        """``buf``: a flat float64 tensor of ``words`` words to lay the views over instead of a fresh allocation (rank 0 of
+        a peer-to-peer gather lets its solver write straight into its row of the gathered buffer)"""
         import torch
         self.cap, self.N, self.rows, self.n_obs = int(cap), int(N), int(rows), int(n_obs)
         self.shapes = dict(x=(cap, N + 1, 3), u=(cap, N, 2), lam=(cap, N + 1, rows), mu=(cap, N + 1, 4 * n_obs),
@@ -40,7 +42,9 @@ class PackedOutputs:
         self.offsets["status"] = o; o += self.int_words
         self.offsets["iters"] = o; o += self.int_words
         self.words = o
-        self.buf = torch.zeros(self.words, dtype=torch.float64, device=device)
+        if buf is not None and (buf.numel() != self.words or buf.dtype != torch.float64 or not buf.is_contiguous()):
+            raise ValueError("buf must be a contiguous float64 tensor of %d words" % self.words)
+        self.buf = torch.zeros(self.words, dtype=torch.float64, device=device) if buf is None else buf
         self.views = self.views_of(self.buf)
 
     @property
@@ -118,7 +122,8 @@ class PeerGather:
         import torch
         self.side.wait_event(after_event)
         with torch.cuda.stream(self.side):
-            self.full[j, self.rank].copy_(packed.buf, non_blocking=True)
+            if packed.buf.data_ptr() != self.full[j, self.rank].data_ptr():      # (rank 0 may solve straight into its row)
+                self.full[j, self.rank].copy_(packed.buf, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.side)
         return done
