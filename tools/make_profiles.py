@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Developer tool: turn the artefacts of tools/gpu_round.sh (gpurun_out/) into the tracked summaries under profiles/.
+"""Developer tool: turn the artefacts of tools/gpu_profile.sh (gpurun_out/) into the tracked summaries under profiles/.
 
     python tools/make_profiles.py <round-tag>     e.g. r1
 """
@@ -54,7 +54,7 @@ def main():
     rt.update({"kernel": "obca_solve_kernel<4,128,3,20,4,16>", "workload": "cfg3 B=8192", "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": 7160 * 8192,
                "source": "ncu --set full --clock-control none, profiles/%s_ncu_metrics.md" % tag})
-    # fp64 instruction counts of the first-pass kernel (tools/gpu_r2h.sh: gpurun_out/fp64_counts_cfg3.csv) -> FLOP per iteration
+    # fp64 instruction counts of the first-pass kernel (tools/gpu_profile.sh: gpurun_out/fp64_counts_cfg3.csv) -> FLOP per iteration
     fc = os.path.join(OUT, "fp64_counts_cfg3.csv")
     if os.path.exists(fc):
         cnt = {}
