@@ -141,3 +141,18 @@ def test_closed_loop_shards_by_scenario(B):
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
         assert np.array_equal(one[k], ref[k], equal_nan=True), k
     assert got["solves"] == ref["solves"] and got["launches"] >= ref["launches"]
+
+
+def test_packed_outputs_over_an_existing_buffer():
+    """rank 0 of a peer-to-peer gather lays its result views over its row of the gathered buffer"""
+    import torch
+    ref = sharding.PackedOutputs(5, 4, 6, 2)
+    full = torch.zeros((2, 3, ref.words), dtype=torch.float64)
+    p = sharding.PackedOutputs(5, 4, 6, 2, buf=full[1, 0])
+    assert p.buf.data_ptr() == full[1, 0].data_ptr() and p.words == ref.words
+    p.views["x"][...] = 1.5; p.views["status"][...] = 7
+    assert float(full[1, 0].sum()) != 0.0 and float(full[0].abs().sum()) == 0.0 and float(full[1, 1:].abs().sum()) == 0.0
+    q = ref.views_of(full[1, 0])
+    assert torch.equal(q["x"], p.views["x"]) and int(q["status"][3]) == 7
+    with pytest.raises(ValueError):
+        sharding.PackedOutputs(5, 4, 6, 2, buf=torch.zeros(ref.words - 1, dtype=torch.float64))
