@@ -124,7 +124,11 @@ int64_t obca_b200_scratch_bytes(const obca_ctx* ctx);
  *   obstacles_shared != 0 => Bo = 1 (one scene broadcast to the batch), else Bo = B
  * outputs
  *   x [B,N+1,3]  u [B,N,2]  lam [B,N+1,rows]  mu [B,N+1,4*n_obs]  T [B] (time scale; 1 in fixed modes)
- *   obj [B]  status [B]  iters [B]                                                                     */
+ *   obj [B]  status [B]  iters [B]
+ * One solve per context at a time: a context owns the work counters, the list of failed instances, the work order and
+ * the watchdog checkpoints of its launches, so a second obca_b200_solve on the same context must be stream-ordered after
+ * the first (same stream, or an event); concurrent solves need one context each (obca_b200_solve_host does that
+ * internally with four launch slots for the chunks of a large batch).                                    */
 int  obca_b200_solve  (obca_ctx* ctx, int batch,
                        const double* x0, const double* u0, const double* xref, const double* uref,
                        const double* T_max, const double* term, const double* Ts_inst,
