@@ -497,6 +497,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
         L = _lib.lib()
         dyn = np.ascontiguousarray(self.dyn[:, 0, :], float)
         cs = np.ascontiguousarray(np.stack([np.cos(dyn[:, 2]), np.sin(dyn[:, 2])], 1))
+        self._launches0 = int(L.obca_b200_loop_launch_count(self._loop))      # (the library's count is cumulative)
         _lib.check(L.obca_b200_loop_reset(self._loop, dyn.ctypes.data, cs.ctypes.data, None))
         _lib.check(L.obca_b200_loop_run(self._loop, self.max_steps if steps is None else int(steps), None))
 
@@ -512,7 +513,7 @@ class ClosedLoopDevice(ClosedLoopBatch):
                                          mode.ctypes.data, x.ctypes.data, u.ctypes.data, ts.ctypes.data,
                                          solves.ctypes.data, None))
         goal = np.asarray(self.s.goalPose, float)
-        self.solves = int(solves.sum()); self.launches = int(L.obca_b200_loop_launch_count(self._loop))
+        self.solves = int(solves.sum()); self.launches = int(L.obca_b200_loop_launch_count(self._loop)) - getattr(self, "_launches0", 0)
         return dict(traj=traj, steps=steps.astype(int), failed=failed.astype(bool),
                     reached=((x[:, 0] - goal[0]) ** 2 + (x[:, 1] - goal[1]) ** 2 < 0.1), mode=mode.astype(int), x=x, u=u,
                     Ts_opt=ts, launches=self.launches, solves=self.solves, solves_by_mode=solves.tolist())
