@@ -69,6 +69,14 @@ def test_longest_first_order_changes_nothing_but_the_time():
         assert s.launches - n0 == 3
         for k in ("x", "u", "T", "obj", "lam", "mu", "status", "iters"):
             assert torch.equal(o[k], o2[k]), k
+    # a key that does not compare (NaN pose in one reference window) must not cost any instance its place in the list
+    xr = a["xref"].copy(); xr[7, 3, 2] = np.nan
+    o3 = s.solve(args[0], args[1], t(xr), *args[3:], T_max=t(a["T_max"]))
+    torch.cuda.synchronize()
+    keep = np.arange(B) != 7
+    assert int(o3["status"][7]) < 0
+    for k in ("x", "u", "T", "obj", "status", "iters"):
+        assert torch.equal(o[k][keep], o3[k][keep]), k
     s.close()
 
 

@@ -227,8 +227,12 @@ __global__ void __launch_bounds__(128) obca_order_score(const obca::KParams kp, 
   }
   if (k == 0) {
     const double hd = fabs(x0[2] - th);
-    score[b] = (float)(13.41 + 0.37 * smin - 0.17 * c05 + 2.29 * c0 + 0.17 * c15 - 0.38 * dsum + 1.12 * hd + 5.34 * dmax +
+    float sc = (float)(13.41 + 0.37 * smin - 0.17 * c05 + 2.29 * c0 + 0.17 * c15 - 0.38 * dsum + 1.12 * hd + 5.34 * dmax +
                        0.03 * x0[0] + 0.35 * fmin(Sk, 3.0));
+    // the ranks must be a permutation whatever the inputs hold (degenerate rows, NaN poses): a key that does not compare
+    // would leave its instance out of the work list
+    if (!(sc == sc)) sc = 0.0f;
+    score[b] = fminf(fmaxf(sc, -1.0e30f), 1.0e30f);
   }
 }
 // rank by counting (stable: ties in index order), the comparisons of one instance spread over gridDim.y blocks;
