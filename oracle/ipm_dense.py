@@ -171,7 +171,7 @@ def _solve_once(p: nlp.Problem, opts=None, model=None):
         E0, parts = err(gr, Jm, Jd, c, d, S, y, Z, 0.0)
         th = np.abs(c).sum() + np.abs(d - S).sum()
         if o["verbose"]:
-            print("it %3d f %.8e th %.2e E0 %.2e (%.1e %.1e %.1e) mu %.1e dw %.1e" % (it, f, th, E0, *parts, mu, dw_last))
+            print("it %3d f %.8e th %.2e E0 %.2e (%.1e %.1e %.1e) mu %.1e dw %.1e" % (it, f, th, E0, *parts[:3], mu, dw_last))
         hist.append((f, th, E0, mu))
         if E0 <= tol:
             status = 0
